@@ -1,0 +1,72 @@
+"""CPU: the NumPy oracle against golden vectors produced by the reference's own code (tests/golden/make_golden.py)
+and against the constants the reference hard-codes."""
+import numpy as np
+import pytest
+
+from oracle import cd_oracle as o
+from tests.helpers import (golden_cases, linear_params, load_golden, max_rel_err, nonlinear_params, scaled_err,
+                           settings_of)
+
+TOL = 1e-9  # north-star fp64 parity bound
+FIELDS = ["filtered_means", "filtered_covariances", "predicted_means", "predicted_covariances"]
+
+
+def test_reference_hardcoded_pushforward_constants():
+    """cdlgssm_test_filter_TRegular.py:61-62: Dopri5, dt0=0.01, Delta=1, F=-0.1, LQcL^T=0.125, float32."""
+    for dt, tol in ((np.float32, 4 * np.finfo(np.float32).eps), (np.float64, 1e-14)):
+        F, LQL = np.array([[[-0.1]]], dt), np.array([[[0.125]]], dt)
+        A, Q, _ = o.compute_pushforward(F, LQL, np.zeros(1, dt), np.ones(1, dt), o.SolverSettings())
+        ref_A = np.float32(0.9048373699188232421875) if dt is np.float32 else np.exp(-0.1)
+        ref_Q = np.float32(0.11329327523708343505859375) if dt is np.float32 else 0.125 * (1 - np.exp(-0.2)) / 0.2
+        assert abs(float(A[0, 0, 0]) - float(ref_A)) <= tol * float(ref_A)
+        assert abs(float(Q[0, 0, 0]) - float(ref_Q)) <= tol * float(ref_Q)
+    assert o.substep_counts(np.zeros(1), np.ones(1), 0.01)[0] == 100
+    g = load_golden("pushforward_constants")
+    assert abs(g["A_float64"].ravel()[0] - np.exp(-0.1)) < 1e-14
+
+
+@pytest.mark.parametrize("name", golden_cases("kf_"))
+def test_linear_filter_and_smoothers(name):
+    g = load_golden(name)
+    p = linear_params(g)
+    u = g.get("u")
+    for stype in (1, 2):
+        if stype == 2 and "s2_smoothed_means" not in g:
+            continue
+        r = o.cdlgssm_smoother(p, g["y"], g["t"], float(g["dt_final"]), settings_of(g), u, smoother_type=stype)
+        if stype == 1:
+            assert max_rel_err(r["marginal_loglik"], g["filt_marginal_loglik"]) < TOL
+            for f in FIELDS:
+                assert scaled_err(r[f], g["filt_" + f]) < TOL, f
+            assert scaled_err(r["smoothed_cross_covariances"], g["s1_smoothed_cross_covariances"]) < TOL
+        else:
+            assert np.isnan(r["smoothed_cross_covariances"]).all() or r["smoothed_cross_covariances"].size == 0
+        for f in ("smoothed_means", "smoothed_covariances"):
+            # the RTS recursion amplifies rounding by cond(P_pred); 1e-8 on the scaled error is the honest bound
+            assert scaled_err(r[f], g[f"s{stype}_" + f]) < 1e-8, (stype, f)
+
+
+@pytest.mark.parametrize("name", golden_cases("ekf_"))
+def test_ekf_and_eks(name):
+    g = load_golden(name)
+    p = nonlinear_params(g)
+    r = o.extended_kalman_filter(p, g["y"], g["t"], float(g["dt_final"]), str(g["state_order"]), settings_of(g),
+                                 int(g["num_iter"]), float(g["cov_rescaling"]))
+    assert max_rel_err(r["marginal_loglik"], g["filt_marginal_loglik"]) < TOL
+    assert max_rel_err(r["marginal_loglik_cumulative"], g["filt_marginal_loglik_cumulative"]) < TOL
+    for f in FIELDS:
+        assert scaled_err(r[f], g["filt_" + f]) < TOL, f
+    if "smooth_smoothed_means" in g:
+        s = o.extended_kalman_smoother(p, g["y"], g["t"], float(g["dt_final"]), str(g["state_order"]), settings_of(g))
+        for f in ("smoothed_means", "smoothed_covariances"):
+            assert scaled_err(s[f], g["smooth_" + f]) < 1e-8, f
+
+
+@pytest.mark.parametrize("name", golden_cases("ukf_"))
+def test_ukf(name):
+    g = load_golden(name)
+    p = nonlinear_params(g)
+    r = o.unscented_kalman_filter(p, g["y"], g["t"], float(g["dt_final"]), settings=settings_of(g))
+    assert max_rel_err(r["marginal_loglik"], g["filt_marginal_loglik"]) < TOL
+    for f in FIELDS:
+        assert scaled_err(r[f], g["filt_" + f]) < TOL, f
