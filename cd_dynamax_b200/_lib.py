@@ -1,0 +1,94 @@
+"""ctypes binding of libcdk.so (include/cdk.h). No CPU fallback: importing fails loudly when the library is missing."""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "lib", "libcdk.so")
+
+NUM_IN, NUM_OUT = 16, 11
+(IN_Y, IN_T, IN_U, IN_M0, IN_P0, IN_F, IN_B, IN_BU, IN_L, IN_QC, IN_H, IN_D, IN_DU, IN_R, IN_FM, IN_FP) = range(16)
+(OUT_LL, OUT_FM, OUT_FP, OUT_PM, OUT_PP, OUT_LLCUM, OUT_SM, OUT_SP, OUT_SCROSS, OUT_STATUS, OUT_SCRATCH) = range(11)
+SOLVERS = {"euler": 0, "heun": 1, "midpoint": 2, "ralston": 3, "bosh3": 4, "rk4": 5, "dopri5": 6}
+DRIFT_LINEAR, DRIFT_LORENZ63, DRIFT_LORENZ96, DRIFT_QUADRATIC = 0, 1, 2, 3
+ORDERS = {"zeroth": 0, "first": 1, "second": 2}
+ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
+                                                  ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
+OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
+                 "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_launch_count", "cdk_version",
+                 "cdk_last_error"]
+
+
+class CdkDesc(ctypes.Structure):
+    """Mirror of `struct cdk_desc` (include/cdk.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_int32), ("K", ctypes.c_int32), ("N", ctypes.c_int64), ("n", ctypes.c_int32),
+        ("m", ctypes.c_int32), ("d_u", ctypes.c_int32), ("E", ctypes.c_int32), ("solver", ctypes.c_int32),
+        ("max_steps", ctypes.c_int32), ("dt0", ctypes.c_double), ("dt_final", ctypes.c_double),
+        ("state_order", ctypes.c_int32), ("num_iter", ctypes.c_int32), ("smoother_type", ctypes.c_int32),
+        ("drift_id", ctypes.c_int32), ("emission_id", ctypes.c_int32), ("n_theta", ctypes.c_int32),
+        ("batched_mask", ctypes.c_uint32), ("perturb_measurements", ctypes.c_int32),
+        ("cov_rescaling", ctypes.c_double), ("alpha", ctypes.c_double), ("beta", ctypes.c_double),
+        ("kappa", ctypes.c_double), ("rng_seed", ctypes.c_uint64), ("rng_offset", ctypes.c_uint64),
+        ("reserved", ctypes.c_int32 * 4),
+    ]
+
+
+class CdkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libcdk.so once. Raises (never falls back) if the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first (python -m cd_dynamax_b200.build). "
+            "cd_dynamax_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    for name in ENTRY_POINTS:
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.POINTER(CdkDesc), pp, pp, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    L.cdk_desc_init.argtypes = [ctypes.POINTER(CdkDesc)]
+    L.cdk_desc_init.restype = None
+    L.cdk_scratch_bytes.argtypes = [ctypes.POINTER(CdkDesc), ctypes.c_char_p]
+    L.cdk_scratch_bytes.restype = ctypes.c_size_t
+    for name in ("cdk_ll_sum_f64", "cdk_ll_sum_f32"):
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    L.cdk_ll_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.cdk_ll_allreduce.restype = ctypes.c_int
+    for name in ("cdk_fma_probe_f64", "cdk_fma_probe_f32"):
+        fn = getattr(L, name)
+        fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        fn.restype = ctypes.c_int
+    L.cdk_launch_count.restype = ctypes.c_int64
+    L.cdk_version.restype = ctypes.c_int
+    L.cdk_last_error.restype = ctypes.c_char_p
+    assert ctypes.sizeof(CdkDesc) == _c_sizeof_desc(L), "cdk_desc layout mismatch between Python and C"
+    _lib = L
+    return L
+
+
+def _c_sizeof_desc(L):
+    d = CdkDesc()
+    L.cdk_desc_init(ctypes.byref(d))
+    return d.struct_size
+
+
+def new_desc():
+    d = CdkDesc()
+    lib().cdk_desc_init(ctypes.byref(d))
+    return d
+
+
+def check(rc, what):
+    if rc != 0:
+        raise CdkError(f"{what} failed with code {rc}: {lib().cdk_last_error().decode()}")

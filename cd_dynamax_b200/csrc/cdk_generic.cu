@@ -1,0 +1,877 @@
+// cdk_generic.cu -- shared-memory kernels for arbitrary (runtime) state / emission dimensions: ONE CTA PER TRAJECTORY.
+//
+// Covers, for n <= CDK_MAX_N, m <= CDK_MAX_M and every solver in the registry:
+//   ALGO_KF_FILTER   cdlgssm_filter            cd_linear/inference.py:555-632 (+ compute_pushforward :105-144,
+//                                               _predict :185-206, _condition_on :209-259)
+//   ALGO_KF_SMOOTH   cdlgssm_smoother scan     cd_linear/inference.py:746-794 (+ _smooth :636-690)
+//   ALGO_EKF_FILTER  extended_kalman_filter    cd_nonlinear/inference_ekf.py:202-326 (all three state orders)
+//   ALGO_EKF_SMOOTH  extended_kalman_smoother  cd_nonlinear/inference_ekf.py:450-539 (+ _smooth :363-448)
+//   ALGO_UKF_FILTER  unscented_kalman_filter   cd_nonlinear/inference_ukf.py:206-308
+// The whole per-trajectory state (moments, RK stage vectors, Jacobian, Cholesky factors) lives in shared memory
+// (up to ~200 KB of the 227 KB a B200 CTA may use); the threads of the CTA split every small matrix product by
+// output element.  Matrices are stored with an odd leading dimension so that row-strided accesses (Cholesky,
+// triangular solves, A B^T products) are bank-conflict free for 64-bit words.
+#include "cdk_common.cuh"
+
+namespace cdk {
+namespace {
+
+#define FOR_T(i, cnt) for (int i = threadIdx.x; i < (cnt); i += blockDim.x)
+
+__host__ __device__ inline int ldp(int c) { return c | 1; }
+
+enum { ODE_PUSH = 0, ODE_EKF = 1, ODE_MEAN = 2, ODE_BACK = 3, ODE_UKF = 4 };
+
+template <typename T>
+struct GArgs {
+  KArgs<T> k;
+  RtTab tab;
+  int nslots;  // RK stage buffers kept in shared memory (1 for "chain" tableaux, S otherwise)
+  int algo;
+};
+
+// shared-memory layout, computed identically on host (size) and device (offsets); units = elements of T
+struct Lay {
+  int n, m, du, ldn, ldm, nn, S, nth, mpoff;
+  int TH, LQL, H, R, DV, BV, BU, DU, YV, UV, MU, P, ODEY, YS, ACC, KS, J, W1, W2, W3, SM, SL, RV, MF, PF, C0, total;
+  __host__ __device__ Lay(const cdk_desc& d, int algo, int nslots) {
+    n = d.n; m = d.m; du = d.d_u; ldn = ldp(n); ldm = ldp(m); nn = n * ldn;
+    const bool lin = algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH;
+    nth = lin ? nn : (d.n_theta > nn ? d.n_theta : nn);
+    const int mx = n > m ? n : m;
+    const int wsz = mx * ldp(mx);
+    mpoff = (n + 1) & ~1;           // offset of P behind MU inside the (m, P) ODE state
+    const int S_mp = mpoff + nn;
+    S = lin ? (2 * nn > S_mp ? 2 * nn : S_mp) : S_mp;  // kf smoother type 2 integrates (m, P) as well
+    int o = 0;
+    auto take = [&](int cnt) { int r = o; o += (cnt + 1) & ~1; return r; };
+    TH = take(nth); LQL = take(nn); H = take(m * ldn); R = take(m * ldm); DV = take(m); BV = take(n);
+    BU = take(n * du); DU = take(m * du); YV = take(m); UV = take(du);
+    MU = take(n); P = take(nn);  // contiguous: [MU | P] is the (m, P) ODE state (n is padded to even by take())
+    ODEY = take(lin ? 2 * nn : 0);
+    YS = take(S); ACC = take(S); KS = take(nslots * S);
+    J = take(nn); W1 = take(wsz); W2 = take(wsz); W3 = take(wsz);
+    SM = take(m * ldm); SL = take(m * ldm); RV = take(2 * m);
+    MF = take(n); PF = take(nn); C0 = take(n);
+    total = o;
+  }
+};
+
+// ---- drift registry, element-wise, on an arbitrary accessor x(j) ---------------------------------------------------
+template <typename T, class XF>
+__device__ __forceinline__ T drift_f(int id, const T* th, int n, int i, XF x) {
+  switch (id) {
+    case CDK_DRIFT_LINEAR: {
+      T s = T(0);
+      for (int k = 0; k < n; ++k) s += th[i * n + k] * x(k);
+      return s + th[n * n + i];
+    }
+    case CDK_DRIFT_LORENZ63:
+      if (i == 0) return th[0] * (x(1) - x(0));
+      if (i == 1) return x(0) * (th[1] - x(2)) - x(1);
+      return x(0) * x(1) - th[2] * x(2);
+    case CDK_DRIFT_LORENZ96: {
+      const int ip = i + 1 == n ? 0 : i + 1, im1 = i == 0 ? n - 1 : i - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
+      return (x(ip) - x(im2)) * x(im1) - x(i) + th[0];
+    }
+    default: {  // quadratic
+      const T* B = th + n;
+      const T* C = th + n + n * n;
+      T s = th[i];
+      for (int j = 0; j < n; ++j) {
+        const T xj = x(j);
+        T c = B[i * n + j];
+        for (int k = 0; k < n; ++k) c += C[(i * n + j) * n + k] * x(k);
+        s += c * xj;
+      }
+      return s;
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T drift_jac(int id, const T* th, int n, int i, int j, const T* x) {
+  switch (id) {
+    case CDK_DRIFT_LINEAR: return th[i * n + j];
+    case CDK_DRIFT_LORENZ63: {
+      if (i == 0) return j == 0 ? -th[0] : (j == 1 ? th[0] : T(0));
+      if (i == 1) return j == 0 ? th[1] - x[2] : (j == 1 ? T(-1) : -x[0]);
+      return j == 0 ? x[1] : (j == 1 ? x[0] : -th[2]);
+    }
+    case CDK_DRIFT_LORENZ96: {
+      const int ip = i + 1 == n ? 0 : i + 1, im1 = i == 0 ? n - 1 : i - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
+      T v = T(0);
+      if (j == ip) v += x[im1];
+      if (j == im2) v -= x[im1];
+      if (j == im1) v += x[ip] - x[im2];
+      if (j == i) v -= T(1);
+      return v;
+    }
+    default: {
+      const T* B = th + n;
+      const T* C = th + n + n * n;
+      T s = B[i * n + j];
+      for (int k = 0; k < n; ++k) s += (C[(i * n + j) * n + k] + C[(i * n + k) * n + j]) * x[k];
+      return s;
+    }
+  }
+}
+
+// g_k = sum_i d2 f_i / dx_i dx_k: the only Hessian contraction the reference's 'second' order uses
+// (0.5*jnp.trace(H_t @ P) traces axes (0,1): inference_ekf.py:111-114).  Zero unless quadratic.
+template <typename T>
+__device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
+  if (id != CDK_DRIFT_QUADRATIC) return T(0);
+  const T* C = th + n + n * n;
+  T s = T(0);
+  for (int i = 0; i < n; ++i) s += C[(i * n + i) * n + k] + C[(i * n + k) * n + i];
+  return s;
+}
+
+// ---- block-cooperative dense helpers (all end WITHOUT a barrier unless noted) ---------------------------------------
+// L = chol(A) (lower; reads the lower triangle of A; A != L). Upper triangle of L zeroed. Ends with a barrier.
+template <typename T>
+__device__ void chol(const T* A, T* L, int n, int ld, T boost) {
+  FOR_T(e, n * ld) L[e] = T(0);
+  __syncthreads();
+  for (int j = 0; j < n; ++j) {
+    for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
+      T sjj = A[j * ld + j] + boost;
+      for (int k = 0; k < j; ++k) sjj -= L[j * ld + k] * L[j * ld + k];
+      const T dj = sqrt(sjj);
+      if (i == j) {
+        L[j * ld + j] = dj;
+      } else {
+        T v = A[i * ld + j];
+        for (int k = 0; k < j; ++k) v -= L[i * ld + k] * L[j * ld + k];
+        L[i * ld + j] = v / dj;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Solve (L L^T) X = B in place, B is [n x c] with leading dimension ldb; one thread per column. Ends with a barrier.
+template <typename T>
+__device__ void chol_solve(const T* L, int n, int ld, T* B, int c, int ldb) {
+  FOR_T(col, c) {
+    for (int i = 0; i < n; ++i) {
+      T v = B[i * ldb + col];
+      for (int k = 0; k < i; ++k) v -= L[i * ld + k] * B[k * ldb + col];
+      B[i * ldb + col] = v / L[i * ld + i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      T v = B[i * ldb + col];
+      for (int k = i + 1; k < n; ++k) v -= L[k * ld + i] * B[k * ldb + col];
+      B[i * ldb + col] = v / L[i * ld + i];
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+struct Ctx {
+  const GArgs<T>& g;
+  Lay L;
+  T* sh;
+  __device__ Ctx(const GArgs<T>& g_, T* sh_) : g(g_), L(g_.k.d, g_.algo, g_.nslots), sh(sh_) {}
+  __device__ T* p(int off) const { return sh + off; }
+};
+
+// k = dt * rhs(kind, ys).  All arrays in shared memory.  Ends with a barrier.
+template <typename T>
+__device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
+  const Lay& L = c.L;
+  const int n = L.n, ld = L.ldn;
+  const cdk_desc& d = c.g.k.d;
+  const T* lql = c.p(L.LQL);
+  if (kind == ODE_PUSH) {
+    // dA = F A ; dQ = F Q + Q F^T + L Qc L^T   (cd_linear/inference.py:114-131)
+    const T* F = c.p(L.TH);
+    const T* A = ys;
+    const T* Q = ys + L.nn;
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      T sa = T(0), sq = T(0);
+      for (int q = 0; q < n; ++q) {
+        const T f = F[i * ld + q];
+        sa += f * A[q * ld + j];
+        sq += f * Q[q * ld + j] + Q[i * ld + q] * F[j * ld + q];
+      }
+      k[i * ld + j] = dt * sa;
+      k[L.nn + i * ld + j] = dt * (sq + lql[i * ld + j]);
+    }
+    __syncthreads();
+    return;
+  }
+  if (kind == ODE_MEAN) {
+    const T* th = c.p(L.TH);
+    FOR_T(i, n) k[i] = dt * drift_f<T>(d.drift_id, th, n, i, [&](int j) { return ys[j]; });
+    __syncthreads();
+    return;
+  }
+  const T* mm = ys;
+  const T* P = ys + L.P - L.MU;  // same relative offset as [MU | P]
+  T* km = k;
+  T* kP = k + (L.P - L.MU);
+  if (kind == ODE_EKF) {
+    // inference_ekf.py:76-123
+    const T* th = c.p(L.TH);
+    T* J = c.p(L.J);
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      J[i * ld + j] = drift_jac<T>(d.drift_id, th, n, i, j, mm);
+    }
+    __syncthreads();
+    const bool second = d.state_order == CDK_ORDER_SECOND && d.drift_id == CDK_DRIFT_QUADRATIC;
+    FOR_T(i, n) {
+      T f = drift_f<T>(d.drift_id, th, n, i, [&](int j) { return mm[j]; });
+      if (second) {
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += drift_graddiv<T>(d.drift_id, th, n, q) * P[q * ld + i];
+        f += T(0.5) * s;
+      }
+      km[i] = dt * f;
+    }
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      T s = T(0);
+      for (int q = 0; q < n; ++q) s += J[i * ld + q] * P[q * ld + j] + P[i * ld + q] * J[j * ld + q];
+      kP[i * ld + j] = dt * (s + lql[i * ld + j]);
+    }
+    __syncthreads();
+    return;
+  }
+  if (kind == ODE_BACK) {
+    // reverse-time smoothing ODE (cd_linear/inference.py:664-684, inference_ekf.py:399-441; reverse_rhs
+    // diffrax_utils.py:13-25): d/ds (m_s, P_s) = -( c0 + G (m_s - m_f),  G P_s + P_s G^T - L Qc L^T )
+    const T* G = c.p(L.J);
+    const T* mf = c.p(L.MF);
+    const T* c0 = c.p(L.C0);
+    FOR_T(i, n) {
+      T s = c0[i];
+      for (int q = 0; q < n; ++q) s += G[i * ld + q] * (mm[q] - mf[q]);
+      km[i] = -dt * s;
+    }
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      T s = T(0);
+      for (int q = 0; q < n; ++q) s += G[i * ld + q] * P[q * ld + j] + P[i * ld + q] * G[j * ld + q];
+      kP[i * ld + j] = -dt * (s - lql[i * ld + j]);
+    }
+    __syncthreads();
+    return;
+  }
+  // ODE_UKF: Sarkka eq. 3.183 (inference_ukf.py:130-152).  With X = [m, m + c L_i, m - c L_i], Lc = chol(P):
+  //   dm = w0 f(m) + w sum_i (f(X_i^+) + f(X_i^-)),      w = 1 / (2 (n + lambda)),  c = sqrt(n + lambda)
+  //   f_X^T W X = sum_k w_c[k] (f_k - fbar)(x_k - xbar)^T = w c sum_i (f_i^+ - f_i^-) L_i^T     (xbar = m)
+  {
+    const T* th = c.p(L.TH);
+    T* Lc = c.p(L.W1);
+    T* dF = c.p(L.W2);  // dF[j*ld + i] = f_j(X_i^+) - f_j(X_i^-)
+    T* sF = c.p(L.W3);  // sF[j*ld + i] = f_j(X_i^+) + f_j(X_i^-)
+    chol<T>(P, Lc, n, ld, T(0));
+    const T lam = T(d.alpha * d.alpha * (d.n + d.kappa) - d.n);
+    const T cs = sqrt(T(d.n) + lam);
+    const T w = T(1) / (T(2) * (T(d.n) + lam));
+    const T w0 = lam / (T(d.n) + lam);
+    FOR_T(e, n * n) {
+      const int j = e / n, i = e - j * n;
+      const T fp = drift_f<T>(d.drift_id, th, n, j, [&](int q) { return mm[q] + cs * Lc[q * ld + i]; });
+      const T fm = drift_f<T>(d.drift_id, th, n, j, [&](int q) { return mm[q] - cs * Lc[q * ld + i]; });
+      dF[j * ld + i] = fp - fm;
+      sF[j * ld + i] = fp + fm;
+    }
+    __syncthreads();
+    FOR_T(j, n) {
+      T s = T(0);
+      for (int i = 0; i < n; ++i) s += sF[j * ld + i];
+      const T f0 = drift_f<T>(d.drift_id, th, n, j, [&](int q) { return mm[q]; });
+      km[j] = dt * (w0 * f0 + w * s);
+    }
+    const T wc = w * cs;
+    FOR_T(e, n * n) {
+      const int a = e / n, b = e - a * n;
+      T s = T(0);
+      for (int i = 0; i < n; ++i) s += dF[a * ld + i] * Lc[b * ld + i] + dF[b * ld + i] * Lc[a * ld + i];
+      kP[a * ld + b] = dt * (wc * s + lql[a * ld + b]);
+    }
+    __syncthreads();
+  }
+}
+
+// Integrate y (length S, shared memory, in place) from t0 to t1 with the fixed-step explicit RK in g.tab.
+// Restates diffrax diffeqsolve + ConstantStepSize (diffrax_utils.py:150-163).  Returns true when max_steps was hit.
+template <typename T>
+__device__ bool ode_solve(const Ctx<T>& c, int kind, T* y, int S, T t0, T t1, T dt0, int max_steps) {
+  const RtTab& tab = c.g.tab;
+  const int nslots = c.g.nslots;
+  T* ys = c.p(c.L.YS);
+  T* acc = c.p(c.L.ACC);
+  T* ks = c.p(c.L.KS);
+  const T tol = clip_tol<T>();
+  T tprev = t0;
+  T tnext = fmin(t0 + dt0, t1);
+  int nsteps = 0;
+  while (tprev < t1) {
+    if (nsteps >= max_steps) {
+      FOR_T(e, S) y[e] = T(NAN);
+      __syncthreads();
+      return true;
+    }
+    const T dt = tnext - tprev;
+    for (int i = 0; i < tab.S; ++i) {
+      FOR_T(e, S) {
+        T v = y[e];
+        if (nslots == 1) {
+          if (i > 0 && tab.a[i][i - 1] != 0.0) v += T(tab.a[i][i - 1]) * ks[e];
+        } else {
+          for (int j = 0; j < i; ++j)
+            if (tab.a[i][j] != 0.0) v += T(tab.a[i][j]) * ks[j * S + e];
+        }
+        ys[e] = v;
+        if (i == 0) acc[e] = v;
+      }
+      __syncthreads();
+      T* ki = ks + (nslots == 1 ? 0 : i * S);
+      ode_rhs<T>(c, kind, ys, ki, dt);
+      if (tab.b[i] != 0.0) {
+        FOR_T(e, S) acc[e] += T(tab.b[i]) * ki[e];
+      }
+      __syncthreads();
+    }
+    FOR_T(e, S) y[e] = acc[e];
+    __syncthreads();
+    ++nsteps;
+    tprev = tnext;
+    const T cand = tprev + dt0;
+    tnext = cand > t1 - tol ? t1 : cand;
+  }
+  return false;
+}
+
+// load a [r x c] row-major global matrix into shared memory with leading dimension ld
+template <typename T>
+__device__ void load_mat(T* dst, const T* src, int r, int c, int ld) {
+  FOR_T(e, r * c) {
+    const int i = e / c, j = e - i * c;
+    dst[i * ld + j] = src[e];
+  }
+}
+template <typename T>
+__device__ void store_mat(T* dst, const T* src, int r, int c, int ld) {
+  FOR_T(e, r * c) {
+    const int i = e / c, j = e - i * c;
+    dst[e] = src[i * ld + j];
+  }
+}
+
+template <typename T>
+__device__ void load_model(const Ctx<T>& c, long long traj, bool linear) {
+  const Lay& L = c.L;
+  const KArgs<T>& a = c.g.k;
+  const int n = L.n, m = L.m, du = L.du;
+  auto src = [&](int slot) { return a.in[slot] + traj * a.in_stride[slot]; };
+  if (linear) {
+    load_mat<T>(c.p(L.TH), src(CDK_IN_F), n, n, L.ldn);
+    FOR_T(i, n) c.p(L.BV)[i] = src(CDK_IN_B)[i];
+    if (du > 0) {
+      FOR_T(i, n * du) c.p(L.BU)[i] = src(CDK_IN_BU)[i];
+      FOR_T(i, m * du) c.p(L.DU)[i] = src(CDK_IN_DU)[i];
+    }
+  } else {
+    FOR_T(i, a.d.n_theta) c.p(L.TH)[i] = src(CDK_IN_F)[i];
+  }
+  load_mat<T>(c.p(L.H), src(CDK_IN_H), m, n, L.ldn);
+  load_mat<T>(c.p(L.R), src(CDK_IN_R), m, m, L.ldm);
+  FOR_T(i, m) c.p(L.DV)[i] = src(CDK_IN_D)[i];
+  // L Qc L^T via W1 = L, W2 = Qc, W3 = L Qc
+  T* Lm = c.p(L.W1);
+  T* Qc = c.p(L.W2);
+  T* LQ = c.p(L.W3);
+  load_mat<T>(Lm, src(CDK_IN_L), n, n, L.ldn);
+  load_mat<T>(Qc, src(CDK_IN_QC), n, n, L.ldn);
+  __syncthreads();
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    T s = T(0);
+    for (int q = 0; q < n; ++q) s += Lm[i * L.ldn + q] * Qc[q * L.ldn + j];
+    LQ[i * L.ldn + j] = s;
+  }
+  __syncthreads();
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    T s = T(0);
+    for (int q = 0; q < n; ++q) s += LQ[i * L.ldn + q] * Lm[j * L.ldn + q];
+    c.p(L.LQL)[i * L.ldn + j] = s;
+  }
+  __syncthreads();
+}
+
+// Measurement update shared by KF / EKF / UKF.  On entry MU, P hold the prediction; on exit the filtered moments.
+// Returns the log-likelihood increment (same value in every thread).
+template <typename T>
+__device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
+  const Lay& L = c.L;
+  const cdk_desc& d = c.g.k.d;
+  const int n = L.n, m = L.m, ldn = L.ldn, ldm = L.ldm;
+  T* mu = c.p(L.MU);
+  T* P = c.p(L.P);
+  const T* H = c.p(L.H);
+  const T* R = c.p(L.R);
+  const T* dv = c.p(L.DV);
+  const T* yv = c.p(L.YV);
+  T* HP = c.p(L.W1);  // [m x n]
+  T* Kt = c.p(L.W2);  // [m x n]  (S + boost)^-1 H P
+  T* SK = c.p(L.W3);  // [m x n]  S Kt
+  T* Sm = c.p(L.SM);
+  T* Sl = c.p(L.SL);
+  T* rv = c.p(L.RV);
+  T* zv = rv + m;
+  __shared__ T ll_sh;
+  const bool ukf = algo == ALGO_UKF_FILTER;
+  for (int it = 0; it < num_iter; ++it) {
+    if (!ukf) {
+      FOR_T(e, m * n) {
+        const int a = e / n, j = e - a * n;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += H[a * ldn + q] * P[q * ldn + j];
+        HP[a * ldn + j] = s;
+      }
+      __syncthreads();
+      FOR_T(e, m * m) {
+        const int a = e / m, b = e - a * m;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += HP[a * ldn + q] * H[b * ldn + q];
+        Sm[a * ldm + b] = R[a * ldm + b] + s;
+      }
+    } else {
+      // inference_ukf.py:162-203 with h(x) = H x + d:  Y_i^+- - yhat = +-c H L_i, X_i^+- - m = +-c L_i
+      //   S = 2 w c^2 (H Lc)(H Lc)^T + R,  cross^T = 2 w c^2 (H Lc) Lc^T
+      T* Lc = c.p(L.J);
+      chol<T>(P, Lc, n, ldn, T(0));
+      T* HL = SK;
+      FOR_T(e, m * n) {
+        const int a = e / n, j = e - a * n;
+        T s = T(0);
+        for (int q = j; q < n; ++q) s += H[a * ldn + q] * Lc[q * ldn + j];
+        HL[a * ldn + j] = s;
+      }
+      __syncthreads();
+      const T lam = T(d.alpha * d.alpha * (d.n + d.kappa) - d.n);
+      const T c2 = T(2) * (T(1) / (T(2) * (T(d.n) + lam))) * (T(d.n) + lam);
+      FOR_T(e, m * m) {
+        const int a = e / m, b = e - a * m;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += HL[a * ldn + q] * HL[b * ldn + q];
+        Sm[a * ldm + b] = c2 * s + R[a * ldm + b];
+      }
+      FOR_T(e, m * n) {
+        const int a = e / n, j = e - a * n;
+        T s = T(0);
+        for (int q = 0; q <= j; ++q) s += HL[a * ldn + q] * Lc[j * ldn + q];
+        HP[a * ldn + j] = c2 * s;  // cross^T
+      }
+    }
+    FOR_T(a, m) {
+      T s = dv[a];
+      for (int q = 0; q < n; ++q) s += H[a * ldn + q] * mu[q];
+      rv[a] = yv[a] - s;  // yv already has D u subtracted (linear model)
+    }
+    __syncthreads();
+    if (it == 0) {
+      // MVN(.).log_prob(y): un-boosted Cholesky (TFP)
+      chol<T>(Sm, Sl, m, ldm, T(0));
+      if (threadIdx.x == 0) {
+        T quad = T(0), logdet = T(0);
+        for (int i = 0; i < m; ++i) {
+          T v = rv[i];
+          for (int q = 0; q < i; ++q) v -= Sl[i * ldm + q] * zv[q];
+          v /= Sl[i * ldm + i];
+          zv[i] = v;
+          quad += v * v;
+          logdet += log(Sl[i * ldm + i]);
+        }
+        ll_sh = T(-0.5) * quad - logdet - T(m) * half_log_2pi<T>();
+      }
+      __syncthreads();
+    }
+    // psd_solve(S, .): chol(sym(S) + 1e-9 I); symmetrise into SK (scratch, [m x ldm] fits), then factor into Sl
+    T* Sb = SK;
+    FOR_T(e, m * m) {
+      const int a = e / m, b = e - a * m;
+      Sb[a * ldm + b] = T(0.5) * (Sm[a * ldm + b] + Sm[b * ldm + a]);
+    }
+    __syncthreads();
+    chol<T>(Sb, Sl, m, ldm, T(1e-9));
+    FOR_T(e, m * n) {
+      const int a = e / n, j = e - a * n;
+      Kt[a * ldn + j] = HP[a * ldn + j];
+    }
+    __syncthreads();
+    chol_solve<T>(Sl, m, ldm, Kt, n, ldn);
+    FOR_T(e, m * n) {
+      const int a = e / n, j = e - a * n;
+      T s = T(0);
+      for (int b = 0; b < m; ++b) s += Sm[a * ldm + b] * Kt[b * ldn + j];
+      SK[a * ldn + j] = s;
+    }
+    __syncthreads();
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      T s = T(0);
+      for (int a = 0; a < m; ++a) s += Kt[a * ldn + i] * SK[a * ldn + j];
+      P[i * ldn + j] -= s;
+    }
+    FOR_T(i, n) {
+      T s = T(0);
+      for (int a = 0; a < m; ++a) s += Kt[a * ldn + i] * rv[a];
+      mu[i] += s;
+    }
+    __syncthreads();
+  }
+  if (!ukf) {
+    // symmetrize (cd_linear/inference.py:259, inference_ekf.py:199); the UKF does not (inference_ukf.py:202)
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      if (i < j) {
+        const T v = T(0.5) * (P[i * ldn + j] + P[j * ldn + i]);
+        P[i * ldn + j] = v;
+        P[j * ldn + i] = v;
+      }
+    }
+    __syncthreads();
+  }
+  return ll_sh;
+}
+
+template <typename T>
+__global__ void generic_filter_kernel(const GArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx<T> c(g, reinterpret_cast<T*>(smem_raw));
+  const Lay& L = c.L;
+  const KArgs<T>& a = g.k;
+  const cdk_desc& d = a.d;
+  const int n = L.n, m = L.m, du = L.du, ldn = L.ldn, K = d.K;
+  const int algo = g.algo;
+  const bool linear = algo == ALGO_KF_FILTER;
+  const long long traj = blockIdx.x;
+  FOR_T(e, L.total) c.sh[e] = T(0);
+  __syncthreads();
+  load_model<T>(c, traj, linear);
+  T* mu = c.p(L.MU);
+  T* P = c.p(L.P);
+  FOR_T(i, n) mu[i] = (a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0])[i];
+  load_mat<T>(P, a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0], n, n, ldn);
+  __syncthreads();
+  const T* Y = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
+  const T* Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  const T* U = du > 0 ? a.in[CDK_IN_U] + traj * a.in_stride[CDK_IN_U] : nullptr;
+  T* FM = static_cast<T*>(a.out[CDK_OUT_FM]);
+  T* FP = static_cast<T*>(a.out[CDK_OUT_FP]);
+  T* PM = static_cast<T*>(a.out[CDK_OUT_PM]);
+  T* PP = static_cast<T*>(a.out[CDK_OUT_PP]);
+  T* LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
+  const long long row0 = traj * (long long)K;
+  const T dt0 = T(d.dt0);
+  T ll = T(0);
+  int status = 0;
+  T* yv = c.p(L.YV);
+  T* uv = c.p(L.UV);
+  for (int k = 0; k < K; ++k) {
+    FOR_T(i, du) uv[i] = U[(long long)k * du + i];
+    __syncthreads();
+    FOR_T(i, m) {
+      T v = Y[(long long)k * m + i];
+      if (du > 0) {  // y - D u (cd_linear/inference.py:258, :613)
+        const T* DU = c.p(L.DU);
+        for (int q = 0; q < du; ++q) v -= DU[i * du + q] * uv[q];
+      }
+      yv[i] = v;
+    }
+    __syncthreads();
+    ll += condition_on<T>(c, algo, algo == ALGO_EKF_FILTER ? d.num_iter : 1);
+    if (FM) FOR_T(i, n) FM[(row0 + k) * n + i] = mu[i];
+    if (FP) store_mat<T>(FP + (row0 + k) * n * n, P, n, n, ldn);
+    if (LLC && threadIdx.x == 0) LLC[row0 + k] = ll;
+    const T t0 = Tm[k];
+    const T t1 = k + 1 < K ? Tm[k + 1] : t0 + T(d.dt_final);
+    bool hit = false;
+    if (linear) {
+      // pushforward from (I, 0), then m = A m + B u + b, P = A P A^T + Q (cd_linear/inference.py:619-620)
+      T* A = c.p(L.ODEY);
+      T* Q = A + L.nn;
+      FOR_T(e, n * ldn) {
+        const int i = e / ldn, j = e - i * ldn;
+        A[e] = i == j ? T(1) : T(0);
+        Q[e] = T(0);
+      }
+      __syncthreads();
+      hit = ode_solve<T>(c, ODE_PUSH, A, 2 * L.nn, t0, t1, dt0, d.max_steps);
+      T* AP = c.p(L.W1);
+      T* mnew = c.p(L.C0);
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += A[i * ldn + q] * P[q * ldn + j];
+        AP[i * ldn + j] = s;
+      }
+      FOR_T(i, n) {
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += A[i * ldn + q] * mu[q];
+        if (du > 0) {
+          const T* BU = c.p(L.BU);
+          for (int q = 0; q < du; ++q) s += BU[i * du + q] * uv[q];
+        }
+        mnew[i] = s + c.p(L.BV)[i];
+      }
+      __syncthreads();
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += AP[i * ldn + q] * A[j * ldn + q];
+        P[i * ldn + j] = s + Q[i * ldn + j];
+      }
+      FOR_T(i, n) mu[i] = mnew[i];
+      __syncthreads();
+    } else if (algo == ALGO_EKF_FILTER && d.state_order == CDK_ORDER_ZEROTH) {
+      // inference_ekf.py:126-138: only the mean is integrated; P += sqrt(dt) (c L) Qc (c L)^T
+      hit = ode_solve<T>(c, ODE_MEAN, mu, n, t0, t1, dt0, d.max_steps);
+      const T sc = sqrt(t1 - t0) * T(d.cov_rescaling) * T(d.cov_rescaling);
+      const T* lql = c.p(L.LQL);
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        P[i * ldn + j] += sc * lql[i * ldn + j];
+      }
+      __syncthreads();
+    } else {
+      hit = ode_solve<T>(c, algo == ALGO_UKF_FILTER ? ODE_UKF : ODE_EKF, mu, L.mpoff + L.nn, t0, t1, dt0, d.max_steps);
+    }
+    if (hit) status = 2;
+    if (PM) FOR_T(i, n) PM[(row0 + k) * n + i] = mu[i];
+    if (PP) store_mat<T>(PP + (row0 + k) * n * n, P, n, n, ldn);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    if (status == 0 && !isfinite(ll)) status = 1;
+    if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
+    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
+  }
+}
+
+// Backward pass of the smoothers.  Reads the filtered moments from HBM (CDK_IN_FM / CDK_IN_FP).
+template <typename T>
+__global__ void generic_smooth_kernel(const GArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Ctx<T> c(g, reinterpret_cast<T*>(smem_raw));
+  const Lay& L = c.L;
+  const KArgs<T>& a = g.k;
+  const cdk_desc& d = a.d;
+  const int n = L.n, du = L.du, ldn = L.ldn, K = d.K;
+  const bool linear = g.algo == ALGO_KF_SMOOTH;
+  const int stype = linear ? d.smoother_type : 2;
+  const long long traj = blockIdx.x;
+  FOR_T(e, L.total) c.sh[e] = T(0);
+  __syncthreads();
+  load_model<T>(c, traj, linear);
+  const T* Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  const T* U = du > 0 ? a.in[CDK_IN_U] + traj * a.in_stride[CDK_IN_U] : nullptr;
+  const T* FMg = a.in[CDK_IN_FM] + traj * a.in_stride[CDK_IN_FM];
+  const T* FPg = a.in[CDK_IN_FP] + traj * a.in_stride[CDK_IN_FP];
+  T* SMg = static_cast<T*>(a.out[CDK_OUT_SM]) + traj * (long long)K * n;
+  T* SPg = static_cast<T*>(a.out[CDK_OUT_SP]) + traj * (long long)K * n * n;
+  T* SCg = a.out[CDK_OUT_SCROSS] ? static_cast<T*>(a.out[CDK_OUT_SCROSS]) + traj * (long long)(K - 1) * n * n : nullptr;
+  T* ms = c.p(L.MU);
+  T* Ps = c.p(L.P);
+  T* mf = c.p(L.MF);
+  T* Pf = c.p(L.PF);
+  FOR_T(i, n) ms[i] = FMg[(long long)(K - 1) * n + i];
+  load_mat<T>(Ps, FPg + (long long)(K - 1) * n * n, n, n, ldn);
+  __syncthreads();
+  FOR_T(i, n) SMg[(long long)(K - 1) * n + i] = ms[i];
+  store_mat<T>(SPg + (long long)(K - 1) * n * n, Ps, n, n, ldn);
+  int status = 0;
+  const T* lql = c.p(L.LQL);
+  for (int k = K - 2; k >= 0; --k) {
+    FOR_T(i, n) mf[i] = FMg[(long long)k * n + i];
+    load_mat<T>(Pf, FPg + (long long)k * n * n, n, n, ldn);
+    __syncthreads();
+    const T t0 = Tm[k], t1 = Tm[k + 1];
+    if (stype == 1) {
+      // Sarkka Alg 3.17 (cd_linear/inference.py:746-773): the pushforward is re-integrated here (:753)
+      T* A = c.p(L.ODEY);
+      T* Q = A + L.nn;
+      FOR_T(e, n * ldn) {
+        const int i = e / ldn, j = e - i * ldn;
+        A[e] = i == j ? T(1) : T(0);
+        Q[e] = T(0);
+      }
+      __syncthreads();
+      if (ode_solve<T>(c, ODE_PUSH, A, 2 * L.nn, t0, t1, T(d.dt0), d.max_steps)) status = 2;
+      T* APf = c.p(L.W1);  // A Pf, then Ct = (Pp + boost)^-1 A Pf  (C = Ct^T)
+      T* Pp = c.p(L.W2);   // A Pf A^T + Q
+      T* Lp = c.p(L.W3);
+      T* Dm = c.p(L.J);    // Ps - Pp, then scratch
+      T* rv = c.p(L.C0);
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += A[i * ldn + q] * Pf[q * ldn + j];
+        APf[i * ldn + j] = s;
+      }
+      __syncthreads();
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += APf[i * ldn + q] * A[j * ldn + q];
+        Pp[i * ldn + j] = Q[i * ldn + j] + s;
+      }
+      FOR_T(i, n) {
+        // m_s^+ - A m_f - B u - b   (:763-766)
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += A[i * ldn + q] * mf[q];
+        if (du > 0) {
+          const T* BU = c.p(L.BU);
+          for (int q = 0; q < du; ++q) s += BU[i * du + q] * U[(long long)k * du + q];
+        }
+        rv[i] = ms[i] - s - c.p(L.BV)[i];
+      }
+      __syncthreads();
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        Dm[i * ldn + j] = Ps[i * ldn + j] - Pp[i * ldn + j];
+        Q[i * ldn + j] = T(0.5) * (Pp[i * ldn + j] + Pp[j * ldn + i]);  // sym(Pp) (Q no longer needed)
+      }
+      __syncthreads();
+      chol<T>(Q, Lp, n, ldn, T(1e-9));
+      chol_solve<T>(Lp, n, ldn, APf, n, ldn);  // APf <- Ct
+      const T* Ct = APf;
+      T* CD = Pp;  // C (Ps - Pp)
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        T s = T(0), x = T(0);
+        for (int q = 0; q < n; ++q) {
+          s += Ct[q * ldn + i] * Dm[q * ldn + j];
+          x += Ct[q * ldn + i] * Ps[q * ldn + j];
+        }
+        CD[i * ldn + j] = s;
+        Q[i * ldn + j] = x;  // C P_s^+
+      }
+      T* msn = c.p(L.YS);
+      FOR_T(i, n) {
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += Ct[q * ldn + i] * rv[q];
+        msn[i] = mf[i] + s;
+      }
+      __syncthreads();
+      if (SCg) {
+        // cross = C P_s^+ + m_s m_s^{+T}   (:771)
+        FOR_T(e, n * n) {
+          const int i = e / n, j = e - i * n;
+          SCg[(long long)k * n * n + e] = Q[i * ldn + j] + msn[i] * ms[j];
+        }
+      }
+      __syncthreads();
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        T s = T(0);
+        for (int q = 0; q < n; ++q) s += CD[i * ldn + q] * Ct[q * ldn + j];
+        Ps[i * ldn + j] = Pf[i * ldn + j] + s;
+      }
+      FOR_T(i, n) ms[i] = msn[i];
+      __syncthreads();
+    } else {
+      // backward ODE: aux = psd_solve(P_f, L Qc L^T)^T; G = F_or_J(m_f) + aux; c0 = F m_f or f(m_f)
+      T* Lp = c.p(L.W3);
+      T* X = c.p(L.W1);
+      T* G = c.p(L.J);
+      T* Psym = c.p(L.W2);
+      T* c0 = c.p(L.C0);
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        Psym[i * ldn + j] = T(0.5) * (Pf[i * ldn + j] + Pf[j * ldn + i]);
+        X[i * ldn + j] = lql[i * ldn + j];
+      }
+      __syncthreads();
+      chol<T>(Psym, Lp, n, ldn, T(1e-9));
+      chol_solve<T>(Lp, n, ldn, X, n, ldn);
+      const T* th = c.p(L.TH);
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        const T fj = linear ? th[i * ldn + j] : drift_jac<T>(d.drift_id, th, n, i, j, mf);
+        G[i * ldn + j] = fj + X[j * ldn + i];
+      }
+      FOR_T(i, n) {
+        if (linear) {
+          T s = T(0);
+          for (int q = 0; q < n; ++q) s += th[i * ldn + q] * mf[q];
+          c0[i] = s;
+        } else {
+          c0[i] = drift_f<T>(d.drift_id, th, n, i, [&](int q) { return mf[q]; });
+        }
+      }
+      __syncthreads();
+      // cd_linear type 2 ignores the user's settings (cd_linear/inference.py:688): host passes defaults in g.tab/d
+      if (ode_solve<T>(c, ODE_BACK, ms, L.mpoff + L.nn, T(0), t1 - t0, T(d.dt0), d.max_steps)) status = 2;
+      if (SCg) FOR_T(e, n * n) SCg[(long long)k * n * n + e] = T(NAN);  // :792
+    }
+    FOR_T(i, n) SMg[(long long)k * n + i] = ms[i];
+    store_mat<T>(SPg + (long long)k * n * n, Ps, n, n, ldn);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && a.out[CDK_OUT_STATUS]) {
+    int* st = static_cast<int*>(a.out[CDK_OUT_STATUS]);
+    bool bad = false;
+    for (int i = 0; i < n; ++i) bad |= !isfinite(ms[i]);
+    if (status == 0 && bad) status = 1;
+    if (status != 0) st[traj] = status;  // keep the filter's status unless the backward pass adds a failure
+  }
+}
+
+}  // namespace
+
+template <typename T>
+int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
+  GArgs<T> g;
+  g.k = a;
+  g.algo = algo;
+  if (algo == ALGO_KF_SMOOTH && a.d.smoother_type == 2) {
+    // _smooth passes no diffeqsolve settings: always Dopri5 / dt0 = 0.01 / max_steps = 1e5 (cd_linear/inference.py:688)
+    g.k.d.solver = CDK_DOPRI5;
+    g.k.d.dt0 = 0.01;
+    g.k.d.max_steps = 100000;
+  }
+  if (!fill_rt_tab(g.k.d.solver, g.tab)) return CDK_E_ENUM;
+  g.nslots = g.k.d.solver == CDK_DOPRI5 ? g.tab.S : 1;
+  Lay L(g.k.d, algo, g.nslots);
+  const size_t smem = (size_t)L.total * sizeof(T);
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (smem > (size_t)max_optin) return CDK_E_SIZE;
+  const int n = a.d.n > a.d.m ? a.d.n : a.d.m;
+  const int threads = n <= 4 ? 32 : (n <= 8 ? 64 : (n <= 16 ? 128 : 256));
+  const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
+  auto kern = smooth ? generic_smooth_kernel<T> : generic_filter_kernel<T>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(generic)");
+  }
+  if (a.d.N > 2147483647LL) return CDK_E_SIZE;
+  kern<<<(unsigned)a.d.N, threads, smem, s>>>(g);
+  note_launch();
+  return check_launch(smooth ? "generic_smooth_kernel" : "generic_filter_kernel");
+}
+
+template int launch_generic<double>(int, const KArgs<double>&, cudaStream_t);
+template int launch_generic<float>(int, const KArgs<float>&, cudaStream_t);
+
+// placeholders until the dedicated kernels land
+template <typename T>
+int launch_kf_warp(int, const KArgs<T>&, cudaStream_t) {
+  return CDK_E_UNSUPPORTED;
+}
+template int launch_kf_warp<double>(int, const KArgs<double>&, cudaStream_t);
+template int launch_kf_warp<float>(int, const KArgs<float>&, cudaStream_t);
+
+}  // namespace cdk

@@ -1,0 +1,190 @@
+/* cdk.h -- C ABI of the B200-native continuous-discrete Gaussian filtering kernels ("cdk").
+ *
+ * This is the drop-in boundary for ONE hot path of hd-UQ/cd_dynamax: batched continuous-discrete Kalman / extended /
+ * unscented / ensemble Kalman filtering and RTS-type smoothing over N independent, irregularly sampled trajectories.
+ * Plain pointers and sizes only; no torch / jax / C++ types.  Every entry point only enqueues work on the given CUDA
+ * stream (no host synchronisation, no allocation, no global state) and returns 0 or a negative CDK_E* code for an
+ * invalid descriptor.  Numerical failure (non-PD covariance, max_steps exceeded) is not an error: that trajectory's
+ * outputs become NaN and status[n] != 0, which is the reference's own "NaNs propagate" behaviour.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference repository root):
+ *   cdk_kf_filter_*    cdlgssm_filter              src/continuous_discrete_linear_gaussian_ssm/inference.py:555-632
+ *   cdk_kf_smooth_*    cdlgssm_smoother backward   src/continuous_discrete_linear_gaussian_ssm/inference.py:694-823
+ *                      scan (types 1 and 2)          (+ _smooth :636-690)
+ *   cdk_ekf_filter_*   extended_kalman_filter      src/continuous_discrete_nonlinear_gaussian_ssm/inference_ekf.py:202-326
+ *   cdk_ekf_smooth_*   extended_kalman_smoother    .../inference_ekf.py:450-539 (+ _smooth :363-448)
+ *   cdk_ukf_filter_*   unscented_kalman_filter     .../inference_ukf.py:206-308
+ *   cdk_enkf_filter_*  ensemble_kalman_filter      .../inference_enkf.py:151-276
+ *   cdk_ll_sum_f64     vmap(marginal_log_prob)(...).sum()      src/ssm_temissions.py:555-567
+ *   cdk_ll_allreduce   the same sum across GPUs (the reference has no multi-device path)
+ * The predict step inside each filter restates diffrax 0.4.0 `diffeqsolve` with `ConstantStepSize`
+ * (src/utils/diffrax_utils.py:40-165); the update restates dynamax `psd_solve`/`symmetrize`
+ * (dynamax/utils/utils.py:202-211) and TFP `MultivariateNormalFullCovariance.log_prob`.
+ *
+ * Layout: all arrays row-major, contiguous, last axis fastest (the JAX default), element type = the entry point's
+ * dtype (times and parameters too); status is int32.  A leading N axis is present on an input iff its bit is set in
+ * cdk_desc.batched_mask (Y and T normally are; parameters are when the caller vmaps over parameter samples).
+ */
+#ifndef CDK_H_
+#define CDK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CDK_VERSION 1
+
+typedef struct CUstream_st* cdk_stream_t; /* == cudaStream_t */
+
+/* error codes (host-side, synchronous) */
+enum {
+  CDK_OK = 0,
+  CDK_E_NULL = -1,        /* a required pointer is NULL */
+  CDK_E_SIZE = -2,        /* descriptor size / dimension out of the supported range */
+  CDK_E_ENUM = -3,        /* unknown solver / drift / emission / order / smoother type */
+  CDK_E_UNSUPPORTED = -4, /* valid request that this build does not implement */
+  CDK_E_CUDA = -5,        /* a CUDA runtime call failed; see cdk_last_error() */
+  CDK_E_NCCL = -6
+};
+
+/* fixed-step explicit solvers (diffrax names; RK4 is the classical tableau the north star names) */
+enum { CDK_EULER = 0, CDK_HEUN = 1, CDK_MIDPOINT = 2, CDK_RALSTON = 3, CDK_BOSH3 = 4, CDK_RK4 = 5, CDK_DOPRI5 = 6 };
+
+/* drift registry: a CUDA kernel cannot take the reference's Python callable (cdnlgssm_utils.py:13-36).
+ * theta layout:  LINEAR    W[n*n] row-major, bias[n]          (LearnableLinear   cdnlgssm_utils.py:50-61)
+ *                LORENZ63  sigma, rho, beta                   (LearnableLorenz63 cdnlgssm_utils.py:63-83)
+ *                LORENZ96  forcing F                          (BASELINE configs 4-5; not in the reference)
+ *                QUADRATIC a[n], B[n*n], C[n*n*n]: f_i = a_i + B_ij x_j + C_ijk x_j x_k                      */
+enum { CDK_DRIFT_LINEAR = 0, CDK_DRIFT_LORENZ63 = 1, CDK_DRIFT_LORENZ96 = 2, CDK_DRIFT_QUADRATIC = 3 };
+/* emission registry: h(x) = H x + d (LearnableLinear) */
+enum { CDK_EMISSION_LINEAR = 0 };
+/* EKFHyperParams.state_order (inference_ekf.py:40) */
+enum { CDK_ORDER_ZEROTH = 0, CDK_ORDER_FIRST = 1, CDK_ORDER_SECOND = 2 };
+
+/* input slots: in[CDK_NUM_IN] */
+enum {
+  CDK_IN_Y = 0,   /* emissions            [N,K,m]                                                   */
+  CDK_IN_T,       /* observation times    [N,K]   (the reference's [K,1] column, squeezed)         */
+  CDK_IN_U,       /* inputs               [N,K,d_u] or NULL (linear model only)                     */
+  CDK_IN_M0,      /* initial mean         [n]                                                       */
+  CDK_IN_P0,      /* initial covariance   [n,n]                                                     */
+  CDK_IN_F,       /* kf: dynamics weights F [n,n];  ekf/ukf/enkf: drift parameter vector theta     */
+  CDK_IN_B,       /* kf: dynamics bias b  [n] (added after the pushforward, cd_linear/inference.py:204) */
+  CDK_IN_BU,      /* kf: dynamics input weights B [n,d_u] or NULL                                   */
+  CDK_IN_L,       /* diffusion coefficient L [n,n]                                                  */
+  CDK_IN_QC,      /* diffusion covariance Qc [n,n]                                                  */
+  CDK_IN_H,       /* emission weights H   [m,n]                                                     */
+  CDK_IN_D,       /* emission bias d      [m]                                                       */
+  CDK_IN_DU,      /* kf: emission input weights D [m,d_u] or NULL                                   */
+  CDK_IN_R,       /* emission covariance R [m,m]                                                    */
+  CDK_IN_FM,      /* smooth: filtered means        [N,K,n]                                          */
+  CDK_IN_FP,      /* smooth: filtered covariances  [N,K,n,n]                                        */
+  CDK_NUM_IN
+};
+
+/* output slots: out[CDK_NUM_OUT]; a NULL pointer means "do not write this output" (the reference's output_fields) */
+enum {
+  CDK_OUT_LL = 0, /* marginal log-likelihood per trajectory [N]                                    */
+  CDK_OUT_FM,     /* filtered means        [N,K,n]                                                  */
+  CDK_OUT_FP,     /* filtered covariances  [N,K,n,n]                                                */
+  CDK_OUT_PM,     /* predicted means       [N,K,n]   (entry k is the prediction for t_{k+1})       */
+  CDK_OUT_PP,     /* predicted covariances [N,K,n,n]                                                */
+  CDK_OUT_LLCUM,  /* cumulative log-likelihood [N,K] ("marginal_loglik" listed in output_fields)   */
+  CDK_OUT_SM,     /* smoothed means        [N,K,n]                                                  */
+  CDK_OUT_SP,     /* smoothed covariances  [N,K,n,n]                                                */
+  CDK_OUT_SCROSS, /* smoothed cross terms  [N,K-1,n,n] (type 1; NaN for type 2)                    */
+  CDK_OUT_STATUS, /* int32 [N]: 0 ok, 1 non-finite result (non-PD / NaN), 2 max_steps exceeded      */
+  CDK_OUT_SCRATCH,/* device scratch of cdk_scratch_bytes() bytes (EnKF with large ensembles), else NULL */
+  CDK_NUM_OUT
+};
+
+typedef struct cdk_desc {
+  int32_t struct_size;    /* sizeof(cdk_desc), checked */
+  int32_t K;              /* observations per trajectory, >= 1 */
+  int64_t N;              /* trajectories, >= 0 */
+  int32_t n;              /* state dimension   1..CDK_MAX_N */
+  int32_t m;              /* emission dimension 1..CDK_MAX_M */
+  int32_t d_u;            /* input dimension, 0 = no inputs */
+  int32_t E;              /* EnKF ensemble size */
+  int32_t solver;         /* CDK_EULER .. CDK_DOPRI5 */
+  int32_t max_steps;      /* diffrax max_steps (default 100000) */
+  double dt0;             /* solver step (diffrax dt0, default 0.01) */
+  double dt_final;        /* length of the gap after the last observation (default 1e-10) */
+  int32_t state_order;    /* ekf */
+  int32_t num_iter;       /* ekf: re-linearisations in the update (>= 1) */
+  int32_t smoother_type;  /* kf smooth: 1 or 2 */
+  int32_t drift_id;
+  int32_t emission_id;
+  int32_t n_theta;        /* length of the drift parameter vector */
+  uint32_t batched_mask;  /* bit i set: in[i] has a leading N axis */
+  int32_t perturb_measurements; /* enkf */
+  double cov_rescaling;   /* ekf zeroth order (inference_ekf.py:135) */
+  double alpha, beta, kappa;    /* ukf (inference_ukf.py:31-33) */
+  uint64_t rng_seed;      /* enkf: Philox4x32-10 key */
+  uint64_t rng_offset;    /* enkf: added to the trajectory index in the counter (sharding across GPUs) */
+  int32_t reserved[4];
+} cdk_desc;
+
+#define CDK_MAX_N 64
+#define CDK_MAX_M 64
+
+/* Fill a descriptor with the reference's defaults (KFHyperParams / EKFHyperParams / UKFHyperParams / diffeqsolve). */
+void cdk_desc_init(cdk_desc* d);
+
+#define CDK_DECL(name) \
+  int name(const cdk_desc* d, const void* const* in, void* const* out, cdk_stream_t stream)
+
+CDK_DECL(cdk_kf_filter_f64);
+CDK_DECL(cdk_kf_filter_f32);
+CDK_DECL(cdk_kf_smooth_f64);
+CDK_DECL(cdk_kf_smooth_f32);
+CDK_DECL(cdk_ekf_filter_f64);
+CDK_DECL(cdk_ekf_filter_f32);
+CDK_DECL(cdk_ekf_smooth_f64);
+CDK_DECL(cdk_ekf_smooth_f32);
+CDK_DECL(cdk_ukf_filter_f64);
+CDK_DECL(cdk_ukf_filter_f32);
+CDK_DECL(cdk_enkf_filter_f64);
+CDK_DECL(cdk_enkf_filter_f32);
+
+/* Bytes of device scratch the given entry point needs in out[CDK_OUT_SCRATCH] (0 for most). algo: "kf_filter", ... */
+size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point);
+
+/* Deterministic sum of ll[N] into *ll_sum (one double / float on the device): the reference's `.sum()` over the
+ * vmapped axis (src/ssm_temissions.py:567). */
+int cdk_ll_sum_f64(const double* ll, int64_t N, double* ll_sum, cdk_stream_t stream);
+int cdk_ll_sum_f32(const float* ll, int64_t N, double* ll_sum, cdk_stream_t stream);
+
+/* Sum *ll_sum (one double on the device) across the ranks of an NCCL communicator, in place.
+ * `nccl_comm` is an ncclComm_t created by the caller; libnccl is resolved at run time (dlopen). */
+int cdk_ll_allreduce(void* nccl_comm, double* ll_sum, cdk_stream_t stream);
+
+/* Legacy XLA GPU custom-call target (jax 0.4.13: xla_client.register_custom_call_target(name, capsule, "CUDA")).
+ * opaque = a cdk_xla_opaque blob: {char entry_point[32]; cdk_desc desc;}.  buffers = in[0..CDK_NUM_IN) followed by
+ * out[0..CDK_NUM_OUT) with absent slots passed as zero-size dummies flagged in desc.reserved[0] (absent-input mask)
+ * and desc.reserved[1] (absent-output mask). */
+typedef struct cdk_xla_opaque {
+  char entry_point[32];
+  cdk_desc desc;
+} cdk_xla_opaque;
+void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* FP64/FP32 FMA-pipe probe used by bench.py for the roofline denominator: runs `iters` dependent-chain-free FMAs per
+ * thread on `blocks` x 256 threads and writes one value per thread to sink (so the work is not eliminated).
+ * flops = 2 * 16 * iters * blocks * 256.  Returns 0 / CDK_E_CUDA. */
+int cdk_fma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
+int cdk_fma_probe_f32(int blocks, int iters, float* sink, cdk_stream_t stream);
+
+/* Number of kernels this library has launched since load (for bench.py's gpu_launches accounting). */
+int64_t cdk_launch_count(void);
+
+int cdk_version(void);
+const char* cdk_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CDK_H_ */

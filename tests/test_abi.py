@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/cdk.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from cd_dynamax_b200 import build as b
+    b.build()
+    from cd_dynamax_b200 import _lib
+    return _lib.lib()
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "cdk.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"CDK_DECL\((cdk_\w+)\)", src))
+    names |= set(re.findall(r"\b(cdk_\w+)\s*\(", src))
+    names -= {"cdk_desc", "cdk_stream_t", "cdk_xla_opaque"}
+    return sorted(names)
+
+
+def test_header_symbols_are_exported(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 12 + 9
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/cdk.h but not exported by libcdk.so"
+
+
+def test_python_symbol_lists_match_header():
+    from cd_dynamax_b200 import _lib
+    assert sorted(_lib.ENTRY_POINTS + _lib.OTHER_SYMBOLS) == declared_symbols()
+
+
+def test_desc_layout_and_defaults(lib):
+    from cd_dynamax_b200 import _lib
+    d = _lib.new_desc()
+    assert d.struct_size == ctypes.sizeof(_lib.CdkDesc)
+    assert d.solver == _lib.SOLVERS["dopri5"] and d.dt0 == 0.01 and d.max_steps == 100000  # diffrax_utils.py:50-52
+    assert d.dt_final == 1e-10 and d.state_order == 2 and d.num_iter == 1
+    assert abs(d.alpha - 3 ** 0.5) < 1e-15 and d.beta == 2.0 and d.kappa == 1.0
+
+
+def test_invalid_descriptors_are_rejected_on_host(lib):
+    """Validation is synchronous and happens before any CUDA call, so it is testable without a GPU."""
+    from cd_dynamax_b200 import _lib
+    ins = (ctypes.c_void_p * _lib.NUM_IN)()
+    outs = (ctypes.c_void_p * _lib.NUM_OUT)()
+    d = _lib.new_desc()
+    d.N, d.K, d.n, d.m = 4, 10, 3, 1
+    d.struct_size = 8
+    assert lib.cdk_ekf_filter_f64(ctypes.byref(d), ins, outs, None) == -2  # CDK_E_SIZE
+    d = _lib.new_desc()
+    d.N, d.K, d.n, d.m, d.solver = 4, 10, 3, 1, 99
+    assert lib.cdk_kf_filter_f64(ctypes.byref(d), ins, outs, None) == -3  # CDK_E_ENUM
+    d = _lib.new_desc()
+    d.N, d.K, d.n, d.m = 4, 10, 3, 1
+    assert lib.cdk_kf_filter_f64(ctypes.byref(d), ins, outs, None) == -1  # CDK_E_NULL: inputs missing
+    assert b"NULL" in lib.cdk_last_error()
+    d.N = 0
+    assert lib.cdk_kf_filter_f64(ctypes.byref(d), ins, outs, None) == 0  # empty batch is a no-op
+    d = _lib.new_desc()
+    d.N, d.K, d.n, d.m, d.drift_id, d.n_theta = 4, 10, 4, 1, 1, 3
+    assert lib.cdk_ekf_filter_f64(ctypes.byref(d), ins, outs, None) == -2  # lorenz63 needs n == 3
+
+
+def test_settings_mapping():
+    from cd_dynamax_b200 import _engine as E, solvers
+    assert E.parse_settings({}) == {"solver": 6, "dt0": 0.01, "max_steps": 100000}
+    assert E.parse_settings({}, sde=True)["solver"] == 1
+    assert E.parse_settings({"solver": solvers.RK4(), "dt0": 0.0025, "max_steps": 1e3}) == {
+        "solver": 5, "dt0": 0.0025, "max_steps": 1000}
+    assert E.parse_settings({"solver": "Euler", "stepsize_controller": solvers.ConstantStepSize()})["solver"] == 0
+    with pytest.raises(NotImplementedError):
+        E.parse_settings({"solver": "tsit5"})
+
+    class PIDController:
+        pass
+    with pytest.raises(NotImplementedError):
+        E.parse_settings({"stepsize_controller": PIDController()})
