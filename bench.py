@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--k-obs", type=int, default=CFG["K"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     ap.add_argument("--cpu-sample-traj", type=int, default=0, help="trajectories in the CPU sample (0 = auto)")
+    ap.add_argument("--simple-data", action="store_true",
+                    help="emissions = 8*randn instead of a simulated Lorenz-63 truth (profiling runs: skips the "
+                         "~100k setup launches that would otherwise sit in front of the profiled kernel)")
     return ap.parse_args()
 
 
@@ -207,7 +210,12 @@ def run_ours(args):
     # ---- synthetic inputs (setup, untimed) ----
     t_np = make_times(N, K, CFG["seed"], rank)
     t_dev = torch.as_tensor(t_np, device=dev)
-    y_dev = make_emissions_torch(t_dev, CFG["seed"] + rank, dev)
+    if args.simple_data:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(CFG["seed"] + rank)
+        y_dev = 8.0 * torch.randn(N, K, 1, generator=gen, device=dev, dtype=torch.float64)
+    else:
+        y_dev = make_emissions_torch(t_dev, CFG["seed"] + rank, dev)
     sum_q = substeps_total(t_np, CFG["dt0"])
     params = cd.ParamsCDNLGSSM(
         initial=cd.ParamsLGSSMInitial(mean=cd.LearnableVector(torch.zeros(3, dtype=torch.float64, device=dev)),
