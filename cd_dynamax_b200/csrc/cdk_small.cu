@@ -1,19 +1,26 @@
-// cdk_small.cu -- register-resident CD-EKF for tiny state dimensions: ONE THREAD PER TRAJECTORY.
+// cdk_small.cu -- register-arithmetic CD-EKF for tiny state dimensions (Lorenz-63: m[3] + symmetric P[6]).
 //
 // Replaces extended_kalman_filter (src/continuous_discrete_nonlinear_gaussian_ssm/inference_ekf.py:202-326) with its
 // _predict (:46-148, moment ODE dm = f(m), dP = F P + P F^T + L Qc L^T) and _condition_on (:153-199) for the
-// registry drifts whose whole filter state fits in registers (Lorenz-63: m[3] + symmetric P[6]).
+// registry drifts whose whole filter state fits in registers.
 //
-// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1):
-//  * the state never leaves registers; the per-step outputs stream straight to HBM, observations/time stamps are
-//    prefetched one gap ahead so the dependent global-load latency is hidden behind ~4.5 RK substeps of FP64 math;
-//  * irregular gaps give every lane its own substep count q_k.  Instead of running each gap to the warp-wide maximum
-//    (what jax.vmap does to diffrax's while_loop), lanes run a FLATTENED substep stream: every loop iteration is one
-//    RK substep for the whole warp, and lanes whose gap just ended do the (cheap) measurement update under a
-//    predicate.  Warp efficiency is ~(q*c_step)/(q*c_step + c_update) instead of mean(q)/max(q);
-//  * 64-thread CTAs so that 65,536 trajectories = 1,024 CTAs fit in ONE wave at 7 CTAs/SM (148*7 = 1,036), which
-//    needs <= 144 registers/thread: model constants live in shared memory, not registers.
+// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_v2`:
+//  * One thread integrates one trajectory-gap at a time, all arithmetic in registers (FP64 FMA pipe bound).
+//  * Irregular gaps give every trajectory its own substep count q_k in {3..6}.  A warp that keeps a fixed set of 32
+//    trajectories runs every gap to the warp-wide maximum (what jax.vmap does to diffrax's while_loop: 4.5/6 = 75 %
+//    lane efficiency).  Instead the CANONICAL per-trajectory state lives in shared memory (SoA by slot) and, every
+//    observation step, the CTA re-assigns trajectories to threads with a counting sort on ceil(gap / dt0), so that the
+//    32 lanes of a warp integrate gaps with (nearly) the same number of substeps.  The sort key only depends on the
+//    time stamps, so it is computed one step ahead, off the critical path; it costs one extra barrier per step.
+//    Which thread integrates a trajectory never changes its arithmetic, so results are bit-reproducible.
+//  * Observations and time stamps stream HBM -> shared memory through a 4-deep cp.async ring (issued three steps ahead).
+//  * The per-step outputs (filtered/predicted mean and covariance) are staged in the same shared-memory slots that hold
+//    the canonical state, and flushed every 2 steps by the whole CTA with coalesced stores (each trajectory's two rows are
+//    contiguous in HBM), instead of 24 lane-scattered 8-byte stores per step (32 L1 wavefronts each).
+//  * 224-thread CTAs, 2 per SM: 148 * 2 * 224 = 66,304 >= 65,536 trajectories in ONE wave (<= 146 registers/thread).
 #include "cdk_common.cuh"
+
+#include <stdlib.h>
 
 namespace cdk {
 namespace {
@@ -56,54 +63,23 @@ struct DriftL63 {
   }
 };
 
-template <int N_>
-struct DriftLinear {
-  static constexpr int NX = N_;
-  static constexpr int NTHETA = N_ * N_ + N_;
-  template <typename T>
-  __device__ __forceinline__ static void f(const T* th, const T (&x)[N_], T (&o)[N_]) {
-    // LearnableLinear.f, cdnlgssm_utils.py:60-61
-#pragma unroll
-    for (int i = 0; i < N_; ++i) {
-      T s = T(0);
-#pragma unroll
-      for (int k = 0; k < N_; ++k) s += th[i * N_ + k] * x[k];
-      o[i] = s + th[N_ * N_ + i];
-    }
-  }
-  template <typename T>
-  __device__ __forceinline__ static void jp(const T* th, const T (&x)[N_], const T (&P)[N_ * (N_ + 1) / 2],
-                                            T (&G)[N_][N_]) {
-#pragma unroll
-    for (int i = 0; i < N_; ++i)
-#pragma unroll
-      for (int j = 0; j < N_; ++j) {
-        T s = T(0);
-#pragma unroll
-        for (int k = 0; k < N_; ++k) s += th[i * N_ + k] * P[pidx<N_>(k, j)];
-        G[i][j] = s;
-      }
-  }
-};
-
-// dt * rhs of the EKF moment ODE (orders 'first' and 'second'; the reference's second-order term
+// rhs of the EKF moment ODE, WITHOUT the dt factor (orders 'first' and 'second'; the reference's second-order term
 // 0.5*einsum('iik,kl->l', Hess, P) is identically zero for every drift handled here -- SURVEY F8).
 template <typename T, class Drift>
-__device__ __forceinline__ void ekf_rhs(const T* th, const T* lql, const St<T, Drift::NX>& y, T dt,
-                                        St<T, Drift::NX>& k) {
+__device__ __forceinline__ void ekf_rhs(const T* th, const T* lql, const St<T, Drift::NX>& y, St<T, Drift::NX>& k) {
   constexpr int NX = Drift::NX;
-  T f[NX];
-  Drift::f(th, y.m, f);
+  Drift::f(th, y.m, k.m);
   T G[NX][NX];
   Drift::jp(th, y.m, y.P, G);
 #pragma unroll
-  for (int i = 0; i < NX; ++i) k.m[i] = dt * f[i];
-#pragma unroll
   for (int i = 0; i < NX; ++i)
 #pragma unroll
-    for (int j = i; j < NX; ++j) k.P[pidx<NX>(i, j)] = dt * ((G[i][j] + G[j][i]) + lql[pidx<NX>(i, j)]);
+    for (int j = i; j < NX; ++j)
+      k.P[pidx<NX>(i, j)] = (i == j) ? fma(T(2), G[i][i], lql[pidx<NX>(i, i)]) : (G[i][j] + G[j][i]) + lql[pidx<NX>(i, j)];
 }
 
+// One explicit RK step y <- y + dt * sum_i b_i f(y_i), y_i = y + dt * sum_j a_ij f(y_j)  (diffrax stores k_i = dt f;
+// folding dt into the coefficients is the same arithmetic up to rounding and saves one multiply per state element).
 template <typename T, class Drift, int SOLVER>
 __device__ __forceinline__ void rk_step(const T* th, const T* lql, St<T, Drift::NX>& y, T dt) {
   using TB = Tab<SOLVER>;
@@ -117,20 +93,20 @@ __device__ __forceinline__ void rk_step(const T* th, const T* lql, St<T, Drift::
 #pragma unroll
     for (int j = 0; j < i; ++j) {
       if (TB::a(i, j) != 0.0) {
-        const T aij = T(TB::a(i, j));
+        const T c = T(TB::a(i, j)) * dt;
 #pragma unroll
-        for (int e = 0; e < NX; ++e) yi.m[e] += aij * k[j].m[e];
+        for (int e = 0; e < NX; ++e) yi.m[e] = fma(c, k[j].m[e], yi.m[e]);
 #pragma unroll
-        for (int e = 0; e < NP; ++e) yi.P[e] += aij * k[j].P[e];
+        for (int e = 0; e < NP; ++e) yi.P[e] = fma(c, k[j].P[e], yi.P[e]);
       }
     }
-    ekf_rhs<T, Drift>(th, lql, yi, dt, k[i]);
+    ekf_rhs<T, Drift>(th, lql, yi, k[i]);
     if (TB::b(i) != 0.0) {
-      const T bi = T(TB::b(i));
+      const T c = T(TB::b(i)) * dt;
 #pragma unroll
-      for (int e = 0; e < NX; ++e) acc.m[e] += bi * k[i].m[e];
+      for (int e = 0; e < NX; ++e) acc.m[e] = fma(c, k[i].m[e], acc.m[e]);
 #pragma unroll
-      for (int e = 0; e < NP; ++e) acc.P[e] += bi * k[i].P[e];
+      for (int e = 0; e < NP; ++e) acc.P[e] = fma(c, k[i].P[e], acc.P[e]);
     }
   }
   y = acc;
@@ -269,42 +245,92 @@ __device__ __forceinline__ T ekf_update(const T* H, const T* dvec, const T* R, S
   return ll;
 }
 
-template <typename T, int NX>
-__device__ __forceinline__ void store_moments(T* __restrict__ M, T* __restrict__ C, long long row,
-                                              const St<T, NX>& s) {
-  if (M) {
+
+// ---- cp.async (LDGSTS) element copies: sizeof(T) in {4, 8} is always naturally aligned -----------------------------
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
+  const unsigned d = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(gsrc), "n"(sizeof(T)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+constexpr int V2_TPB = 224;        // 7 warps; 2 CTAs / SM
+constexpr int V2_LD = V2_TPB + 1;  // SoA row stride: odd, so the fields of one slot fall into distinct banks
+constexpr int V2_RING = 4;         // input ring depth in observation steps
+constexpr int V2_NB = 32;          // counting-sort buckets (substep count clamped to 0..31)
+
+template <typename T, int NX, int NY, int NPAR>
+struct V2Smem {
+  static constexpr int NP = NX * (NX + 1) / 2;
+  static constexpr int NF = 2 * (NX + NP);  // FM | FP | PM | PP (P packed)
+  static constexpr int OFF_FM = 0, OFF_FP = NX, OFF_PM = NX + NP, OFF_PP = 2 * NX + NP;
+  T stg[2][NF][V2_LD];
+  T inY[V2_RING][NY][V2_LD];
+  T inT[V2_RING][V2_LD];
+  T ll[V2_LD];
+  int status[V2_TPB];
+  int perm[V2_TPB];
+  int hist[2][V2_NB];
+  // followed by the model constants: NPAR values (shared) or V2_TPB * NPAR (one block per slot when batched)
+};
+
+// Cooperative, coalesced write of NB staged steps (k0 .. k0+NB-1) of every live slot of the CTA.
+template <typename T, int NX, int NY, int NPAR, int NB>
+__device__ __forceinline__ void v2_flush(const V2Smem<T, NX, NY, NPAR>& sm, void* const* out, int k0, int K,
+                                         long long traj0, int nlive) {
+  using S = V2Smem<T, NX, NY, NPAR>;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) M[row * NX + i] = s.m[i];
-  }
-  if (C) {
-#pragma unroll
-    for (int i = 0; i < NX; ++i)
-#pragma unroll
-      for (int j = 0; j < NX; ++j) C[row * NX * NX + i * NX + j] = s.P[pidx<NX>(i, j)];
+  for (int a = 0; a < 4; ++a) {
+    T* __restrict__ G = static_cast<T*>(out[a == 0 ? CDK_OUT_FM : a == 1 ? CDK_OUT_FP : a == 2 ? CDK_OUT_PM : CDK_OUT_PP]);
+    if (!G) continue;
+    const bool mat = (a & 1) != 0;
+    const int len = mat ? NX * NX : NX;
+    const int off = a == 0 ? S::OFF_FM : a == 1 ? S::OFF_FP : a == 2 ? S::OFF_PM : S::OFF_PP;
+    const int per = NB * len;
+    const int total = nlive * per;
+    for (int u = threadIdx.x; u < total; u += V2_TPB) {
+      const int slot = u / per;
+      const int e = u - slot * per;
+      const int st = e / len;
+      const int el = e - st * len;
+      int field = off + el;
+      if (mat) {
+        const int i = el / NX, j = el - i * NX;
+        field = off + pidx<NX>(i, j);
+      }
+      G[((traj0 + slot) * (long long)K + k0) * len + e] = sm.stg[(k0 + st) & 1][field][slot];
+    }
   }
 }
 
-constexpr int SMALL_TPB = 64;
-
-template <typename T, class Drift, int NY, int SOLVER>
-__global__ void __launch_bounds__(SMALL_TPB, 7) ekf_small_kernel(const KArgs<T> a) {
+template <typename T, class Drift, int NY, int SOLVER, bool REGROUP>
+__global__ void __launch_bounds__(V2_TPB, 2) ekf_small_v2(const KArgs<T> a) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
-  // shared model constants: theta | lql (packed) | H | d | R.  One copy per CTA, or one per thread when batched.
-  constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;
+  constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;  // theta | lql (packed) | H | d | R
+  using S = V2Smem<T, NX, NY, NPAR>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* sh = reinterpret_cast<T*>(smem_raw);
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  T* parbase = reinterpret_cast<T*>(smem_raw + ((sizeof(S) + 15) & ~size_t(15)));
 
   const long long N = a.d.N;
   const int K = a.d.K;
-  const long long traj = (long long)blockIdx.x * SMALL_TPB + threadIdx.x;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const long long traj0 = (long long)blockIdx.x * V2_TPB;
+  const int nlive = (int)((N - traj0) < V2_TPB ? (N - traj0) : V2_TPB);
+  const bool home_live = tid < nlive;
+  const long long traj = traj0 + tid;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  T* par = par_batched ? sh + threadIdx.x * NPAR : sh;
-  const long long tj = traj < N ? traj : (N - 1);
-  if (par_batched || threadIdx.x == 0) {
+
+  // ---- prologue: model constants, initial moments, first three input steps, assignment for step 0 ----
+  if ((par_batched && home_live) || (!par_batched && tid == 0)) {
+    T* par = par_batched ? parbase + tid * NPAR : parbase;
+    const long long tj = par_batched ? traj : 0;
     const T* th = a.in[CDK_IN_F] + tj * a.in_stride[CDK_IN_F];
     const T* Lm = a.in[CDK_IN_L] + tj * a.in_stride[CDK_IN_L];
     const T* Qc = a.in[CDK_IN_QC] + tj * a.in_stride[CDK_IN_QC];
@@ -327,113 +353,184 @@ __global__ void __launch_bounds__(SMALL_TPB, 7) ekf_small_kernel(const KArgs<T> 
     for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
     for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
   }
-  __syncthreads();
-  if (traj >= N) return;
-  const T* th = par;
-  const T* lql = par + NTH;
-  const T* Hs = par + NTH + NP;
-  const T* ds = Hs + NY * NX;
-  const T* Rs = ds + NY;
-
-  const T* __restrict__ Y = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
-  const T* __restrict__ Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
-  T* __restrict__ FM = static_cast<T*>(a.out[CDK_OUT_FM]);
-  T* __restrict__ FP = static_cast<T*>(a.out[CDK_OUT_FP]);
-  T* __restrict__ PM = static_cast<T*>(a.out[CDK_OUT_PM]);
-  T* __restrict__ PP = static_cast<T*>(a.out[CDK_OUT_PP]);
-  T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
-
-  St<T, NX> s;
-  {
+  if (tid < 2 * V2_NB) (&sm.hist[0][0])[tid] = 0;
+  sm.status[tid] = 0;
+  sm.ll[tid] = T(0);
+  const T* __restrict__ Yg = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Tg = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  if (home_live) {
     const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
     const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
+    // the prior is the prediction for t_0 (inference_ekf.py:320): it sits where step -1 would have left it
 #pragma unroll
-    for (int i = 0; i < NX; ++i) s.m[i] = m0[i];
+    for (int i = 0; i < NX; ++i) sm.stg[1][S::OFF_PM + i][tid] = m0[i];
 #pragma unroll
     for (int i = 0; i < NX; ++i)
 #pragma unroll
-      for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = P0[i * NX + j];
+      for (int j = i; j < NX; ++j) sm.stg[1][S::OFF_PP + pidx<NX>(i, j)][tid] = P0[i * NX + j];
   }
+  auto prefetch = [&](int kk) {
+    if (home_live && kk < K) {
+#pragma unroll
+      for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (V2_RING - 1)][c][tid], Yg + (long long)kk * NY + c);
+      cp_async_elem(&sm.inT[kk & (V2_RING - 1)][tid], Tg + kk);
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  prefetch(1);
+  prefetch(2);
+  cp_async_wait_all();
 
   const T dt0 = T(a.d.dt0);
   const T dtf = T(a.d.dt_final);
   const T tol = clip_tol<T>();
   const int max_steps = a.d.max_steps;
   const int num_iter = a.d.num_iter;
+  const T inv_dt0 = T(1) / dt0;
+  T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
 
-  // prefetched observation for the next update and the end time of the gap that follows it
-  T y_nx[NY];
-#pragma unroll
-  for (int i = 0; i < NY; ++i) y_nx[i] = Y[i];
-  T t_cur = Tm[0];
-  T t_nxt = K > 1 ? Tm[1] : t_cur + dtf;
-
-  T ll = T(0);
-  int status = 0;
-  int k = 0;
-  int nsteps = 0;
-  T tprev = T(0), tnext = T(0), t1 = T(0);
-  bool need_update = true;
-  const long long row0 = traj * (long long)K;
-
-  while (true) {
-    if (need_update) {
-      ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y_nx, num_iter);
-      if (LLC) LLC[row0 + k] = ll;
-      store_moments<T, NX>(FM, FP, row0 + k, s);
-      tprev = t_cur;
-      t1 = t_nxt;
-      if (k + 1 < K) {
-#pragma unroll
-        for (int i = 0; i < NY; ++i) y_nx[i] = Y[(long long)(k + 1) * NY + i];
-        t_cur = t1;
-        t_nxt = (k + 2 < K) ? Tm[k + 2] : t1 + dtf;
-      }
-      tnext = fmin(tprev + dt0, t1);
-      nsteps = 0;
-      need_update = false;
+  // counting-sort key of the gap that follows observation kk of the home slot (own cp.async data: no barrier needed)
+  int my_bucket = 0, my_rank = 0;
+  auto sort_count = [&](int kk) {
+    int b = 0;
+    if (home_live) {
+      const T t0 = sm.inT[kk & (V2_RING - 1)][tid];
+      const T t1 = kk + 1 < K ? sm.inT[(kk + 1) & (V2_RING - 1)][tid] : t0 + dtf;
+      const T q = ceil((t1 - t0) * inv_dt0);
+      b = q > T(1) ? (q < T(V2_NB - 1) ? (int)q : V2_NB - 1) : 1;  // live slots: 1..31, dead slots: 0
     }
-    if (tprev < t1) {
-      if (nsteps >= max_steps) {  // diffrax max_steps exceeded: poison this trajectory, abandon the gap
-        status = 2;
+    const unsigned grp = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&sm.hist[kk & 1][b], __popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    my_bucket = b;
+    my_rank = base + __popc(grp & ((1u << lane) - 1u));
+  };
+  auto sort_scatter = [&](int kk) {
+    const int cnt = sm.hist[kk & 1][lane];
+    int incl = cnt;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = __shfl_sync(0xffffffffu, incl - cnt, my_bucket);
+    sm.perm[excl + my_rank] = tid;
+  };
+  __syncthreads();
+  if (REGROUP) {
+    sort_count(0);
+    __syncthreads();
+    sort_scatter(0);
+    __syncthreads();
+  }
+
+  for (int k = 0; k < K; ++k) {
+    // ---- phase A: update at t_k, then integrate the gap t_k -> t_{k+1}, for the trajectory assigned to this thread ----
+    const int p = REGROUP ? sm.perm[tid] : tid;
+    if (p < nlive) {
+      const T* par = par_batched ? parbase + p * NPAR : parbase;
+      const T* th = par;
+      const T* lql = par + NTH;
+      const T* Hs = par + NTH + NP;
+      const T* ds = Hs + NY * NX;
+      const T* Rs = ds + NY;
+      const int prv = (k + 1) & 1, cur = k & 1, ring = k & (V2_RING - 1);
+      St<T, NX> s;
 #pragma unroll
-        for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
-        tprev = t1;
-      } else {
+      for (int i = 0; i < NX; ++i) s.m[i] = sm.stg[prv][S::OFF_PM + i][p];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) s.P[i] = sm.stg[prv][S::OFF_PP + i][p];
+      T y[NY];
+#pragma unroll
+      for (int c = 0; c < NY; ++c) y[c] = sm.inY[ring][c][p];
+      T tprev = sm.inT[ring][p];
+      const T t1 = k + 1 < K ? sm.inT[(k + 1) & (V2_RING - 1)][p] : tprev + dtf;
+      const T ll = sm.ll[p] + ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+      sm.ll[p] = ll;
+      if (LLC) LLC[(traj0 + p) * (long long)K + k] = ll;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_FM + i][p] = s.m[i];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_FP + i][p] = s.P[i];
+      // diffrax ConstantStepSize stepping (diffrax_utils.py:150-163)
+      T tnext = fmin(tprev + dt0, t1);
+      int nsteps = 0;
+      while (tprev < t1) {
+        if (nsteps >= max_steps) {  // diffrax max_steps exceeded: poison this trajectory, abandon the gap
+          sm.status[p] = 2;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
+          break;
+        }
         rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
         ++nsteps;
         tprev = tnext;
         const T cand = tprev + dt0;
         tnext = cand > t1 - tol ? t1 : cand;
       }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_PM + i][p] = s.m[i];
+#pragma unroll
+      for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_PP + i][p] = s.P[i];
     }
-    if (!(tprev < t1)) {
-      store_moments<T, NX>(PM, PP, row0 + k, s);
-      ++k;
-      if (k == K) break;
-      need_update = true;
+    // ---- phase A': count the sort key of step k+1 (its time stamps were requested >= 1 step ago) ----
+    cp_async_wait_all();
+    if (REGROUP && k + 1 < K) sort_count(k + 1);
+    const bool flush = (k & 1) || k == K - 1;
+    if (REGROUP || flush) __syncthreads();
+    // ---- phase C: assignment for step k+1, input prefetch for step k+3, output flush every 2 steps ----
+    if (REGROUP) {
+      if (k + 1 < K) sort_scatter(k + 1);
+      if (tid < V2_NB) sm.hist[k & 1][tid] = 0;
     }
+    prefetch(k + 3);
+    if (flush) {
+      if (k & 1)
+        v2_flush<T, NX, NY, NPAR, 2>(sm, a.out, k - 1, K, traj0, nlive);
+      else
+        v2_flush<T, NX, NY, NPAR, 1>(sm, a.out, k, K, traj0, nlive);
+    }
+    if (REGROUP || flush) __syncthreads();
   }
-  if (status == 0 && !isfinite(ll)) status = 1;
-  if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
-  if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
+  if (home_live) {
+    const T ll = sm.ll[tid];
+    int status = sm.status[tid];
+    if (status == 0 && !isfinite(ll)) status = 1;
+    if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
+    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
+  }
 }
 
 template <typename T, class Drift, int NY, int SOLVER>
 int launch_one(const KArgs<T>& a, cudaStream_t s) {
   constexpr int NX = Drift::NX;
   constexpr int NPAR = Drift::NTHETA + NX * (NX + 1) / 2 + NY * NX + NY + NY * NY;
+  using S = V2Smem<T, NX, NY, NPAR>;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  const size_t smem = sizeof(T) * NPAR * (par_batched ? SMALL_TPB : 1);
-  const long long blocks = (a.d.N + SMALL_TPB - 1) / SMALL_TPB;
+  const size_t smem = ((sizeof(S) + 15) & ~size_t(15)) + sizeof(T) * NPAR * (par_batched ? V2_TPB : 1);
+  const long long blocks = (a.d.N + V2_TPB - 1) / V2_TPB;
   if (blocks == 0) return CDK_OK;
-  ekf_small_kernel<T, Drift, NY, SOLVER><<<(unsigned)blocks, SMALL_TPB, smem, s>>>(a);
+  if (blocks > 2147483647LL) return CDK_E_SIZE;
+  // CDK_EKF_REGROUP=0 keeps a fixed thread <-> trajectory assignment (profiling A/B); default is per-step regrouping
+  static const bool regroup = []() {
+    const char* e = getenv("CDK_EKF_REGROUP");
+    return !(e && e[0] == '0');
+  }();
+  auto kern = regroup ? ekf_small_v2<T, Drift, NY, SOLVER, true> : ekf_small_v2<T, Drift, NY, SOLVER, false>;
+  if (smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(ekf_small_v2)");
+  }
+  kern<<<(unsigned)blocks, V2_TPB, smem, s>>>(a);
   note_launch();
-  return check_launch("ekf_small_kernel");
+  return check_launch("ekf_small_v2");
 }
 
 template <typename T, class Drift, int NY>
