@@ -14,7 +14,7 @@ ORDERS = {"zeroth": 0, "first": 1, "second": 2}
 ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
-                 "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_launch_count", "cdk_version",
+                 "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_version",
                  "cdk_last_error"]
 
 
@@ -65,7 +65,7 @@ def lib():
         fn.restype = ctypes.c_int
     L.cdk_ll_allreduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.cdk_ll_allreduce.restype = ctypes.c_int
-    for name in ("cdk_fma_probe_f64", "cdk_fma_probe_f32"):
+    for name in ("cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_dmma_probe_f64"):
         fn = getattr(L, name)
         fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         fn.restype = ctypes.c_int

@@ -188,6 +188,25 @@ static int fma_probe(int blocks, int iters, T* sink, cdk_stream_t stream) {
   return check_launch("fma_probe_kernel");
 }
 
+// ---- FP64 tensor-core (DMMA m8n8k4) probe -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double* sink) {
+  double c[8][2];
+  const double a = 1.0 + 1e-9 * threadIdx.x, b = 1.0 - 1e-9 * threadIdx.x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 1e-3 * i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace cdk
 
 using namespace cdk;
@@ -296,6 +315,13 @@ void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque
 
 int cdk_fma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream) { return fma_probe<double>(blocks, iters, sink, stream); }
 int cdk_fma_probe_f32(int blocks, int iters, float* sink, cdk_stream_t stream) { return fma_probe<float>(blocks, iters, sink, stream); }
+
+int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream) {
+  if (!sink || blocks < 1 || iters < 1) return fail(CDK_E_NULL, "dmma_probe: bad arguments");
+  dmma_probe_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(iters, sink);
+  note_launch();
+  return check_launch("dmma_probe_kernel");
+}
 
 int64_t cdk_launch_count(void) { return (int64_t)g_launches.load(); }
 int cdk_version(void) { return CDK_VERSION; }

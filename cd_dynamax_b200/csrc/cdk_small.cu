@@ -4,7 +4,7 @@
 // _predict (:46-148, moment ODE dm = f(m), dP = F P + P F^T + L Qc L^T) and _condition_on (:153-199) for the
 // registry drifts whose whole filter state fits in registers.
 //
-// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_v2`:
+// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_v3`:
 //  * One thread integrates one trajectory-gap at a time, all arithmetic in registers (FP64 FMA pipe bound).
 //  * Irregular gaps give every trajectory its own substep count q_k in {3..6}.  A warp that keeps a fixed set of 32
 //    trajectories runs every gap to the warp-wide maximum (what jax.vmap does to diffrax's while_loop: 4.5/6 = 75 %
@@ -14,10 +14,12 @@
 //    time stamps, so it is computed one step ahead, off the critical path; it costs one extra barrier per step.
 //    Which thread integrates a trajectory never changes its arithmetic, so results are bit-reproducible.
 //  * Observations and time stamps stream HBM -> shared memory through a 4-deep cp.async ring (issued three steps ahead).
-//  * The per-step outputs (filtered/predicted mean and covariance) are staged in the same shared-memory slots that hold
-//    the canonical state, and flushed every 2 steps by the whole CTA with coalesced stores (each trajectory's two rows are
-//    contiguous in HBM), instead of 24 lane-scattered 8-byte stores per step (32 L1 wavefronts each).
-//  * 224-thread CTAs, 2 per SM: 148 * 2 * 224 = 66,304 >= 65,536 trajectories in ONE wave (<= 146 registers/thread).
+//  * Warp specialisation: 7 worker warps (224 trajectory slots) + 1 I/O warp per CTA.  While the workers integrate step
+//    k, the I/O warp (a) issues the cp.async loads of step k+3, (b) computes the assignment of step k+1, and (c) flushes
+//    the outputs of step k-1 -- which sit in the same shared-memory slots that hold the canonical state (double-buffered
+//    by step parity) -- with coalesced stores, instead of 24 lane-scattered 8-byte stores per step (32 L1 wavefronts
+//    each).  The worker critical path is update + substeps + ONE barrier per step.
+//  * 256-thread CTAs, 2 per SM: 148 * 2 * 224 = 66,304 >= 65,536 trajectories in ONE wave (128 registers/thread).
 #include "cdk_common.cuh"
 
 #include <stdlib.h>
@@ -118,6 +120,41 @@ template <typename T, int NX, int NY>
 __device__ __forceinline__ T ekf_update(const T* H, const T* dvec, const T* R, St<T, NX>& s, const T (&y)[NY],
                                         int num_iter) {
   T ll = T(0);
+  if constexpr (NY == 1) {
+    // Scalar emission: the 1x1 Cholesky / triangular solves collapse to two independent reciprocals and one log, which
+    // the scheduler can overlap (the generic path below is one long sqrt -> rcp -> log dependency chain).
+    //   log N(y; h(m), S) = -r^2 / (2 S) - log(S) / 2 - log(2 pi) / 2;   K = P H^T / (S + 1e-9);   P -= K S K^T
+    for (int it = 0; it < num_iter; ++it) {
+      T HP[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        T acc = T(0);
+#pragma unroll
+        for (int k = 0; k < NX; ++k) acc += H[k] * s.P[pidx<NX>(k, j)];
+        HP[j] = acc;
+      }
+      T S = R[0], hm = dvec[0];
+#pragma unroll
+      for (int k = 0; k < NX; ++k) {
+        S += HP[k] * H[k];
+        hm += H[k] * s.m[k];
+      }
+      const T r = y[0] - hm;
+      const T rb = T(1) / (S + T(1e-9));
+      if (it == 0) ll = T(-0.5) * (r * r / S) - T(0.5) * log(S) - half_log_2pi<T>();
+      T Kt[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) Kt[j] = HP[j] * rb;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const T ks = Kt[i] * S;
+#pragma unroll
+        for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] -= ks * Kt[j];
+        s.m[i] += Kt[i] * r;
+      }
+    }
+    return ll;
+  }
   for (int it = 0; it < num_iter; ++it) {
     T HP[NY][NX];
 #pragma unroll
@@ -255,31 +292,36 @@ __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int V2_TPB = 224;        // 7 warps; 2 CTAs / SM
-constexpr int V2_LD = V2_TPB + 1;  // SoA row stride: odd, so the fields of one slot fall into distinct banks
-constexpr int V2_RING = 4;         // input ring depth in observation steps
-constexpr int V2_NB = 32;          // counting-sort buckets (substep count clamped to 0..31)
+constexpr int V3_W = 224;         // worker threads (7 warps) = trajectory slots per CTA
+constexpr int V3_TPB = 256;       // + 1 I/O warp; 2 CTAs / SM (128 registers / thread)
+constexpr int V3_LD = V3_W + 1;   // SoA row stride: odd, so the fields of one slot fall into distinct banks
+constexpr int V3_RING = 4;        // input ring depth in observation steps
+constexpr int V3_NB = 32;         // counting-sort buckets (substep count clamped to 1..31; 0 = dead slot)
+constexpr int V3_SPL = V3_W / 32; // slots per I/O-warp lane
 
-template <typename T, int NX, int NY, int NPAR>
-struct V2Smem {
+template <typename T, int NX, int NY>
+struct V3Smem {
   static constexpr int NP = NX * (NX + 1) / 2;
   static constexpr int NF = 2 * (NX + NP);  // FM | FP | PM | PP (P packed)
   static constexpr int OFF_FM = 0, OFF_FP = NX, OFF_PM = NX + NP, OFF_PP = 2 * NX + NP;
-  T stg[2][NF][V2_LD];
-  T inY[V2_RING][NY][V2_LD];
-  T inT[V2_RING][V2_LD];
-  T ll[V2_LD];
-  int status[V2_TPB];
-  int perm[V2_TPB];
-  int hist[2][V2_NB];
-  // followed by the model constants: NPAR values (shared) or V2_TPB * NPAR (one block per slot when batched)
+  T stg[2][NF][V3_LD];  // canonical state + output staging, by step parity
+  T inY[V3_RING][NY][V3_LD];
+  T inT[V3_RING][V3_LD];
+  T ll[V3_LD];
+  int status[V3_W];
+  int perm[2][V3_W];  // thread -> slot assignment, by step parity
+  int hist[V3_NB];
+  // followed by the model constants: NPAR values (shared) or V3_W * NPAR (one block per slot when batched)
 };
 
-// Cooperative, coalesced write of NB staged steps (k0 .. k0+NB-1) of every live slot of the CTA.
-template <typename T, int NX, int NY, int NPAR, int NB>
-__device__ __forceinline__ void v2_flush(const V2Smem<T, NX, NY, NPAR>& sm, void* const* out, int k0, int K,
-                                         long long traj0, int nlive) {
-  using S = V2Smem<T, NX, NY, NPAR>;
+// I/O warp: coalesced write of the staged outputs of step kk for every live slot.  Lane l owns a FIXED element of the
+// row (l % len) and walks over the slots with a constant stride (32 / len), so each pass is LDS + STG + pointer bumps;
+// consecutive lanes write consecutive addresses inside one trajectory's row.
+template <typename T, int NX, int NY>
+__device__ __forceinline__ void v3_flush(const V3Smem<T, NX, NY>& sm, void* const* out, int kk, int K, long long traj0,
+                                         int nlive, int lane) {
+  using S = V3Smem<T, NX, NY>;
+  const T* base = &sm.stg[kk & 1][0][0];
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     T* __restrict__ G = static_cast<T*>(out[a == 0 ? CDK_OUT_FM : a == 1 ? CDK_OUT_FP : a == 2 ? CDK_OUT_PM : CDK_OUT_PP]);
@@ -287,30 +329,29 @@ __device__ __forceinline__ void v2_flush(const V2Smem<T, NX, NY, NPAR>& sm, void
     const bool mat = (a & 1) != 0;
     const int len = mat ? NX * NX : NX;
     const int off = a == 0 ? S::OFF_FM : a == 1 ? S::OFF_FP : a == 2 ? S::OFF_PM : S::OFF_PP;
-    const int per = NB * len;
-    const int total = nlive * per;
-    for (int u = threadIdx.x; u < total; u += V2_TPB) {
-      const int slot = u / per;
-      const int e = u - slot * per;
-      const int st = e / len;
-      const int el = e - st * len;
-      int field = off + el;
-      if (mat) {
-        const int i = el / NX, j = el - i * NX;
-        field = off + pidx<NX>(i, j);
-      }
-      G[((traj0 + slot) * (long long)K + k0) * len + e] = sm.stg[(k0 + st) & 1][field][slot];
+    const int stride = 32 / len;  // slots per pass
+    if (lane >= stride * len) continue;
+    const int slot0 = lane / len, el = lane - slot0 * len;
+    const int field = off + (mat ? pidx<NX>(el / NX, el % NX) : el);
+    const T* src = base + field * V3_LD + slot0;
+    T* dst = G + ((traj0 + slot0) * (long long)K + kk) * len + el;
+    const long long dstep = (long long)stride * K * len;
+#pragma unroll 4
+    for (int slot = slot0; slot < nlive; slot += stride) {
+      *dst = *src;
+      src += stride;
+      dst += dstep;
     }
   }
 }
 
 template <typename T, class Drift, int NY, int SOLVER, bool REGROUP>
-__global__ void __launch_bounds__(V2_TPB, 2) ekf_small_v2(const KArgs<T> a) {
+__global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
   constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;  // theta | lql (packed) | H | d | R
-  using S = V2Smem<T, NX, NY, NPAR>;
+  using S = V3Smem<T, NX, NY>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
   T* parbase = reinterpret_cast<T*>(smem_raw + ((sizeof(S) + 15) & ~size_t(15)));
@@ -319,15 +360,22 @@ __global__ void __launch_bounds__(V2_TPB, 2) ekf_small_v2(const KArgs<T> a) {
   const int K = a.d.K;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const long long traj0 = (long long)blockIdx.x * V2_TPB;
-  const int nlive = (int)((N - traj0) < V2_TPB ? (N - traj0) : V2_TPB);
-  const bool home_live = tid < nlive;
+  const bool io_warp = tid >= V3_W;
+  const long long traj0 = (long long)blockIdx.x * V3_W;
+  const int nlive = (int)((N - traj0) < V3_W ? (N - traj0) : V3_W);
+  const bool home_live = tid < nlive;  // worker thread whose home slot holds a trajectory
   const long long traj = traj0 + tid;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
+  const T* __restrict__ Ybase = a.in[CDK_IN_Y] + traj0 * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Tbase = a.in[CDK_IN_T] + traj0 * a.in_stride[CDK_IN_T];
+  const long long ystride = a.in_stride[CDK_IN_Y], tstride = a.in_stride[CDK_IN_T];
+  const T dt0 = T(a.d.dt0);
+  const T dtf = T(a.d.dt_final);
+  const T inv_dt0 = T(1) / dt0;
 
-  // ---- prologue: model constants, initial moments, first three input steps, assignment for step 0 ----
+  // ---- prologue: model constants, initial moments, first three input steps ----
   if ((par_batched && home_live) || (!par_batched && tid == 0)) {
     T* par = par_batched ? parbase + tid * NPAR : parbase;
     const long long tj = par_batched ? traj : 0;
@@ -353,11 +401,12 @@ __global__ void __launch_bounds__(V2_TPB, 2) ekf_small_v2(const KArgs<T> a) {
     for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
     for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
   }
-  if (tid < 2 * V2_NB) (&sm.hist[0][0])[tid] = 0;
-  sm.status[tid] = 0;
-  sm.ll[tid] = T(0);
-  const T* __restrict__ Yg = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
-  const T* __restrict__ Tg = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  if (!io_warp) {
+    sm.status[tid] = 0;
+    sm.ll[tid] = T(0);
+    sm.perm[0][tid] = tid;
+    sm.perm[1][tid] = tid;
+  }
   if (home_live) {
     const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
     const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
@@ -368,136 +417,145 @@ __global__ void __launch_bounds__(V2_TPB, 2) ekf_small_v2(const KArgs<T> a) {
     for (int i = 0; i < NX; ++i)
 #pragma unroll
       for (int j = i; j < NX; ++j) sm.stg[1][S::OFF_PP + pidx<NX>(i, j)][tid] = P0[i * NX + j];
-  }
-  auto prefetch = [&](int kk) {
-    if (home_live && kk < K) {
+    for (int kk = 0; kk < 3 && kk < K; ++kk) {
 #pragma unroll
-      for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (V2_RING - 1)][c][tid], Yg + (long long)kk * NY + c);
-      cp_async_elem(&sm.inT[kk & (V2_RING - 1)][tid], Tg + kk);
+      for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk][c][tid], Ybase + tid * ystride + (long long)kk * NY + c);
+      cp_async_elem(&sm.inT[kk][tid], Tbase + tid * tstride + kk);
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+  }
+  __syncthreads();
+
+  // ---- I/O warp helpers (one warp serves all V3_W slots: slot = lane + 32 r) ----
+  auto io_prefetch = [&](int kk) {
+    if (kk < K) {
+#pragma unroll
+      for (int r = 0; r < V3_SPL; ++r) {
+        const int slot = lane + 32 * r;
+        if (slot < nlive) {
+#pragma unroll
+          for (int c = 0; c < NY; ++c)
+            cp_async_elem(&sm.inY[kk & (V3_RING - 1)][c][slot], Ybase + slot * ystride + (long long)kk * NY + c);
+          cp_async_elem(&sm.inT[kk & (V3_RING - 1)][slot], Tbase + slot * tstride + kk);
+        }
+      }
     }
     cp_async_commit();
   };
-  prefetch(0);
-  prefetch(1);
-  prefetch(2);
-  cp_async_wait_all();
-
-  const T dt0 = T(a.d.dt0);
-  const T dtf = T(a.d.dt_final);
-  const T tol = clip_tol<T>();
-  const int max_steps = a.d.max_steps;
-  const int num_iter = a.d.num_iter;
-  const T inv_dt0 = T(1) / dt0;
-  T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
-
-  // counting-sort key of the gap that follows observation kk of the home slot (own cp.async data: no barrier needed)
-  int my_bucket = 0, my_rank = 0;
-  auto sort_count = [&](int kk) {
-    int b = 0;
-    if (home_live) {
-      const T t0 = sm.inT[kk & (V2_RING - 1)][tid];
-      const T t1 = kk + 1 < K ? sm.inT[(kk + 1) & (V2_RING - 1)][tid] : t0 + dtf;
-      const T q = ceil((t1 - t0) * inv_dt0);
-      b = q > T(1) ? (q < T(V2_NB - 1) ? (int)q : V2_NB - 1) : 1;  // live slots: 1..31, dead slots: 0
+  // counting sort of the slots by the substep count of the gap after observation kk -> perm[kk & 1]
+  auto io_sort = [&](int kk) {
+    sm.hist[lane] = 0;
+    __syncwarp();
+    int bkt[V3_SPL], pos[V3_SPL];
+#pragma unroll
+    for (int r = 0; r < V3_SPL; ++r) {
+      const int slot = lane + 32 * r;
+      int b = 0;
+      if (slot < nlive) {
+        const T t0 = sm.inT[kk & (V3_RING - 1)][slot];
+        const T t1 = kk + 1 < K ? sm.inT[(kk + 1) & (V3_RING - 1)][slot] : t0 + dtf;
+        const T q = ceil((t1 - t0) * inv_dt0);
+        b = q > T(1) ? (q < T(V3_NB - 1) ? (int)q : V3_NB - 1) : 1;
+      }
+      const unsigned grp = __match_any_sync(0xffffffffu, b);
+      const int leader = __ffs(grp) - 1;
+      int base = 0;
+      if (lane == leader) {
+        base = sm.hist[b];
+        sm.hist[b] = base + __popc(grp);
+      }
+      __syncwarp();
+      base = __shfl_sync(0xffffffffu, base, leader);
+      bkt[r] = b;
+      pos[r] = base + __popc(grp & ((1u << lane) - 1u));
     }
-    const unsigned grp = __match_any_sync(0xffffffffu, b);
-    const int leader = __ffs(grp) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&sm.hist[kk & 1][b], __popc(grp));
-    base = __shfl_sync(grp, base, leader);
-    my_bucket = b;
-    my_rank = base + __popc(grp & ((1u << lane) - 1u));
-  };
-  auto sort_scatter = [&](int kk) {
-    const int cnt = sm.hist[kk & 1][lane];
+    const int cnt = sm.hist[lane];
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    const int excl = __shfl_sync(0xffffffffu, incl - cnt, my_bucket);
-    sm.perm[excl + my_rank] = tid;
+    const int excl = incl - cnt;
+#pragma unroll
+    for (int r = 0; r < V3_SPL; ++r) {
+      const int off = __shfl_sync(0xffffffffu, excl, bkt[r]);
+      sm.perm[kk & 1][off + pos[r]] = lane + 32 * r;
+    }
   };
+  if (REGROUP && io_warp) io_sort(0);
   __syncthreads();
-  if (REGROUP) {
-    sort_count(0);
-    __syncthreads();
-    sort_scatter(0);
-    __syncthreads();
-  }
+
+  const T tol = clip_tol<T>();
+  const int max_steps = a.d.max_steps;
+  const int num_iter = a.d.num_iter;
+  T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
 
   for (int k = 0; k < K; ++k) {
-    // ---- phase A: update at t_k, then integrate the gap t_k -> t_{k+1}, for the trajectory assigned to this thread ----
-    const int p = REGROUP ? sm.perm[tid] : tid;
-    if (p < nlive) {
-      const T* par = par_batched ? parbase + p * NPAR : parbase;
-      const T* th = par;
-      const T* lql = par + NTH;
-      const T* Hs = par + NTH + NP;
-      const T* ds = Hs + NY * NX;
-      const T* Rs = ds + NY;
-      const int prv = (k + 1) & 1, cur = k & 1, ring = k & (V2_RING - 1);
-      St<T, NX> s;
+    if (!io_warp) {
+      // ---- worker: update at t_k, then integrate the gap t_k -> t_{k+1}, for the slot assigned to this thread ----
+      const int p = REGROUP ? sm.perm[k & 1][tid] : tid;
+      if (p < nlive) {
+        const T* par = par_batched ? parbase + p * NPAR : parbase;
+        const T* th = par;
+        const T* lql = par + NTH;
+        const T* Hs = par + NTH + NP;
+        const T* ds = Hs + NY * NX;
+        const T* Rs = ds + NY;
+        const int prv = (k + 1) & 1, cur = k & 1, ring = k & (V3_RING - 1);
+        St<T, NX> s;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) s.m[i] = sm.stg[prv][S::OFF_PM + i][p];
+        for (int i = 0; i < NX; ++i) s.m[i] = sm.stg[prv][S::OFF_PM + i][p];
 #pragma unroll
-      for (int i = 0; i < NP; ++i) s.P[i] = sm.stg[prv][S::OFF_PP + i][p];
-      T y[NY];
+        for (int i = 0; i < NP; ++i) s.P[i] = sm.stg[prv][S::OFF_PP + i][p];
+        T y[NY];
 #pragma unroll
-      for (int c = 0; c < NY; ++c) y[c] = sm.inY[ring][c][p];
-      T tprev = sm.inT[ring][p];
-      const T t1 = k + 1 < K ? sm.inT[(k + 1) & (V2_RING - 1)][p] : tprev + dtf;
-      const T ll = sm.ll[p] + ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
-      sm.ll[p] = ll;
-      if (LLC) LLC[(traj0 + p) * (long long)K + k] = ll;
+        for (int c = 0; c < NY; ++c) y[c] = sm.inY[ring][c][p];
+        T tprev = sm.inT[ring][p];
+        const T t1 = k + 1 < K ? sm.inT[(k + 1) & (V3_RING - 1)][p] : tprev + dtf;
+        const T ll = sm.ll[p] + ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+        sm.ll[p] = ll;
+        if (LLC) LLC[(traj0 + p) * (long long)K + k] = ll;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_FM + i][p] = s.m[i];
+        for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_FM + i][p] = s.m[i];
 #pragma unroll
-      for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_FP + i][p] = s.P[i];
-      // diffrax ConstantStepSize stepping (diffrax_utils.py:150-163)
-      T tnext = fmin(tprev + dt0, t1);
-      int nsteps = 0;
-      while (tprev < t1) {
-        if (nsteps >= max_steps) {  // diffrax max_steps exceeded: poison this trajectory, abandon the gap
-          sm.status[p] = 2;
+        for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_FP + i][p] = s.P[i];
+        // diffrax ConstantStepSize stepping (diffrax_utils.py:150-163)
+        T tnext = fmin(tprev + dt0, t1);
+        int nsteps = 0;
+        while (tprev < t1) {
+          if (nsteps >= max_steps) {  // diffrax max_steps exceeded: poison this trajectory, abandon the gap
+            sm.status[p] = 2;
 #pragma unroll
-          for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+            for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
 #pragma unroll
-          for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
-          break;
+            for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
+            break;
+          }
+          rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
+          ++nsteps;
+          tprev = tnext;
+          const T cand = tprev + dt0;
+          tnext = cand > t1 - tol ? t1 : cand;
         }
-        rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
-        ++nsteps;
-        tprev = tnext;
-        const T cand = tprev + dt0;
-        tnext = cand > t1 - tol ? t1 : cand;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_PM + i][p] = s.m[i];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_PP + i][p] = s.P[i];
       }
-#pragma unroll
-      for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_PM + i][p] = s.m[i];
-#pragma unroll
-      for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_PP + i][p] = s.P[i];
+    } else {
+      // ---- I/O warp, overlapped with the workers: inputs for step k+3, assignment for step k+1, outputs of step k-1 ----
+      cp_async_wait_all();  // the group of step k+2 was issued a full step ago
+      io_prefetch(k + 3);   // ring slot of step k-1, no longer read by anyone
+      if (REGROUP && k + 1 < K) io_sort(k + 1);
+      if (k > 0) v3_flush<T, NX, NY>(sm, a.out, k - 1, K, traj0, nlive, lane);
     }
-    // ---- phase A': count the sort key of step k+1 (its time stamps were requested >= 1 step ago) ----
-    cp_async_wait_all();
-    if (REGROUP && k + 1 < K) sort_count(k + 1);
-    const bool flush = (k & 1) || k == K - 1;
-    if (REGROUP || flush) __syncthreads();
-    // ---- phase C: assignment for step k+1, input prefetch for step k+3, output flush every 2 steps ----
-    if (REGROUP) {
-      if (k + 1 < K) sort_scatter(k + 1);
-      if (tid < V2_NB) sm.hist[k & 1][tid] = 0;
-    }
-    prefetch(k + 3);
-    if (flush) {
-      if (k & 1)
-        v2_flush<T, NX, NY, NPAR, 2>(sm, a.out, k - 1, K, traj0, nlive);
-      else
-        v2_flush<T, NX, NY, NPAR, 1>(sm, a.out, k, K, traj0, nlive);
-    }
-    if (REGROUP || flush) __syncthreads();
+    __syncthreads();
   }
-  if (home_live) {
+  if (io_warp) {
+    v3_flush<T, NX, NY>(sm, a.out, K - 1, K, traj0, nlive, lane);
+  } else if (home_live) {
     const T ll = sm.ll[tid];
     int status = sm.status[tid];
     if (status == 0 && !isfinite(ll)) status = 1;
@@ -510,12 +568,12 @@ template <typename T, class Drift, int NY, int SOLVER>
 int launch_one(const KArgs<T>& a, cudaStream_t s) {
   constexpr int NX = Drift::NX;
   constexpr int NPAR = Drift::NTHETA + NX * (NX + 1) / 2 + NY * NX + NY + NY * NY;
-  using S = V2Smem<T, NX, NY, NPAR>;
+  using S = V3Smem<T, NX, NY>;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  const size_t smem = ((sizeof(S) + 15) & ~size_t(15)) + sizeof(T) * NPAR * (par_batched ? V2_TPB : 1);
-  const long long blocks = (a.d.N + V2_TPB - 1) / V2_TPB;
+  const size_t smem = ((sizeof(S) + 15) & ~size_t(15)) + sizeof(T) * NPAR * (par_batched ? V3_W : 1);
+  const long long blocks = (a.d.N + V3_W - 1) / V3_W;
   if (blocks == 0) return CDK_OK;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
   // CDK_EKF_REGROUP=0 keeps a fixed thread <-> trajectory assignment (profiling A/B); default is per-step regrouping
@@ -523,14 +581,14 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
     const char* e = getenv("CDK_EKF_REGROUP");
     return !(e && e[0] == '0');
   }();
-  auto kern = regroup ? ekf_small_v2<T, Drift, NY, SOLVER, true> : ekf_small_v2<T, Drift, NY, SOLVER, false>;
+  auto kern = regroup ? ekf_small_v3<T, Drift, NY, SOLVER, true> : ekf_small_v3<T, Drift, NY, SOLVER, false>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(ekf_small_v2)");
+      return check_launch("cudaFuncSetAttribute(ekf_small_v3)");
   }
-  kern<<<(unsigned)blocks, V2_TPB, smem, s>>>(a);
+  kern<<<(unsigned)blocks, V3_TPB, smem, s>>>(a);
   note_launch();
-  return check_launch("ekf_small_v2");
+  return check_launch("ekf_small_v3");
 }
 
 template <typename T, class Drift, int NY>

@@ -177,6 +177,9 @@ void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque
  * flops = 2 * 16 * iters * blocks * 256.  Returns 0 / CDK_E_CUDA. */
 int cdk_fma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
 int cdk_fma_probe_f32(int blocks, int iters, float* sink, cdk_stream_t stream);
+/* FP64 tensor-core probe (mma.sync m8n8k4 f64, the path the EnKF ensemble contractions use): 8 independent
+ * accumulator tiles per warp; flops = 2 * 8*8*4 * 8 * iters * blocks * 8 warps. */
+int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
 
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches accounting). */
 int64_t cdk_launch_count(void);
