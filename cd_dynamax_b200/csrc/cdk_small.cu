@@ -4,7 +4,7 @@
 // _predict (:46-148, moment ODE dm = f(m), dP = F P + P F^T + L Qc L^T) and _condition_on (:153-199) for the
 // registry drifts whose whole filter state fits in registers.
 //
-// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_v3`:
+// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_v5`:
 //  * One thread integrates one trajectory-gap at a time, all arithmetic in registers (FP64 FMA pipe bound).
 //  * Irregular gaps give every trajectory its own substep count q_k in {3..6}.  A warp that keeps a fixed set of 32
 //    trajectories runs every gap to the warp-wide maximum (what jax.vmap does to diffrax's while_loop: 4.5/6 = 75 %
@@ -22,7 +22,9 @@
 //  * 256-thread CTAs, 2 per SM: 148 * 2 * 224 = 66,304 >= 65,536 trajectories in ONE wave (128 registers/thread).
 #include "cdk_common.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 namespace cdk {
 namespace {
@@ -154,7 +156,7 @@ __device__ __forceinline__ T ekf_update(const T* H, const T* dvec, const T* R, S
       }
     }
     return ll;
-  }
+  } else {
   for (int it = 0; it < num_iter; ++it) {
     T HP[NY][NX];
 #pragma unroll
@@ -280,6 +282,7 @@ __device__ __forceinline__ T ekf_update(const T* H, const T* dvec, const T* R, S
     }
   }
   return ll;
+  }
 }
 
 
@@ -292,82 +295,91 @@ __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-constexpr int V3_W = 224;         // worker threads (7 warps) = trajectory slots per CTA
-constexpr int V3_TPB = 256;       // + 1 I/O warp; 2 CTAs / SM (128 registers / thread)
-constexpr int V3_LD = V3_W + 1;   // SoA row stride: odd, so the fields of one slot fall into distinct banks
-constexpr int V3_RING = 4;        // input ring depth in observation steps
-constexpr int V3_NB = 32;         // counting-sort buckets (substep count clamped to 1..31; 0 = dead slot)
-constexpr int V3_SPL = V3_W / 32; // slots per I/O-warp lane
+constexpr int V5_W = 224;         // worker threads (7 warps) = trajectory slots per CTA
+constexpr int V5_TPB = 256;       // + 1 helper warp; 2 CTAs / SM (128 registers / thread)
+constexpr int V5_LD = V5_W + 1;   // SoA row stride of the input rings (odd: conflict-free)
+constexpr int V5_TRING = 6;       // time-stamp ring depth (steps k .. k+3 are read, k+5 is in flight)
+constexpr int V5_TAHEAD = 5;
+constexpr int V5_YRING = 4;       // emission ring depth (step k is read, k+2 is in flight)
+constexpr int V5_YAHEAD = 2;
+constexpr int V5_NB = 32;         // counting-sort buckets (substep count clamped to 1..31; 0 = dead slot)
+constexpr int V5_SPL = V5_W / 32; // slots per helper-warp lane
 
-template <typename T, int NX, int NY>
-struct V3Smem {
-  static constexpr int NP = NX * (NX + 1) / 2;
-  static constexpr int NF = 2 * (NX + NP);  // FM | FP | PM | PP (P packed)
-  static constexpr int OFF_FM = 0, OFF_FP = NX, OFF_PM = NX + NP, OFF_PP = 2 * NX + NP;
-  T stg[2][NF][V3_LD];  // canonical state + output staging, by step parity
-  T inY[V3_RING][NY][V3_LD];
-  T inT[V3_RING][V3_LD];
-  T ll[V3_LD];
-  int status[V3_W];
-  int perm[2][V3_W];  // thread -> slot assignment, by step parity
-  int hist[V3_NB];
-  // followed by the model constants: NPAR values (shared) or V3_W * NPAR (one block per slot when batched)
+// TMA descriptors of the four per-step output arrays viewed as 2-D tensors [N][K*len] (len = NX or NX*NX): one box is
+// {2 steps x len elements, 224 trajectories}, so ONE cp.async.bulk.tensor store per array writes a whole CTA's two steps.
+struct alignas(64) V5Maps {
+  CUtensorMap m[4];  // FM, FP, PM, PP
+  int use_tma;
 };
 
-// I/O warp: coalesced write of the staged outputs of step kk for every live slot.  Lane l owns a FIXED element of the
-// row (l % len) and walks over the slots with a constant stride (32 / len), so each pass is LDS + STG + pointer bumps;
-// consecutive lanes write consecutive addresses inside one trajectory's row.
 template <typename T, int NX, int NY>
-__device__ __forceinline__ void v3_flush(const V3Smem<T, NX, NY>& sm, void* const* out, int kk, int K, long long traj0,
-                                         int nlive, int lane) {
-  using S = V3Smem<T, NX, NY>;
-  const T* base = &sm.stg[kk & 1][0][0];
+struct alignas(128) V5Smem {
+  // Output staging = canonical state, in the exact global row layout [slot][2 steps][len] (dense: it is a TMA box).
+  T fm[V5_W][2][NX];
+  alignas(128) T fp[V5_W][2][NX * NX];
+  alignas(128) T pm[V5_W][2][NX];
+  alignas(128) T pp[V5_W][2][NX * NX];
+  T inY[V5_YRING][NY][V5_LD];
+  T inT[V5_TRING][V5_LD];
+  T ll[V5_LD];
+  int status[V5_W];
+  int perm[2][V5_W];   // thread -> slot assignment, by step parity
+  int hist[3][V5_NB];  // counting-sort histograms, by step mod 3 (counted 2 steps ahead, scanned 1 step ahead)
+  // followed by the model constants: NPAR values (shared) or V5_W * NPAR (one block per slot when batched)
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem_src));
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(s)
+               : "memory");
+}
+
+// Fallback flush (fp32, odd K, unaligned outputs): all threads copy rows [k0, k0 + nrow) of every live slot.
+template <typename T, int NX, int NY>
+__device__ __forceinline__ void v5_flush_generic(const V5Smem<T, NX, NY>& sm, void* const* out, int k0, int nrow, int K,
+                                                 long long traj0, int nlive) {
 #pragma unroll
   for (int a = 0; a < 4; ++a) {
     T* __restrict__ G = static_cast<T*>(out[a == 0 ? CDK_OUT_FM : a == 1 ? CDK_OUT_FP : a == 2 ? CDK_OUT_PM : CDK_OUT_PP]);
     if (!G) continue;
-    const bool mat = (a & 1) != 0;
-    const int len = mat ? NX * NX : NX;
-    const int off = a == 0 ? S::OFF_FM : a == 1 ? S::OFF_FP : a == 2 ? S::OFF_PM : S::OFF_PP;
-    const int stride = 32 / len;  // slots per pass
-    if (lane >= stride * len) continue;
-    const int slot0 = lane / len, el = lane - slot0 * len;
-    const int field = off + (mat ? pidx<NX>(el / NX, el % NX) : el);
-    const T* src = base + field * V3_LD + slot0;
-    T* dst = G + ((traj0 + slot0) * (long long)K + kk) * len + el;
-    const long long dstep = (long long)stride * K * len;
-#pragma unroll 4
-    for (int slot = slot0; slot < nlive; slot += stride) {
-      *dst = *src;
-      src += stride;
-      dst += dstep;
+    const int len = (a & 1) ? NX * NX : NX;
+    const T* src = a == 0 ? &sm.fm[0][0][0] : a == 1 ? &sm.fp[0][0][0] : a == 2 ? &sm.pm[0][0][0] : &sm.pp[0][0][0];
+    const int per = nrow * len;
+    const int total = nlive * per;
+    const int r0 = k0 & 1;
+    for (int u = threadIdx.x; u < total; u += V5_TPB) {
+      const int slot = u / per;
+      const int e = u - slot * per;
+      G[((traj0 + slot) * (long long)K + k0) * len + e] = src[slot * 2 * len + r0 * len + e];
     }
   }
 }
 
 template <typename T, class Drift, int NY, int SOLVER, bool REGROUP>
-__global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
+__global__ void __launch_bounds__(V5_TPB, 2) ekf_small_v5(const KArgs<T> a, const __grid_constant__ V5Maps maps) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
   constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;  // theta | lql (packed) | H | d | R
-  using S = V3Smem<T, NX, NY>;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using S = V5Smem<T, NX, NY>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   S& sm = *reinterpret_cast<S*>(smem_raw);
-  T* parbase = reinterpret_cast<T*>(smem_raw + ((sizeof(S) + 15) & ~size_t(15)));
+  T* parbase = reinterpret_cast<T*>(smem_raw + sizeof(S));
 
   const long long N = a.d.N;
   const int K = a.d.K;
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  const bool io_warp = tid >= V3_W;
-  const long long traj0 = (long long)blockIdx.x * V3_W;
-  const int nlive = (int)((N - traj0) < V3_W ? (N - traj0) : V3_W);
+  const bool helper = tid >= V5_W;
+  const long long traj0 = (long long)blockIdx.x * V5_W;
+  const int nlive = (int)((N - traj0) < V5_W ? (N - traj0) : V5_W);
   const bool home_live = tid < nlive;  // worker thread whose home slot holds a trajectory
   const long long traj = traj0 + tid;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
+  const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0;
   const T* __restrict__ Ybase = a.in[CDK_IN_Y] + traj0 * a.in_stride[CDK_IN_Y];
   const T* __restrict__ Tbase = a.in[CDK_IN_T] + traj0 * a.in_stride[CDK_IN_T];
   const long long ystride = a.in_stride[CDK_IN_Y], tstride = a.in_stride[CDK_IN_T];
@@ -375,7 +387,7 @@ __global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
   const T dtf = T(a.d.dt_final);
   const T inv_dt0 = T(1) / dt0;
 
-  // ---- prologue: model constants, initial moments, first three input steps ----
+  // ---- prologue: model constants, initial moments, first input steps ----
   if ((par_batched && home_live) || (!par_batched && tid == 0)) {
     T* par = par_batched ? parbase + tid * NPAR : parbase;
     const long long tj = par_batched ? traj : 0;
@@ -401,25 +413,27 @@ __global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
     for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
     for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
   }
-  if (!io_warp) {
+  if (!helper) {
     sm.status[tid] = 0;
     sm.ll[tid] = T(0);
     sm.perm[0][tid] = tid;
     sm.perm[1][tid] = tid;
+  } else {
+    for (int i = lane; i < 3 * V5_NB; i += 32) (&sm.hist[0][0])[i] = 0;
   }
   if (home_live) {
     const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
     const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
-    // the prior is the prediction for t_0 (inference_ekf.py:320): it sits where step -1 would have left it
+    // the prior is the prediction for t_0 (inference_ekf.py:320): it sits where step -1 (row 1) would have left it
 #pragma unroll
-    for (int i = 0; i < NX; ++i) sm.stg[1][S::OFF_PM + i][tid] = m0[i];
+    for (int i = 0; i < NX; ++i) sm.pm[tid][1][i] = m0[i];
 #pragma unroll
-    for (int i = 0; i < NX; ++i)
+    for (int i = 0; i < NX * NX; ++i) sm.pp[tid][1][i] = P0[i];
+    for (int kk = 0; kk < V5_TAHEAD && kk < K; ++kk) {
+      if (kk < V5_YAHEAD) {
 #pragma unroll
-      for (int j = i; j < NX; ++j) sm.stg[1][S::OFF_PP + pidx<NX>(i, j)][tid] = P0[i * NX + j];
-    for (int kk = 0; kk < 3 && kk < K; ++kk) {
-#pragma unroll
-      for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk][c][tid], Ybase + tid * ystride + (long long)kk * NY + c);
+        for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk][c][tid], Ybase + tid * ystride + (long long)kk * NY + c);
+      }
       cp_async_elem(&sm.inT[kk][tid], Tbase + tid * tstride + kk);
     }
     cp_async_commit();
@@ -427,65 +441,45 @@ __global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
   }
   __syncthreads();
 
-  // ---- I/O warp helpers (one warp serves all V3_W slots: slot = lane + 32 r) ----
-  auto io_prefetch = [&](int kk) {
-    if (kk < K) {
-#pragma unroll
-      for (int r = 0; r < V3_SPL; ++r) {
-        const int slot = lane + 32 * r;
-        if (slot < nlive) {
-#pragma unroll
-          for (int c = 0; c < NY; ++c)
-            cp_async_elem(&sm.inY[kk & (V3_RING - 1)][c][slot], Ybase + slot * ystride + (long long)kk * NY + c);
-          cp_async_elem(&sm.inT[kk & (V3_RING - 1)][slot], Tbase + slot * tstride + kk);
-        }
-      }
+  // ---- per-step regrouping (worker threads): counting sort of the home slots by the substep count of the gap after
+  //      observation kk.  count(kk) runs during step kk-2, scatter(kk) during step kk-1 -> perm[kk & 1] for step kk.
+  int my_bucket = 0, my_rank = 0;
+  auto sort_count = [&](int kk) {
+    int b = 0;
+    if (home_live) {
+      const T t0 = sm.inT[kk % V5_TRING][tid];
+      const T t1 = kk + 1 < K ? sm.inT[(kk + 1) % V5_TRING][tid] : t0 + dtf;
+      const T q = ceil((t1 - t0) * inv_dt0);
+      b = q > T(1) ? (q < T(V5_NB - 1) ? (int)q : V5_NB - 1) : 1;
     }
-    cp_async_commit();
+    const unsigned grp = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(grp) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&sm.hist[kk % 3][b], __popc(grp));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    my_bucket = b;
+    my_rank = base + __popc(grp & ((1u << lane) - 1u));
   };
-  // counting sort of the slots by the substep count of the gap after observation kk -> perm[kk & 1]
-  auto io_sort = [&](int kk) {
-    sm.hist[lane] = 0;
-    __syncwarp();
-    int bkt[V3_SPL], pos[V3_SPL];
-#pragma unroll
-    for (int r = 0; r < V3_SPL; ++r) {
-      const int slot = lane + 32 * r;
-      int b = 0;
-      if (slot < nlive) {
-        const T t0 = sm.inT[kk & (V3_RING - 1)][slot];
-        const T t1 = kk + 1 < K ? sm.inT[(kk + 1) & (V3_RING - 1)][slot] : t0 + dtf;
-        const T q = ceil((t1 - t0) * inv_dt0);
-        b = q > T(1) ? (q < T(V3_NB - 1) ? (int)q : V3_NB - 1) : 1;
-      }
-      const unsigned grp = __match_any_sync(0xffffffffu, b);
-      const int leader = __ffs(grp) - 1;
-      int base = 0;
-      if (lane == leader) {
-        base = sm.hist[b];
-        sm.hist[b] = base + __popc(grp);
-      }
-      __syncwarp();
-      base = __shfl_sync(0xffffffffu, base, leader);
-      bkt[r] = b;
-      pos[r] = base + __popc(grp & ((1u << lane) - 1u));
-    }
-    const int cnt = sm.hist[lane];
+  auto sort_scatter = [&](int kk) {
+    const int cnt = sm.hist[kk % 3][lane];
     int incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    const int excl = incl - cnt;
-#pragma unroll
-    for (int r = 0; r < V3_SPL; ++r) {
-      const int off = __shfl_sync(0xffffffffu, excl, bkt[r]);
-      sm.perm[kk & 1][off + pos[r]] = lane + 32 * r;
-    }
+    const int off = __shfl_sync(0xffffffffu, incl - cnt, my_bucket);
+    sm.perm[kk & 1][off + my_rank] = tid;
   };
-  if (REGROUP && io_warp) io_sort(0);
-  __syncthreads();
+  if (REGROUP) {
+    if (!helper) sort_count(0);
+    __syncthreads();
+    if (!helper) {
+      sort_scatter(0);
+      if (K > 1) sort_count(1);
+    }
+    __syncthreads();
+  }
 
   const T tol = clip_tol<T>();
   const int max_steps = a.d.max_steps;
@@ -493,34 +487,45 @@ __global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
   T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
 
   for (int k = 0; k < K; ++k) {
-    if (!io_warp) {
+    const int row = k & 1;
+    if (!helper) {
+      if (REGROUP && k + 1 < K) sort_scatter(k + 1);
       // ---- worker: update at t_k, then integrate the gap t_k -> t_{k+1}, for the slot assigned to this thread ----
       const int p = REGROUP ? sm.perm[k & 1][tid] : tid;
-      if (p < nlive) {
-        const T* par = par_batched ? parbase + p * NPAR : parbase;
-        const T* th = par;
-        const T* lql = par + NTH;
+      const bool live = p < nlive;
+      const T* par = par_batched ? parbase + (live ? p : 0) * NPAR : parbase;
+      const T* th = par;
+      const T* lql = par + NTH;
+      St<T, NX> s;
+      T tprev = T(0), t1 = T(0), ll = T(0);
+      if (live) {
         const T* Hs = par + NTH + NP;
         const T* ds = Hs + NY * NX;
         const T* Rs = ds + NY;
-        const int prv = (k + 1) & 1, cur = k & 1, ring = k & (V3_RING - 1);
-        St<T, NX> s;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) s.m[i] = sm.stg[prv][S::OFF_PM + i][p];
+        for (int i = 0; i < NX; ++i) s.m[i] = sm.pm[p][row ^ 1][i];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) s.P[i] = sm.stg[prv][S::OFF_PP + i][p];
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = sm.pp[p][row ^ 1][i * NX + j];
         T y[NY];
 #pragma unroll
-        for (int c = 0; c < NY; ++c) y[c] = sm.inY[ring][c][p];
-        T tprev = sm.inT[ring][p];
-        const T t1 = k + 1 < K ? sm.inT[(k + 1) & (V3_RING - 1)][p] : tprev + dtf;
-        const T ll = sm.ll[p] + ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+        for (int c = 0; c < NY; ++c) y[c] = sm.inY[k % V5_YRING][c][p];
+        tprev = sm.inT[k % V5_TRING][p];
+        t1 = k + 1 < K ? sm.inT[(k + 1) % V5_TRING][p] : tprev + dtf;
+        ll = sm.ll[p] + ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+      }
+      // the TMA store of the previous 2-step block must have finished READING the staging rows before row 0 is rewritten
+      if (use_tma && row == 0) asm volatile("bar.sync 1, %0;" ::"n"(V5_TPB) : "memory");
+      if (live) {
         sm.ll[p] = ll;
         if (LLC) LLC[(traj0 + p) * (long long)K + k] = ll;
 #pragma unroll
-        for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_FM + i][p] = s.m[i];
+        for (int i = 0; i < NX; ++i) sm.fm[p][row][i] = s.m[i];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_FP + i][p] = s.P[i];
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = 0; j < NX; ++j) sm.fp[p][row][i * NX + j] = s.P[pidx<NX>(i, j)];
         // diffrax ConstantStepSize stepping (diffrax_utils.py:150-163)
         T tnext = fmin(tprev + dt0, t1);
         int nsteps = 0;
@@ -540,22 +545,63 @@ __global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
           tnext = cand > t1 - tol ? t1 : cand;
         }
 #pragma unroll
-        for (int i = 0; i < NX; ++i) sm.stg[cur][S::OFF_PM + i][p] = s.m[i];
+        for (int i = 0; i < NX; ++i) sm.pm[p][row][i] = s.m[i];
 #pragma unroll
-        for (int i = 0; i < NP; ++i) sm.stg[cur][S::OFF_PP + i][p] = s.P[i];
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = 0; j < NX; ++j) sm.pp[p][row][i * NX + j] = s.P[pidx<NX>(i, j)];
       }
+      if (REGROUP && k + 2 < K) sort_count(k + 2);
     } else {
-      // ---- I/O warp, overlapped with the workers: inputs for step k+3, assignment for step k+1, outputs of step k-1 ----
-      cp_async_wait_all();  // the group of step k+2 was issued a full step ago
-      io_prefetch(k + 3);   // ring slot of step k-1, no longer read by anyone
-      if (REGROUP && k + 1 < K) io_sort(k + 1);
-      if (k > 0) v3_flush<T, NX, NY>(sm, a.out, k - 1, K, traj0, nlive, lane);
+      // ---- helper warp: output store of the previous block, input loads, sort housekeeping ----
+      if (use_tma && row == 0) {
+        if (k > 0 && lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const int c1 = (int)traj0;
+          if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], (k - 2) * NX, c1);
+          if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], (k - 2) * NX * NX, c1);
+          if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], (k - 2) * NX, c1);
+          if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], (k - 2) * NX * NX, c1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("bar.sync 1, %0;" ::"n"(V5_TPB) : "memory");
+      }
+      const int kt = k + V5_TAHEAD, ky = k + V5_YAHEAD;
+#pragma unroll
+      for (int r = 0; r < V5_SPL; ++r) {
+        const int slot = lane + 32 * r;
+        if (slot < nlive) {
+          if (ky < K) {
+#pragma unroll
+            for (int c = 0; c < NY; ++c)
+              cp_async_elem(&sm.inY[ky % V5_YRING][c][slot], Ybase + slot * ystride + (long long)ky * NY + c);
+          }
+          if (kt < K) cp_async_elem(&sm.inT[kt % V5_TRING][slot], Tbase + slot * tstride + kt);
+        }
+      }
+      cp_async_commit();
+      sm.hist[k % 3][lane] = 0;  // scanned during step k-1, counted again during step k+1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // the loads issued during step k-1 have landed
     }
     __syncthreads();
+    if (!use_tma && (row == 1 || k == K - 1)) {
+      v5_flush_generic<T, NX, NY>(sm, a.out, k - row, row + 1, K, traj0, nlive);
+      __syncthreads();
+    }
   }
-  if (io_warp) {
-    v3_flush<T, NX, NY>(sm, a.out, K - 1, K, traj0, nlive, lane);
-  } else if (home_live) {
+  if (use_tma && helper && lane == 0) {  // K is even on this path: the last block is rows K-2, K-1
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int c1 = (int)traj0;
+    if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], (K - 2) * NX, c1);
+    if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], (K - 2) * NX * NX, c1);
+    if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], (K - 2) * NX, c1);
+    if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], (K - 2) * NX * NX, c1);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (home_live) {
     const T ll = sm.ll[tid];
     int status = sm.status[tid];
     if (status == 0 && !isfinite(ll)) status = 1;
@@ -564,16 +610,62 @@ __global__ void __launch_bounds__(V3_TPB, 2) ekf_small_v3(const KArgs<T> a) {
   }
 }
 
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = []() -> encode_tiled_fn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<encode_tiled_fn>(p);
+  }();
+  return fn;
+}
+
+// Build the four output tensor maps.  Returns false when the TMA path does not apply (fp32, odd K, unaligned pointers,
+// CDK_EKF_TMA=0): the kernel then uses the cooperative-copy flush.
+template <typename T>
+bool make_maps(const KArgs<T>& a, int NX, V5Maps& maps) {
+  memset(&maps, 0, sizeof(maps));
+  static const bool disabled = []() {
+    const char* e = getenv("CDK_EKF_TMA");
+    return e && e[0] == '0';
+  }();
+  if (disabled || sizeof(T) != 8 || (a.d.K & 1) || a.d.N > 0x7fffffffLL) return false;
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return false;
+  const int slots[4] = {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP};
+  for (int i = 0; i < 4; ++i) {
+    void* ptr = a.out[slots[i]];
+    if (!ptr) continue;
+    if (reinterpret_cast<uintptr_t>(ptr) & 15) return false;
+    const cuuint64_t len = (i & 1) ? NX * NX : NX;
+    const cuuint64_t gdim[2] = {len * (cuuint64_t)a.d.K, (cuuint64_t)a.d.N};
+    const cuuint64_t gstr[1] = {len * (cuuint64_t)a.d.K * sizeof(T)};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * len), (cuuint32_t)V5_W};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  maps.use_tma = 1;
+  return true;
+}
+
 template <typename T, class Drift, int NY, int SOLVER>
 int launch_one(const KArgs<T>& a, cudaStream_t s) {
   constexpr int NX = Drift::NX;
   constexpr int NPAR = Drift::NTHETA + NX * (NX + 1) / 2 + NY * NX + NY + NY * NY;
-  using S = V3Smem<T, NX, NY>;
+  using S = V5Smem<T, NX, NY>;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  const size_t smem = ((sizeof(S) + 15) & ~size_t(15)) + sizeof(T) * NPAR * (par_batched ? V3_W : 1);
-  const long long blocks = (a.d.N + V3_W - 1) / V3_W;
+  const size_t smem = sizeof(S) + sizeof(T) * NPAR * (par_batched ? V5_W : 1);
+  const long long blocks = (a.d.N + V5_W - 1) / V5_W;
   if (blocks == 0) return CDK_OK;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
   // CDK_EKF_REGROUP=0 keeps a fixed thread <-> trajectory assignment (profiling A/B); default is per-step regrouping
@@ -581,14 +673,16 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
     const char* e = getenv("CDK_EKF_REGROUP");
     return !(e && e[0] == '0');
   }();
-  auto kern = regroup ? ekf_small_v3<T, Drift, NY, SOLVER, true> : ekf_small_v3<T, Drift, NY, SOLVER, false>;
+  V5Maps maps;
+  make_maps<T>(a, NX, maps);
+  auto kern = regroup ? ekf_small_v5<T, Drift, NY, SOLVER, true> : ekf_small_v5<T, Drift, NY, SOLVER, false>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(ekf_small_v3)");
+      return check_launch("cudaFuncSetAttribute(ekf_small_v5)");
   }
-  kern<<<(unsigned)blocks, V3_TPB, smem, s>>>(a);
+  kern<<<(unsigned)blocks, V5_TPB, smem, s>>>(a, maps);
   note_launch();
-  return check_launch("ekf_small_v3");
+  return check_launch("ekf_small_v5");
 }
 
 template <typename T, class Drift, int NY>

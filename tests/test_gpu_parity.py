@@ -146,6 +146,28 @@ def test_ekf_l63_fast_path_vs_oracle(solver, dt0):
         assert scaled_err(getattr(f, fld), r[fld]) < TOL, fld
 
 
+@pytest.mark.parametrize("N,K", [(1, 1), (3, 7), (225, 33), (500, 64)])
+def test_ekf_l63_fast_path_ragged_shapes(N, K):
+    """Odd / tiny K and N around the 224-slot CTA size: the TMA store path needs even K, the cooperative flush covers
+    the rest; both must give the oracle's numbers."""
+    cd = api()
+    t, y = c3_problem(N, K, seed=7 + N + K)
+    g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]),
+             L=np.eye(3), Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))
+    p = nonlinear_params_api(g)
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    f = cd.cdnlgssm_filter(p, y, t[..., None], hp)
+    po = o.NonlinearParams(m0=g["m0"], P0=g["P0"], drift=make_drift("lorenz63", g["theta"], 3), L=g["L"], Qc=g["Qc"],
+                           H=g["H"], R=g["R"], d=g["d"])
+    r = o.extended_kalman_filter(po, y, t, settings=o.SolverSettings("rk4", 0.0025))
+    assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < TOL
+    for fld in FIELDS:
+        assert scaled_err(getattr(f, fld), r[fld]) < TOL, fld
+    # a subset of outputs (NULL output pointers) must not change the others
+    f2 = cd.cdnlgssm_filter(p, y, t[..., None], hp, output_fields=["predicted_covariances"])
+    assert f2.filtered_means is None and np.array_equal(f2.predicted_covariances, f.predicted_covariances)
+
+
 def test_ekf_l63_fp32_variant_bound():
     """fp32 variant vs the fp64 oracle: stated bound 2e-3 on the scaled error of the moments and 2e-4 relative on the
     log-likelihood over K = 200 steps (the reference's own fp32 'match' ladder tops out at 1e-4, test_utils.py:160-180;
