@@ -491,7 +491,11 @@ __global__ void __launch_bounds__(V5_TPB, 2) ekf_small_v5(const KArgs<T> a, cons
     if (!helper) {
       if (REGROUP && k + 1 < K) sort_scatter(k + 1);
       // ---- worker: update at t_k, then integrate the gap t_k -> t_{k+1}, for the slot assigned to this thread ----
-      const int p = REGROUP ? sm.perm[k & 1][tid] : tid;
+      // Sorted chunk c (32 consecutive ranks, c = 6 has the longest gaps) -> warp: the heavy and light chunks are paired on
+      // the warps that share an SM sub-partition (warp w issues on sub-partition w % 4), the heaviest chunk goes to the
+      // sub-partition that only hosts one worker warp (+ the helper warp), so the four FP64 pipes carry equal work.
+      const int chunk = (0x2106345 >> (4 * (tid >> 5))) & 7;  // warps 0..6 -> chunks 5,4,3,6,0,1,2
+      const int p = REGROUP ? sm.perm[k & 1][chunk * 32 + lane] : tid;
       const bool live = p < nlive;
       const T* par = par_batched ? parbase + (live ? p : 0) * NPAR : parbase;
       const T* th = par;

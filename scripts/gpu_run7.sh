@@ -1,0 +1,5 @@
+set -x
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/r7_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 --simple-data --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/r7_bench_regroup.json
+CDK_EKF_REGROUP=0 timeout 600 python bench.py --steps 5 --warmup 3 --simple-data --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/r7_bench_lockstep.json
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ekf_small -s 2 -c 1 -o gpurun_out/r7_ekf_small python bench.py --steps 1 --warmup 3 --simple-data --no-cpu-baseline > gpurun_out/r7_ncu_full.log 2>&1
