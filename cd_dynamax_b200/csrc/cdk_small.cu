@@ -295,6 +295,9 @@ __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+#ifndef CDK_EKF_DEFAULT_MODE
+#define CDK_EKF_DEFAULT_MODE 0
+#endif
 constexpr int V5_W = 224;         // worker threads (7 warps) = trajectory slots per CTA
 constexpr int V5_TPB = 256;       // + 1 helper warp; 2 CTAs / SM (128 registers / thread)
 constexpr int V5_LD = V5_W + 1;   // SoA row stride of the input rings (odd: conflict-free)
@@ -614,6 +617,205 @@ __global__ void __launch_bounds__(V5_TPB, 2) ekf_small_v5(const KArgs<T> a, cons
   }
 }
 
+// ======================================================================================================================
+// Variant B: INDEPENDENT WARPS.  One warp = one CTA = 32 trajectories kept for the whole kernel; the filter state never
+// leaves registers, every gap runs to the warp-wide maximum substep count (predicated lanes, 4.5/6 = 75 % lane efficiency
+// on the benchmark grid) -- but there is no CTA-wide barrier at all, so the ~15 resident warps of an SM drift out of phase
+// and the latency-bound measurement update of one warp hides behind the FP64-bound substeps of the others.  Inputs come
+// through a private 4-deep cp.async ring; each warp stores its own 2-step output block with four TMA tensor stores.
+// ======================================================================================================================
+constexpr int LW_RING = 4;
+
+template <typename T, int NX, int NY>
+struct alignas(128) LWSmem {
+  T fm[32][2][NX];
+  alignas(128) T fp[32][2][NX * NX];
+  alignas(128) T pm[32][2][NX];
+  alignas(128) T pp[32][2][NX * NX];
+  T inY[LW_RING][NY][32];
+  T inT[LW_RING][32];
+  // followed by the model constants: NPAR values (shared) or 32 * NPAR (one block per lane when batched)
+};
+
+template <typename T, class Drift, int NY, int SOLVER>
+__global__ void __launch_bounds__(32) ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps) {
+  constexpr int NX = Drift::NX;
+  constexpr int NP = St<T, NX>::NP;
+  constexpr int NTH = Drift::NTHETA;
+  constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;  // theta | lql (packed) | H | d | R
+  using S = LWSmem<T, NX, NY>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  S& sm = *reinterpret_cast<S*>(smem_raw);
+  T* parbase = reinterpret_cast<T*>(smem_raw + sizeof(S));
+
+  const long long N = a.d.N;
+  const int K = a.d.K;
+  const int lane = threadIdx.x;
+  const long long traj0 = (long long)blockIdx.x * 32;
+  const long long traj = traj0 + lane;
+  const bool live = traj < N;
+  const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
+  const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
+                            (1u << CDK_IN_D) | (1u << CDK_IN_R);
+  const bool par_batched = (a.d.batched_mask & par_mask) != 0;
+  const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0;
+
+  if ((par_batched && live) || (!par_batched && lane == 0)) {
+    T* par = par_batched ? parbase + lane * NPAR : parbase;
+    const long long tj = par_batched ? traj : 0;
+    const T* th = a.in[CDK_IN_F] + tj * a.in_stride[CDK_IN_F];
+    const T* Lm = a.in[CDK_IN_L] + tj * a.in_stride[CDK_IN_L];
+    const T* Qc = a.in[CDK_IN_QC] + tj * a.in_stride[CDK_IN_QC];
+    const T* H = a.in[CDK_IN_H] + tj * a.in_stride[CDK_IN_H];
+    const T* dv = a.in[CDK_IN_D] + tj * a.in_stride[CDK_IN_D];
+    const T* R = a.in[CDK_IN_R] + tj * a.in_stride[CDK_IN_R];
+    for (int i = 0; i < NTH; ++i) par[i] = th[i];
+    for (int i = 0; i < NX; ++i)
+      for (int j = i; j < NX; ++j) {
+        T acc = T(0);
+        for (int p = 0; p < NX; ++p) {
+          T lq = T(0);
+          for (int q = 0; q < NX; ++q) lq += Lm[i * NX + q] * Qc[q * NX + p];
+          acc += lq * Lm[j * NX + p];
+        }
+        par[NTH + pidx<NX>(i, j)] = acc;
+      }
+    for (int i = 0; i < NY * NX; ++i) par[NTH + NP + i] = H[i];
+    for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
+    for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
+  }
+  const T* __restrict__ Yg = a.in[CDK_IN_Y] + (live ? traj : 0) * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Tg = a.in[CDK_IN_T] + (live ? traj : 0) * a.in_stride[CDK_IN_T];
+  auto prefetch = [&](int kk) {
+    if (live && kk < K) {
+#pragma unroll
+      for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (LW_RING - 1)][c][lane], Yg + (long long)kk * NY + c);
+      cp_async_elem(&sm.inT[kk & (LW_RING - 1)][lane], Tg + kk);
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
+  prefetch(1);
+  prefetch(2);
+  St<T, NX> s;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) s.m[i] = T(0);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s.P[i] = T(0);
+  if (live) {
+    const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
+    const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.m[i] = m0[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = P0[i * NX + j];
+  }
+  __syncwarp();
+  const T* par = par_batched ? parbase + lane * NPAR : parbase;
+  const T* th = par;
+  const T* lql = par + NTH;
+  const T* Hs = par + NTH + NP;
+  const T* ds = Hs + NY * NX;
+  const T* Rs = ds + NY;
+  const T dt0 = T(a.d.dt0);
+  const T dtf = T(a.d.dt_final);
+  const T tol = clip_tol<T>();
+  const int max_steps = a.d.max_steps;
+  const int num_iter = a.d.num_iter;
+  T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
+  T ll = T(0);
+  int status = 0;
+
+  for (int k = 0; k < K; ++k) {
+    const int row = k & 1;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");  // own loads of steps <= k+1 have landed
+    T tprev = T(0), t1 = T(0);
+    if (live) {
+      T y[NY];
+#pragma unroll
+      for (int c = 0; c < NY; ++c) y[c] = sm.inY[k & (LW_RING - 1)][c][lane];
+      tprev = sm.inT[k & (LW_RING - 1)][lane];
+      t1 = k + 1 < K ? sm.inT[(k + 1) & (LW_RING - 1)][lane] : tprev + dtf;
+      ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+      if (LLC) LLC[traj * (long long)K + k] = ll;
+    }
+    prefetch(k + 3);
+    if (use_tma && row == 0 && k > 0) {  // the previous block's TMA store must have finished reading the staging rows
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+    if (live) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sm.fm[lane][row][i] = s.m[i];
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) sm.fp[lane][row][i * NX + j] = s.P[pidx<NX>(i, j)];
+      T tnext = fmin(tprev + dt0, t1);
+      int nsteps = 0;
+      while (tprev < t1) {
+        if (nsteps >= max_steps) {
+          status = 2;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
+          break;
+        }
+        rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
+        ++nsteps;
+        tprev = tnext;
+        const T cand = tprev + dt0;
+        tnext = cand > t1 - tol ? t1 : cand;
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) sm.pm[lane][row][i] = s.m[i];
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) sm.pp[lane][row][i * NX + j] = s.P[pidx<NX>(i, j)];
+    }
+    if (row == 1 || k == K - 1) {
+      __syncwarp();
+      if (use_tma) {
+        if (lane == 0) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          const int c1 = (int)traj0;
+          if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], (k - 1) * NX, c1);
+          if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], (k - 1) * NX * NX, c1);
+          if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], (k - 1) * NX, c1);
+          if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], (k - 1) * NX * NX, c1);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      } else {
+        const int k0 = k - row, nrow = row + 1;
+#pragma unroll
+        for (int arr = 0; arr < 4; ++arr) {
+          T* __restrict__ G = static_cast<T*>(
+              a.out[arr == 0 ? CDK_OUT_FM : arr == 1 ? CDK_OUT_FP : arr == 2 ? CDK_OUT_PM : CDK_OUT_PP]);
+          if (!G) continue;
+          const int len = (arr & 1) ? NX * NX : NX;
+          const T* src = arr == 0 ? &sm.fm[0][0][0] : arr == 1 ? &sm.fp[0][0][0] : arr == 2 ? &sm.pm[0][0][0] : &sm.pp[0][0][0];
+          const int per = nrow * len;
+          for (int u = lane; u < nlive * per; u += 32) {
+            const int slot = u / per, e = u - slot * per;
+            G[((traj0 + slot) * (long long)K + k0) * len + e] = src[slot * 2 * len + e];
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (live) {
+    if (status == 0 && !isfinite(ll)) status = 1;
+    if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
+    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
+  }
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -633,7 +835,7 @@ encode_tiled_fn get_encode_tiled() {
 // Build the four output tensor maps.  Returns false when the TMA path does not apply (fp32, odd K, unaligned pointers,
 // CDK_EKF_TMA=0): the kernel then uses the cooperative-copy flush.
 template <typename T>
-bool make_maps(const KArgs<T>& a, int NX, V5Maps& maps) {
+bool make_maps(const KArgs<T>& a, int NX, int box_rows, V5Maps& maps) {
   memset(&maps, 0, sizeof(maps));
   static const bool disabled = []() {
     const char* e = getenv("CDK_EKF_TMA");
@@ -650,7 +852,7 @@ bool make_maps(const KArgs<T>& a, int NX, V5Maps& maps) {
     const cuuint64_t len = (i & 1) ? NX * NX : NX;
     const cuuint64_t gdim[2] = {len * (cuuint64_t)a.d.K, (cuuint64_t)a.d.N};
     const cuuint64_t gstr[1] = {len * (cuuint64_t)a.d.K * sizeof(T)};
-    const cuuint32_t box[2] = {(cuuint32_t)(2 * len), (cuuint32_t)V5_W};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * len), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     if (enc(&maps.m[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, ptr, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -672,14 +874,33 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   const long long blocks = (a.d.N + V5_W - 1) / V5_W;
   if (blocks == 0) return CDK_OK;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
-  // CDK_EKF_REGROUP=0 keeps a fixed thread <-> trajectory assignment (profiling A/B); default is per-step regrouping
-  static const bool regroup = []() {
-    const char* e = getenv("CDK_EKF_REGROUP");
-    return !(e && e[0] == '0');
+  // CDK_EKF_MODE=regroup : CTA-wide per-step regrouping (ekf_small_v5);  lockstep : same kernel, fixed assignment;
+  //              warp    : independent warps (ekf_small_lw).
+  static const int mode = []() {
+    const char* e = getenv("CDK_EKF_MODE");
+    if (e && e[0] == 'r') return 0;
+    if (e && e[0] == 'l') return 1;
+    if (e && e[0] == 'w') return 2;
+    return CDK_EKF_DEFAULT_MODE;
   }();
   V5Maps maps;
-  make_maps<T>(a, NX, maps);
-  auto kern = regroup ? ekf_small_v5<T, Drift, NY, SOLVER, true> : ekf_small_v5<T, Drift, NY, SOLVER, false>;
+  if (mode == 2) {
+    using SW = LWSmem<T, NX, NY>;
+    const size_t smw = sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1);
+    const long long wblocks = (a.d.N + 31) / 32;
+    if (wblocks > 2147483647LL) return CDK_E_SIZE;
+    make_maps<T>(a, NX, 32, maps);
+    auto kw = ekf_small_lw<T, Drift, NY, SOLVER>;
+    if (smw > 48 * 1024) {
+      if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
+    }
+    kw<<<(unsigned)wblocks, 32, smw, s>>>(a, maps);
+    note_launch();
+    return check_launch("ekf_small_lw");
+  }
+  make_maps<T>(a, NX, V5_W, maps);
+  auto kern = mode == 0 ? ekf_small_v5<T, Drift, NY, SOLVER, true> : ekf_small_v5<T, Drift, NY, SOLVER, false>;
   if (smem > 48 * 1024) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(ekf_small_v5)");
