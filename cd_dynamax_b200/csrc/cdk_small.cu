@@ -618,7 +618,8 @@ __global__ void __launch_bounds__(V5_TPB, 2) ekf_small_v5(const KArgs<T> a, cons
 }
 
 // ======================================================================================================================
-// Variant B: INDEPENDENT WARPS.  One warp = one CTA = 32 trajectories kept for the whole kernel; the filter state never
+// Variant B: INDEPENDENT WARPS.  One warp = 32 trajectories kept for the whole kernel (7 such warps share a CTA only to
+// get an even 2-CTAs-per-SM placement; they never synchronise with each other); the filter state never
 // leaves registers, every gap runs to the warp-wide maximum substep count (predicated lanes, 4.5/6 = 75 % lane efficiency
 // on the benchmark grid) -- but there is no CTA-wide barrier at all, so the ~15 resident warps of an SM drift out of phase
 // and the latency-bound measurement update of one warp hides behind the FP64-bound substeps of the others.  Inputs come
@@ -637,21 +638,26 @@ struct alignas(128) LWSmem {
   // followed by the model constants: NPAR values (shared) or 32 * NPAR (one block per lane when batched)
 };
 
+constexpr int LW_WPC = 7;  // independent warps per CTA: 293 CTAs of 224 trajectories = 2 CTAs / SM in one wave
+
 template <typename T, class Drift, int NY, int SOLVER>
-__global__ void __launch_bounds__(32) ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps) {
+__global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps,
+                                                               const int warp_bytes) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
   constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;  // theta | lql (packed) | H | d | R
   using S = LWSmem<T, NX, NY>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  S& sm = *reinterpret_cast<S*>(smem_raw);
-  T* parbase = reinterpret_cast<T*>(smem_raw + sizeof(S));
+  const int warp = threadIdx.x >> 5;
+  S& sm = *reinterpret_cast<S*>(smem_raw + (size_t)warp * warp_bytes);  // every warp owns a private slice
+  T* parbase = reinterpret_cast<T*>(smem_raw + (size_t)warp * warp_bytes + sizeof(S));
 
   const long long N = a.d.N;
   const int K = a.d.K;
-  const int lane = threadIdx.x;
-  const long long traj0 = (long long)blockIdx.x * 32;
+  const int lane = threadIdx.x & 31;
+  const long long traj0 = ((long long)blockIdx.x * LW_WPC + warp) * 32;
+  if (traj0 >= N) return;  // whole warp out of range (warps never synchronise with each other)
   const long long traj = traj0 + lane;
   const bool live = traj < N;
   const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
@@ -886,8 +892,9 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   V5Maps maps;
   if (mode == 2) {
     using SW = LWSmem<T, NX, NY>;
-    const size_t smw = sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1);
-    const long long wblocks = (a.d.N + 31) / 32;
+    const int warp_bytes = (int)((sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1) + 127) & ~size_t(127));
+    const size_t smw = (size_t)warp_bytes * LW_WPC;
+    const long long wblocks = (a.d.N + 32 * LW_WPC - 1) / (32 * LW_WPC);
     if (wblocks > 2147483647LL) return CDK_E_SIZE;
     make_maps<T>(a, NX, 32, maps);
     auto kw = ekf_small_lw<T, Drift, NY, SOLVER>;
@@ -895,7 +902,7 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
       if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw) != cudaSuccess)
         return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
     }
-    kw<<<(unsigned)wblocks, 32, smw, s>>>(a, maps);
+    kw<<<(unsigned)wblocks, 32 * LW_WPC, smw, s>>>(a, maps, warp_bytes);
     note_launch();
     return check_launch("ekf_small_lw");
   }
