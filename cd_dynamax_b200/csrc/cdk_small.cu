@@ -120,7 +120,9 @@ __device__ __forceinline__ void rk_step(const T* th, const T* lql, St<T, Drift::
 // sh: H[NY*NX], d[NY], R[NY*NY] in shared memory.
 template <typename T, int NX, int NY>
 __device__ __forceinline__ T ekf_update(const T* H, const T* dvec, const T* R, St<T, NX>& s, const T (&y)[NY],
-                                        int num_iter) {
+                                        int num_iter, T* s_defer = nullptr) {
+  // s_defer (scalar emission only): the caller accumulates log S itself (as the log of a running product, one log per
+  // 8 steps instead of one per step); the returned increment then omits the -log(S)/2 term and *s_defer = S.
   T ll = T(0);
   if constexpr (NY == 1) {
     // Scalar emission: the 1x1 Cholesky / triangular solves collapse to two independent reciprocals and one log, which
@@ -143,7 +145,14 @@ __device__ __forceinline__ T ekf_update(const T* H, const T* dvec, const T* R, S
       }
       const T r = y[0] - hm;
       const T rb = T(1) / (S + T(1e-9));
-      if (it == 0) ll = T(-0.5) * (r * r / S) - T(0.5) * log(S) - half_log_2pi<T>();
+      if (it == 0) {
+        if (s_defer) {
+          *s_defer = S;
+          ll = T(-0.5) * (r * r / S) - half_log_2pi<T>();
+        } else {
+          ll = T(-0.5) * (r * r / S) - T(0.5) * log(S) - half_log_2pi<T>();
+        }
+      }
       T Kt[NX];
 #pragma unroll
       for (int j = 0; j < NX; ++j) Kt[j] = HP[j] * rb;
@@ -296,7 +305,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 #ifndef CDK_EKF_DEFAULT_MODE
-#define CDK_EKF_DEFAULT_MODE 0
+#define CDK_EKF_DEFAULT_MODE 2
 #endif
 constexpr int V5_W = 224;         // worker threads (7 warps) = trajectory slots per CTA
 constexpr int V5_TPB = 256;       // + 1 helper warp; 2 CTAs / SM (128 registers / thread)
@@ -731,8 +740,21 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
   const int max_steps = a.d.max_steps;
   const int num_iter = a.d.num_iter;
   T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
-  T ll = T(0);
+  T ll = T(0), sprod = T(1);
+  bool sbad = false;
   int status = 0;
+  auto tma_pair = [&](int first, int k0) {  // lane 0: store arrays {first, first + 1} of the block starting at step k0
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    const int c1 = (int)traj0;
+    if (first == 0) {
+      if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], k0 * NX, c1);
+      if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], k0 * NX * NX, c1);
+    } else {
+      if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], k0 * NX, c1);
+      if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], k0 * NX * NX, c1);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  };
 
   for (int k = 0; k < K; ++k) {
     const int row = k & 1;
@@ -744,12 +766,29 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
       for (int c = 0; c < NY; ++c) y[c] = sm.inY[k & (LW_RING - 1)][c][lane];
       tprev = sm.inT[k & (LW_RING - 1)][lane];
       t1 = k + 1 < K ? sm.inT[(k + 1) & (LW_RING - 1)][lane] : tprev + dtf;
-      ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
-      if (LLC) LLC[traj * (long long)K + k] = ll;
+      if (NY == 1 && !LLC) {
+        // sum_k log S_k = log prod_k S_k, folded every 8 steps (factors outside [1e-8, 1e8] take the direct log); a
+        // non-positive S (non-PD covariance) must still poison the log-likelihood as log() would.
+        T Sk;
+        ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter, &Sk);
+        if (!(Sk > T(0))) sbad = true;
+        if (Sk > T(1e-8) && Sk < T(1e8)) {
+          sprod *= Sk;  // at most 8 (fp32: 4) factors in [1e-8, 1e8]: no overflow / underflow
+        } else {
+          ll -= T(0.5) * log(Sk);
+        }
+        if ((k & (sizeof(T) == 8 ? 7 : 3)) == (sizeof(T) == 8 ? 7 : 3)) {
+          ll -= T(0.5) * log(sprod);
+          sprod = T(1);
+        }
+      } else {
+        ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+        if (LLC) LLC[traj * (long long)K + k] = ll;
+      }
     }
     prefetch(k + 3);
-    if (use_tma && row == 0 && k > 0) {  // the previous block's TMA store must have finished reading the staging rows
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (use_tma && row == 0 && k > 0) {  // the FM/FP store of the previous block was issued ~6 substeps ago
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
     if (live) {
@@ -759,6 +798,12 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
       for (int i = 0; i < NX; ++i)
 #pragma unroll
         for (int j = 0; j < NX; ++j) sm.fp[lane][row][i * NX + j] = s.P[pidx<NX>(i, j)];
+    }
+    if (use_tma && row == 1) {  // the filtered rows of this block are complete: store them while the gap is integrated
+      __syncwarp();
+      if (lane == 0) tma_pair(0, k - 1);
+    }
+    if (live) {
       T tnext = fmin(tprev + dt0, t1);
       int nsteps = 0;
       while (tprev < t1) {
@@ -776,6 +821,12 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
         const T cand = tprev + dt0;
         tnext = cand > t1 - tol ? t1 : cand;
       }
+    }
+    if (use_tma && row == 0 && k > 0) {  // the PM/PP store of the previous block was issued one whole step ago
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+    if (live) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) sm.pm[lane][row][i] = s.m[i];
 #pragma unroll
@@ -786,15 +837,7 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
     if (row == 1 || k == K - 1) {
       __syncwarp();
       if (use_tma) {
-        if (lane == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          const int c1 = (int)traj0;
-          if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], (k - 1) * NX, c1);
-          if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], (k - 1) * NX * NX, c1);
-          if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], (k - 1) * NX, c1);
-          if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], (k - 1) * NX * NX, c1);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
+        if (lane == 0) tma_pair(2, k - 1);
       } else {
         const int k0 = k - row, nrow = row + 1;
 #pragma unroll
@@ -816,6 +859,8 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
   }
   if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (live) {
+    ll -= T(0.5) * log(sprod);
+    if (sbad) ll = T(NAN);
     if (status == 0 && !isfinite(ll)) status = 1;
     if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
     if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
