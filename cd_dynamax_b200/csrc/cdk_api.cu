@@ -254,10 +254,7 @@ CDK_DEF(cdk_enkf_filter_f32, float, ALGO_ENKF_FILTER)
 
 size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point) {
   if (!d || !entry_point) return 0;
-  if (strncmp(entry_point, "enkf_filter", 11) == 0 || strncmp(entry_point, "cdk_enkf_filter", 15) == 0) {
-    // two copies of the ensemble + emission ensemble per trajectory, sized for the wider dtype
-    return (size_t)d->N * (size_t)d->E * (size_t)(2 * d->n + d->m) * sizeof(double);
-  }
+  // no entry point needs device scratch today: the EnKF keeps its ensemble in (distributed) shared memory
   return 0;
 }
 

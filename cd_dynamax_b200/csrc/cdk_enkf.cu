@@ -1,11 +1,605 @@
-// cdk_enkf.cu -- CD-EnKF (placeholder until the ensemble kernel lands).
-#include "cdk_common.cuh"
+// cdk_enkf.cu -- continuous-discrete ensemble Kalman filter: ONE THREAD-BLOCK CLUSTER PER TRAJECTORY.
+//
+// Replaces ensemble_kalman_filter (src/continuous_discrete_nonlinear_gaussian_ssm/inference_enkf.py:151-276) with its
+// _predict (:47-89, per-member SDE solve) and _condition_on (:92-148, stochastic perturbed-observation update).
+// The reference draws from jax.random (threefry) and a diffrax VirtualBrownianTree, neither reproducible outside JAX;
+// this kernel and the CPU oracle share a counter-based Philox4x32-10 stream instead (oracle/cd_oracle.py enkf_normals),
+// so parity against the oracle is to rounding and parity against the reference is distributional (as in its own test,
+// src/test_scripts/cdnlgssm_test_filter_linear_TRegular.py:434-470).
+//
+// B200 mapping (BASELINE config 5: n = 40, m = 20, E = 1,024 members, N = 1,024 trajectories, K = 500):
+//  * the ensemble X[n][E] (320 KB in fp64) does not fit one SM's shared memory, so a trajectory is owned by a CLUSTER of
+//    C CTAs (C = 4 here), each keeping E/C members resident in shared memory for the whole kernel (dimension-major, so
+//    member-per-thread accesses are conflict-free).  Nothing but the per-step moments ever goes to HBM.
+//  * per-member work (Philox + Box-Muller noise, drift, Euler-Maruyama / Heun step, gain application) is one thread per
+//    member with the member's state in registers;
+//  * the E-contractions -- the ensemble covariance X'X'^T that every step needs twice (filtered and predicted moments;
+//    the predicted one also yields C_xy = C_xx H^T and C_yy = H C_xx H^T of the next update because h is linear) -- run
+//    on the FP64 TENSOR CORES (mma.sync m8n8k4 f64, SASS DMMA): each warp owns whole 8x8 output tiles and sweeps the
+//    members, anomalies are formed on the fly in the fragment loads.  tcgen05 has no FP64 kind; DMMA is the FP64 tensor
+//    path on sm_100a (measured 37.1 TFLOP/s = the FMA-pipe peak, but at 1/16 of the instruction count);
+//  * CTA partial sums / partial covariances are combined through distributed shared memory (cluster.map_shared_rank),
+//    every CTA summing the partials in rank order so that all CTAs of the cluster hold bit-identical moments and can run
+//    the small (m x m) gain algebra redundantly without another exchange.
+#include <cooperative_groups.h>
+
+#include <stdlib.h>
+
+#include "cdk_dense.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace cdk {
-template <typename T>
-int launch_enkf(const KArgs<T>&, cudaStream_t) {
-  return CDK_E_UNSUPPORTED;
+namespace {
+
+constexpr int ENKF_TPB = 256;
+enum { RNG_INIT = 0, RNG_OBS = 1, RNG_DYN = 2 };
+
+// ---- Philox4x32-10 + Box-Muller: bit-identical to oracle/cd_oracle.py philox4x32 / philox_normal_pair ----------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&r)[4]) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  r[0] = c0;
+  r[1] = c1;
+  r[2] = c2;
+  r[3] = c3;
 }
+
+// two standard normals for (member, trajectory, step, stream | substep | pair)
+__device__ __noinline__ void normal_pair(uint32_t member, uint32_t traj, uint32_t step, uint32_t c3, uint64_t seed,
+                                            double& z0, double& z1) {
+  uint32_t r[4];
+  philox4x32_10(member, traj, step, c3, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), r);
+  const double u1 = ((double)(r[0] >> 5) * 67108864.0 + (double)(r[1] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(r[2] >> 5) * 67108864.0 + (double)(r[3] >> 6) + 0.5) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincos(6.283185307179586 * u2, &s, &c);
+  z0 = rad * c;
+  z1 = rad * s;
+}
+
+__device__ __forceinline__ uint32_t rng_c3(int stream, int substep, int pair) {
+  return ((uint32_t)stream << 28) | (((uint32_t)substep & 0xFFFFFu) << 8) | (uint32_t)pair;
+}
+
+// ---- shared-memory layout (identical on host and device) -----------------------------------------------------------
+struct ELay {
+  int n, m, ldn, ldm, ldE, nth;
+  // byte offsets
+  size_t X, PSUM, CPART, CXX, MEAN, H, R, CHR, DV, G, HP, S, SL, KT, SK, YV, RV, TH, MISC, total;
+  __host__ __device__ ELay(int n_, int m_, int nth_, int Eloc, size_t ts) {
+    n = n_; m = m_; nth = nth_;
+    ldn = ldp(n); ldm = ldp(m);
+    ldE = ((Eloc + 31) / 32) * 32 + 4;  // = 4 (mod 32): DMMA fragment loads X[i0 + gid][e0 + tig] are conflict-free
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) & ~size_t(15); return r; };
+    X = take(ts * n * ldE);
+    PSUM = take(8 * n);
+    CPART = take(8 * n * ldn);
+    CXX = take(ts * n * ldn);
+    MEAN = take(ts * n);
+    H = take(ts * m * ldn);
+    R = take(ts * m * ldm);
+    CHR = take(ts * m * ldm);
+    DV = take(ts * m);
+    G = take(ts * n * ldn);
+    HP = take(ts * m * ldn);
+    S = take(ts * m * ldm);
+    SL = take(ts * m * ldm);
+    KT = take(ts * m * ldn);
+    SK = take(ts * (m > n ? m : n) * ldn);
+    YV = take(ts * m);
+    RV = take(ts * 2 * m);
+    TH = take(ts * (nth > 0 ? nth : 1));
+    MISC = take(64);
+    total = o;
+  }
+};
+
+template <typename T>
+struct EArgs {
+  KArgs<T> k;
+  int C;     // cluster size (CTAs per trajectory)
+  int Eloc;  // members per CTA (the last CTA may own fewer)
+};
+
+// ---- FP64 tensor-core partial covariance ----------------------------------------------------------------------------
+// Cp[i][j] = sum over this CTA's members e of (X[i][e] - mu[i]) (X[j][e] - mu[j]), i, j < n (full symmetric matrix written).
+// mma.sync.m8n8k4.f64: A (8x4, row) lane -> (row gid = lane/4, col tig = lane%4); B (4x8, col) lane -> (row tig, col gid);
+// C/D (8x8) lane -> (row gid, cols 2*tig, 2*tig+1).  With A = X'[i-block][members], B = X'[members][j-block] both
+// fragments are the SAME load pattern X[blk*8 + gid][e0 + tig].
+template <typename T>
+__device__ void cov_partial_dmma(const T* __restrict__ X, int ldE, int nmem, const T* __restrict__ mu, int n,
+                                 double* __restrict__ Cp, int ldc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int nb = (n + 7) >> 3;
+  const int ntile = nb * (nb + 1) / 2;
+  const int nk = (nmem + 3) & ~3;
+  for (int t = warp; t < ntile; t += nwarp) {
+    // upper-triangular tile index t -> (bi <= bj)
+    int bi = 0, rem = t;
+    while (rem >= nb - bi) {
+      rem -= nb - bi;
+      ++bi;
+    }
+    const int bj = bi + rem;
+    const int ia = bi * 8 + gid, jb = bj * 8 + gid;
+    const bool va = ia < n, vb = jb < n;
+    const T* xa = X + (size_t)(va ? ia : 0) * ldE;
+    const T* xb = X + (size_t)(vb ? jb : 0) * ldE;
+    const double ma = va ? (double)mu[ia] : 0.0, mb = vb ? (double)mu[jb] : 0.0;
+    double d[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};  // 4 independent accumulator sets (k-steps interleaved)
+    for (int e0 = 0; e0 < nk; e0 += 16) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + 4 * u + tig;
+        const bool ve = e < nmem;
+        const double av = (va && ve) ? (double)xa[e] - ma : 0.0;
+        const double bv = (vb && ve) ? (double)xb[e] - mb : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(d[u][0]), "+d"(d[u][1])
+                     : "d"(av), "d"(bv));
+      }
+    }
+    const double c0 = (d[0][0] + d[1][0]) + (d[2][0] + d[3][0]);
+    const double c1 = (d[0][1] + d[1][1]) + (d[2][1] + d[3][1]);
+    const int ri = bi * 8 + gid, cj = bj * 8 + 2 * tig;
+    if (ri < n) {
+      if (cj < n) {
+        Cp[ri * ldc + cj] = c0;
+        Cp[cj * ldc + ri] = c0;
+      }
+      if (cj + 1 < n) {
+        Cp[ri * ldc + cj + 1] = c1;
+        Cp[(cj + 1) * ldc + ri] = c1;
+      }
+    }
+  }
+}
+
+// Ensemble mean and covariance (divided by E - 1) of the whole cluster's members; result in sh MEAN / CXX of EVERY CTA.
+template <typename T>
+__device__ void moments(cg::cluster_group& cluster, const ELay& L, unsigned char* sh, int nmem, int E, int C) {
+  const int n = L.n, ldn = L.ldn;
+  T* X = reinterpret_cast<T*>(sh + L.X);
+  double* psum = reinterpret_cast<double*>(sh + L.PSUM);
+  double* Cp = reinterpret_cast<double*>(sh + L.CPART);
+  T* Cxx = reinterpret_cast<T*>(sh + L.CXX);
+  T* mean = reinterpret_cast<T*>(sh + L.MEAN);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int i = warp; i < n; i += nwarp) {
+    double s = 0.0;
+    for (int e = lane; e < nmem; e += 32) s += (double)X[(size_t)i * L.ldE + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) psum[i] = s;
+  }
+  cluster.sync();
+  FOR_T(i, n) {
+    double s = 0.0;
+    for (int r = 0; r < C; ++r) s += cluster.map_shared_rank(psum, r)[i];
+    mean[i] = (T)(s / (double)E);
+  }
+  __syncthreads();
+  cov_partial_dmma<T>(X, L.ldE, nmem, mean, n, Cp, ldn);
+  cluster.sync();
+  const double inv = 1.0 / (double)(E - 1);
+  FOR_T(idx, n * n) {
+    const int i = idx / n, j = idx - i * n;
+    if (i <= j) {
+      double s = 0.0;
+      for (int r = 0; r < C; ++r) s += cluster.map_shared_rank(Cp, r)[i * ldn + j];
+      const T v = (T)(s * inv);
+      Cxx[i * ldn + j] = v;
+      Cxx[j * ldn + i] = v;
+    }
+  }
+  cluster.sync();  // nobody may overwrite psum / Cp (next moments call) or read a stale Cxx before everyone is done
+}
+
+// ---- per-member drift on a thread-private state ---------------------------------------------------------------------
+// NX > 0 fixes the drift at compile time (NX = 40: Lorenz-96, NX = 3: Lorenz-63) so that fully unrolled code stays small.
+template <typename T, int NX>
+__device__ __forceinline__ T member_f(int drift_id, const T* th, int n, int i, const T* x) {
+  if (NX == 3) {
+    if (i == 0) return th[0] * (x[1] - x[0]);
+    if (i == 1) return x[0] * (th[1] - x[2]) - x[1];
+    return x[0] * x[1] - th[2] * x[2];
+  }
+  if (NX > 3) {
+    const int ip = i + 1 == n ? 0 : i + 1, im1 = i == 0 ? n - 1 : i - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
+    return (x[ip] - x[im2]) * x[im1] - x[i] + th[0];
+  }
+  return drift_f<T>(drift_id, th, n, i, [&](int j) { return x[j]; });
+}
+
+// NX > 0: compile-time state dimension (member state in registers, loops unrolled); NX == 0: runtime n <= CDK_MAX_N
+// (thread-private arrays in local memory).
+template <typename T, int NX>
+__global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
+  constexpr int NXA = NX > 0 ? NX : CDK_MAX_N;
+  constexpr int UF = NX > 0 ? NX : 1;             // unroll factor of loops over the state dimension
+  constexpr int UFP = NX > 0 ? (NX + 1) / 2 : 1;  // ... over normal pairs
+  extern __shared__ __align__(16) unsigned char sh[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const KArgs<T>& a = g.k;
+  const cdk_desc& d = a.d;
+  const int n = NX > 0 ? NX : d.n, m = d.m, K = d.K, E = d.E, C = g.C;
+  const int rank = (int)cluster.block_rank();
+  const long long traj = blockIdx.x / C;
+  const ELay L(n, m, d.n_theta, g.Eloc, sizeof(T));
+  const int ldn = L.ldn, ldm = L.ldm, ldE = L.ldE;
+  const int e_base = rank * g.Eloc;
+  const int nmem = max(0, min(g.Eloc, E - e_base));
+  T* X = reinterpret_cast<T*>(sh + L.X);
+  T* Cxx = reinterpret_cast<T*>(sh + L.CXX);
+  T* mean = reinterpret_cast<T*>(sh + L.MEAN);
+  T* H = reinterpret_cast<T*>(sh + L.H);
+  T* R = reinterpret_cast<T*>(sh + L.R);
+  T* chR = reinterpret_cast<T*>(sh + L.CHR);
+  T* dv = reinterpret_cast<T*>(sh + L.DV);
+  T* G = reinterpret_cast<T*>(sh + L.G);
+  T* HP = reinterpret_cast<T*>(sh + L.HP);
+  T* Sm = reinterpret_cast<T*>(sh + L.S);
+  T* Sl = reinterpret_cast<T*>(sh + L.SL);
+  T* Kt = reinterpret_cast<T*>(sh + L.KT);
+  T* SK = reinterpret_cast<T*>(sh + L.SK);
+  T* yv = reinterpret_cast<T*>(sh + L.YV);
+  T* rv = reinterpret_cast<T*>(sh + L.RV);
+  T* zv = rv + m;
+  T* th = reinterpret_cast<T*>(sh + L.TH);
+  int* misc = reinterpret_cast<int*>(sh + L.MISC);
+  T* llsh = reinterpret_cast<T*>(sh + L.MISC + 16);
+
+  auto src = [&](int slot) { return a.in[slot] + traj * a.in_stride[slot]; };
+  const uint32_t ctr_traj = (uint32_t)(((unsigned long long)traj + d.rng_offset) & 0xffffffffull);
+  const uint64_t seed = d.rng_seed;
+
+  // ---- model constants: G = L chol(Qc) (inference_enkf.py:74-80), chol(R) for the perturbed observations (:135) ----
+  FOR_T(e, (int)(L.total / sizeof(T)) - (int)(L.CXX / sizeof(T))) reinterpret_cast<T*>(sh + L.CXX)[e] = T(0);
+  __syncthreads();
+  FOR_T(i, d.n_theta) th[i] = src(CDK_IN_F)[i];
+  {
+    T* Lm = SK;   // [n x ldn] scratch
+    T* Qc = Cxx;  // scratch until the first moments(); receives the product L chol(Qc) after the factorisation
+    T* Lq = G;    // chol(Qc)
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      Lm[i * ldn + j] = src(CDK_IN_L)[e];
+      Qc[i * ldn + j] = src(CDK_IN_QC)[e];
+    }
+    FOR_T(e, m * n) {
+      const int i = e / n, j = e - i * n;
+      H[i * ldn + j] = src(CDK_IN_H)[e];
+    }
+    FOR_T(e, m * m) {
+      const int i = e / m, j = e - i * m;
+      R[i * ldm + j] = src(CDK_IN_R)[e];
+    }
+    FOR_T(i, m) dv[i] = src(CDK_IN_D)[i];
+    __syncthreads();
+    chol<T>(Qc, Lq, n, ldn, T(0));  // Lq = chol(Qc) in G
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      T s = T(0);
+      for (int q = j; q < n; ++q) s += Lm[i * ldn + q] * Lq[q * ldn + j];
+      Qc[i * ldn + j] = s;  // Qc no longer needed after the factorisation
+    }
+    __syncthreads();
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      G[i * ldn + j] = Qc[i * ldn + j];
+    }
+    chol<T>(R, chR, m, ldm, T(0));
+    __syncthreads();
+  }
+  // diagonal diffusion? (then the noise is G_ii dW_i: no n x n product per member and substep)
+  int offdiag = 0;
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    if (i != j && G[i * ldn + j] != T(0)) offdiag = 1;
+  }
+  const bool diagG = __syncthreads_or(offdiag) == 0;
+
+  // ---- initial ensemble: m0 + chol(P0) z (inference_enkf.py:260-262) ----
+  {
+    T* P0 = Cxx;
+    T* Lp = SK;
+    FOR_T(e, n * n) {
+      const int i = e / n, j = e - i * n;
+      P0[i * ldn + j] = src(CDK_IN_P0)[e];
+    }
+    FOR_T(i, n) mean[i] = src(CDK_IN_M0)[i];
+    __syncthreads();
+    chol<T>(P0, Lp, n, ldn, T(0));
+    for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
+      T z[NXA];
+#pragma unroll UFP
+      for (int j = 0; j < NXA; j += 2) {
+        if (j < n) {
+          double z0, z1;
+          normal_pair((uint32_t)(e_base + el), ctr_traj, 0u, rng_c3(RNG_INIT, 0, j >> 1), seed, z0, z1);
+          z[j] = (T)z0;
+          if (j + 1 < NXA) z[j + 1] = (T)z1;
+        }
+      }
+#pragma unroll UF
+      for (int i = 0; i < NXA; ++i) {
+        if (i < n) {
+          T s = T(0);
+#pragma unroll UF
+          for (int j = 0; j < NXA; ++j)
+            if (j <= i) s += Lp[i * ldn + j] * z[j];
+          X[(size_t)i * ldE + el] = mean[i] + s;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  moments<T>(cluster, L, sh, nmem, E, C);
+
+  const T* Y = src(CDK_IN_Y);
+  const T* Tm = src(CDK_IN_T);
+  T* FM = static_cast<T*>(a.out[CDK_OUT_FM]);
+  T* FP = static_cast<T*>(a.out[CDK_OUT_FP]);
+  T* PM = static_cast<T*>(a.out[CDK_OUT_PM]);
+  T* PP = static_cast<T*>(a.out[CDK_OUT_PP]);
+  T* LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
+  const long long row0 = traj * (long long)K;
+  const T dt0 = T(d.dt0);
+  const T tol = clip_tol<T>();
+  T ll = T(0);
+  int status = 0;
+
+  auto write_moments = [&](T* Mo, T* Co, long long row) {
+    if (rank != 0) return;
+    if (Mo) FOR_T(i, n) Mo[row * n + i] = mean[i];
+    if (Co) FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        Co[row * n * n + e] = Cxx[i * ldn + j];
+      }
+  };
+
+  for (int k = 0; k < K; ++k) {
+    // ================= update (inference_enkf.py:92-148), every CTA of the cluster redundantly =================
+    FOR_T(i, m) yv[i] = Y[(long long)k * m + i];
+    FOR_T(e, m * n) {  // HP = H Cxx  (= C_xy^T because h is linear)
+      const int p = e / n, j = e - p * n;
+      T s = T(0);
+      for (int q = 0; q < n; ++q) s += H[p * ldn + q] * Cxx[q * ldn + j];
+      HP[p * ldn + j] = s;
+    }
+    __syncthreads();
+    FOR_T(e, m * m) {  // S = H Cxx H^T + R
+      const int p = e / m, q2 = e - p * m;
+      T s = T(0);
+      for (int q = 0; q < n; ++q) s += HP[p * ldn + q] * H[q2 * ldn + q];
+      Sm[p * ldm + q2] = s + R[p * ldm + q2];
+    }
+    FOR_T(p, m) {  // innovation of the ensemble mean
+      T s = dv[p];
+      for (int q = 0; q < n; ++q) s += H[p * ldn + q] * mean[q];
+      rv[p] = yv[p] - s;
+    }
+    __syncthreads();
+    chol<T>(Sm, Sl, m, ldm, T(0));  // MVN(ybar, S).log_prob(y): un-boosted Cholesky (:129)
+    if (threadIdx.x == 0) {
+      T quad = T(0), logdet = T(0);
+      for (int i = 0; i < m; ++i) {
+        T v = rv[i];
+        for (int q = 0; q < i; ++q) v -= Sl[i * ldm + q] * zv[q];
+        v /= Sl[i * ldm + i];
+        zv[i] = v;
+        quad += v * v;
+        logdet += log(Sl[i * ldm + i]);
+      }
+      *llsh = T(-0.5) * quad - logdet - T(m) * half_log_2pi<T>();
+    }
+    // K^T = psd_solve(S, C_xy^T): chol(sym(S) + 1e-9 I)  (:141-143)
+    T* Sb = SK;
+    FOR_T(e, m * m) {
+      const int p = e / m, q2 = e - p * m;
+      Sb[p * ldm + q2] = T(0.5) * (Sm[p * ldm + q2] + Sm[q2 * ldm + p]);
+    }
+    __syncthreads();
+    ll += *llsh;
+    chol<T>(Sb, Sl, m, ldm, T(1e-9));
+    FOR_T(e, m * n) {
+      const int p = e / n, j = e - p * n;
+      Kt[p * ldn + j] = HP[p * ldn + j];
+    }
+    __syncthreads();
+    chol_solve<T>(Sl, m, ldm, Kt, n, ldn);
+    // per member: x += K ((y + chol(R) z) - (H x + d))   (:135-146)
+    for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
+      T x[NXA];
+#pragma unroll UF
+      for (int i = 0; i < NXA; ++i)
+        if (i < n) x[i] = X[(size_t)i * ldE + el];
+      T r[CDK_MAX_M];
+      if (d.perturb_measurements) {
+        for (int p = 0; p < m; p += 2) {
+          double z0, z1;
+          normal_pair((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_OBS, 0, p >> 1), seed, z0, z1);
+          r[p] = (T)z0;
+          if (p + 1 < m) r[p + 1] = (T)z1;
+        }
+        for (int p = m - 1; p >= 0; --p) {  // r <- chol(R) z, in place from the bottom row up
+          T s = T(0);
+          for (int q = 0; q <= p; ++q) s += chR[p * ldm + q] * r[q];
+          r[p] = s;
+        }
+      } else {
+        for (int p = 0; p < m; ++p) r[p] = T(0);
+      }
+      for (int p = 0; p < m; ++p) {
+        T hx = dv[p];
+#pragma unroll UF
+        for (int i = 0; i < NXA; ++i)
+          if (i < n) hx += H[p * ldn + i] * x[i];
+        r[p] = (yv[p] + r[p]) - hx;
+      }
+      for (int p = 0; p < m; ++p) {
+        const T rp = r[p];
+#pragma unroll UF
+        for (int i = 0; i < NXA; ++i)
+          if (i < n) x[i] += Kt[p * ldn + i] * rp;
+      }
+#pragma unroll UF
+      for (int i = 0; i < NXA; ++i)
+        if (i < n) X[(size_t)i * ldE + el] = x[i];
+    }
+    __syncthreads();
+    moments<T>(cluster, L, sh, nmem, E, C);  // filtered moments (:225-228)
+    write_moments(FM, FP, row0 + k);
+    if (LLC && rank == 0 && threadIdx.x == 0) LLC[row0 + k] = ll;
+
+    // ================= predict (inference_enkf.py:47-89): per-member SDE solve over the gap =================
+    const T t0 = Tm[k];
+    const T t1 = k + 1 < K ? Tm[k + 1] : t0 + T(d.dt_final);
+    T tprev = t0;
+    T tnext = fmin(t0 + dt0, t1);
+    int nsteps = 0;
+    while (tprev < t1) {
+      if (nsteps >= d.max_steps) {  // diffrax max_steps exceeded: poison the ensemble, abandon the gap
+        status = 2;
+        for (int el = threadIdx.x; el < nmem; el += blockDim.x)
+          for (int i = 0; i < n; ++i) X[(size_t)i * ldE + el] = T(NAN);
+        break;
+      }
+      const T dt = tnext - tprev;
+      const T sqdt = sqrt(dt);
+      for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
+        T x[NXA], xe[NXA];  // xe first holds the noise G dW, then the Euler-Maruyama state
+#pragma unroll UF
+        for (int i = 0; i < NXA; ++i)
+          if (i < n) x[i] = X[(size_t)i * ldE + el];
+        if (diagG) {
+#pragma unroll UFP
+          for (int j = 0; j < NXA; j += 2) {
+            if (j < n) {
+              double z0, z1;
+              normal_pair((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 1), seed, z0, z1);
+              xe[j] = G[j * ldn + j] * (sqdt * (T)z0);
+              if (j + 1 < NXA && j + 1 < n) xe[j + 1] = G[(j + 1) * ldn + j + 1] * (sqdt * (T)z1);
+            }
+          }
+        } else {
+#pragma unroll UF
+          for (int i = 0; i < NXA; ++i) xe[i] = T(0);
+          for (int j = 0; j < n; j += 2) {  // pairs stay a runtime loop: the rank-2 update below is the unrolled part
+            double z0, z1;
+            normal_pair((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 1), seed, z0, z1);
+            const T dw0 = sqdt * (T)z0, dw1 = j + 1 < n ? sqdt * (T)z1 : T(0);
+            const int j1 = j + 1 < n ? j + 1 : j;
+#pragma unroll UF
+            for (int i = 0; i < NXA; ++i)
+              if (i < n) xe[i] += G[i * ldn + j] * dw0 + G[i * ldn + j1] * dw1;
+          }
+        }
+#pragma unroll UF
+        for (int i = 0; i < NXA; ++i)
+          if (i < n) xe[i] = fma(dt, member_f<T, NX>(d.drift_id, th, n, i, x), x[i]) + xe[i];
+        if (d.solver == CDK_HEUN) {
+          // x + dt/2 (f(x) + f(xe)) + noise, written as xe + dt/2 (f(xe) - f(x)) so the noise is not kept (oracle: same form)
+          const T hdt = T(0.5) * dt;
+#pragma unroll UF
+          for (int i = 0; i < NXA; ++i)
+            if (i < n)
+              X[(size_t)i * ldE + el] =
+                  xe[i] + hdt * (member_f<T, NX>(d.drift_id, th, n, i, xe) - member_f<T, NX>(d.drift_id, th, n, i, x));
+        } else {
+#pragma unroll UF
+          for (int i = 0; i < NXA; ++i)
+            if (i < n) X[(size_t)i * ldE + el] = xe[i];
+        }
+      }
+      ++nsteps;
+      tprev = tnext;
+      const T cand = tprev + dt0;
+      tnext = cand > t1 - tol ? t1 : cand;
+    }
+    __syncthreads();
+    moments<T>(cluster, L, sh, nmem, E, C);  // predicted moments (:234-238); they also feed the next update
+    write_moments(PM, PP, row0 + k);
+  }
+  if (rank == 0 && threadIdx.x == 0) {
+    if (status == 0 && !isfinite(ll)) status = 1;
+    if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
+    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
+  }
+  (void)misc;
+}
+
+template <typename T, int NX>
+int launch_nx(const EArgs<T>& g, size_t smem, cudaStream_t s) {
+  auto kern = enkf_kernel<T, NX>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(enkf_kernel)");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(g.k.d.N * g.C), 1, 1);
+  cfg.blockDim = dim3(ENKF_TPB, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)g.C;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g);
+  note_launch();
+  (void)e;  // a failed launch is also recorded as the last error
+  return check_launch("enkf_kernel");
+}
+
+}  // namespace
+
+template <typename T>
+int launch_enkf(const KArgs<T>& a, cudaStream_t s) {
+  const cdk_desc& d = a.d;
+  if (d.N * 8 > 2147483647LL) return CDK_E_SIZE;
+  int dev = 0, max_optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  int forced = 0;
+  if (const char* e = getenv("CDK_ENKF_CLUSTER")) forced = atoi(e);
+  EArgs<T> g;
+  g.k = a;
+  g.C = 0;
+  size_t smem = 0;
+  for (int C = 1; C <= 8; C *= 2) {
+    if (forced && C != forced) continue;
+    const int Eloc = (((d.E + C - 1) / C) + 3) & ~3;
+    const ELay L(d.n, d.m, d.n_theta, Eloc, sizeof(T));
+    if (L.total <= (size_t)max_optin && (forced || Eloc <= 2 * ENKF_TPB || C == 8)) {
+      g.C = C;
+      g.Eloc = Eloc;
+      smem = L.total;
+      break;
+    }
+  }
+  if (g.C == 0) return CDK_E_SIZE;  // ensemble too large for 8 CTAs x 227 KB
+  if (d.n == 40 && d.drift_id == CDK_DRIFT_LORENZ96) return launch_nx<T, 40>(g, smem, s);
+  if (d.n == 3 && d.drift_id == CDK_DRIFT_LORENZ63) return launch_nx<T, 3>(g, smem, s);
+  return launch_nx<T, 0>(g, smem, s);
+}
+
 template int launch_enkf<double>(const KArgs<double>&, cudaStream_t);
 template int launch_enkf<float>(const KArgs<float>&, cudaStream_t);
+
 }  // namespace cdk

@@ -816,7 +816,8 @@ def ensemble_kalman_filter(
             elif settings.solver == "heun":
                 f0 = p.drift.f(X)
                 Xe = X + dt[:, None, None] * f0 + noise
-                Xn = X + dt[:, None, None] * np.dtype(dtype).type(0.5) * (f0 + p.drift.f(Xe)) + noise
+                # x + dt/2 (f(x) + f(xe)) + noise, written without the noise term (the CUDA kernel does not keep it)
+                Xn = Xe + dt[:, None, None] * np.dtype(dtype).type(0.5) * (p.drift.f(Xe) - f0)
             else:
                 raise ValueError("EnKF supports solver 'euler' (Euler-Maruyama) or 'heun'")
             X = np.where(active[:, None, None], Xn, X)

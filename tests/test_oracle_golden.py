@@ -70,3 +70,24 @@ def test_ukf(name):
     assert max_rel_err(r["marginal_loglik"], g["filt_marginal_loglik"]) < TOL
     for f in FIELDS:
         assert scaled_err(r[f], g["filt_" + f]) < TOL, f
+
+
+def test_enkf_oracle_matches_kalman_filter_in_distribution():
+    """Pins the EnKF restatement the way the reference's own test does (cdnlgssm_test_filter_linear_TRegular.py:434-470):
+    on a linear model its moments approach the CD-KF's as the ensemble grows."""
+    rng = np.random.default_rng(11)
+    n, m, N, K = 3, 2, 2, 15
+    F = -0.5 * np.eye(n) + 0.2 * rng.standard_normal((n, n))
+    H = rng.standard_normal((m, n))
+    gaps = 0.05 * rng.uniform(0.5, 1.5, size=(N, K)); gaps[:, 0] = 0.0
+    t = np.cumsum(gaps, axis=1)
+    y = rng.standard_normal((N, K, m))
+    lin = o.LinearParams(m0=np.zeros(n), P0=np.eye(n), F=F, L=np.eye(n), Qc=0.3 * np.eye(n), H=H, R=0.5 * np.eye(m))
+    kf = o.cdlgssm_filter(lin, y, t, settings=o.SolverSettings("dopri5", 0.01))
+    nl = o.NonlinearParams(m0=np.zeros(n), P0=np.eye(n), drift=o.LinearDrift(F, np.zeros(n)), L=np.eye(n), Qc=0.3 * np.eye(n),
+                           H=H, R=0.5 * np.eye(m))
+    errs = []
+    for E in (256, 4096):
+        en = o.ensemble_kalman_filter(nl, y, t, E=E, seed=5, settings=o.SolverSettings("euler", 0.0025))
+        errs.append(np.max(np.abs(en["filtered_means"] - kf["filtered_means"])))
+    assert errs[1] < 0.08 and errs[1] < errs[0]
