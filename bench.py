@@ -44,7 +44,7 @@ CFG = dict(N=65536, K=1000, n=3, m=1, mean_gap=0.01, dt0=0.0025, solver="rk4", s
 FLOP_SUBSTEP_SURVEY, FLOP_UPDATE_SURVEY = 496.0, 107.0
 FLOP_SUBSTEP_EXEC, FLOP_UPDATE_EXEC = 338.0, 60.0
 BYTES_PER_OBS_STEP = 16 + 192  # y,t in (16 B) + filtered/predicted mean+cov out (24 doubles)
-TRAFFIC_NCU_BYTES = None  # filled from profiles/ once an ncu --set full capture of the shipped kernel exists
+TRAFFIC_NCU_BYTES = 15.78e9  # dram read 2.40 GB + write 13.38 GB: profiles/r01_ekf_small_lw_independent_warps_tma.txt
 
 
 def parse():
@@ -166,7 +166,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_traj = args.cpu_sample_traj or max(64, 32 * cores)
+    n_traj = args.cpu_sample_traj or 512 * cores
     res = cpu_reference_leg(n_traj, args.k_obs, steps=args.steps, warmup=min(args.warmup, 1))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -199,6 +199,7 @@ def run_ours(args):
     import cd_dynamax_b200 as cd
     from cd_dynamax_b200 import _engine as E
     from cd_dynamax_b200 import _lib as L
+    from cd_dynamax_b200 import parallel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -237,9 +238,7 @@ def run_ours(args):
 
     def step_resident():
         post = cd.cdnlgssm_filter(params, y_dev, t_dev[..., None], hp)
-        s = E.ll_sum(post.marginal_loglik)
-        if world > 1:
-            dist.all_reduce(s)
+        s = parallel.allreduce_loglik(E.ll_sum(post.marginal_loglik))  # one NCCL all-reduce of 8 bytes when world > 1
         return post, s
 
     def barrier():
@@ -388,7 +387,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        res = cpu_reference_leg(args.cpu_sample_traj or max(64, 32 * cores), K, steps=2, warmup=1)
+        res = cpu_reference_leg(args.cpu_sample_traj or 512 * cores, K, steps=2, warmup=1)
         line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                                 "sample": res["sample"]}
     print(json.dumps(line), flush=True)
