@@ -120,10 +120,13 @@ struct Tab<CDK_DOPRI5> {
   }
 };
 
-// Runtime tableau (for the shared-memory kernels): up to 6 stages.
+// Runtime tableau (for the shared-memory kernels): up to 6 stages, stored SPARSE per stage (nnz / column / value) so the
+// stage assembly is a short uniform loop instead of a scan over a dense row with floating-point compares.
 struct RtTab {
   int S;
-  double a[6][6];
+  int nnz[6];
+  int col[6][5];
+  double val[6][5];
   double b[6];
 };
 
@@ -131,9 +134,20 @@ inline bool fill_rt_tab(int solver, RtTab& t) {
   auto copy = [&](auto tab) {
     using TT = decltype(tab);
     t.S = TT::S;
-    for (int i = 0; i < 6; ++i)
-      for (int j = 0; j < 6; ++j) t.a[i][j] = (i < TT::S && j < TT::S) ? TT::a(i, j) : 0.0;
-    for (int i = 0; i < 6; ++i) t.b[i] = i < TT::S ? TT::b(i) : 0.0;
+    for (int i = 0; i < 6; ++i) {
+      t.nnz[i] = 0;
+      for (int j = 0; j < 5; ++j) {
+        t.col[i][j] = 0;
+        t.val[i][j] = 0.0;
+      }
+      for (int j = 0; j < i && i < TT::S; ++j)
+        if (TT::a(i, j) != 0.0) {
+          t.col[i][t.nnz[i]] = j;
+          t.val[i][t.nnz[i]] = TT::a(i, j);
+          ++t.nnz[i];
+        }
+      t.b[i] = i < TT::S ? TT::b(i) : 0.0;
+    }
   };
   switch (solver) {
     case CDK_EULER: copy(Tab<CDK_EULER>{}); return true;

@@ -81,7 +81,10 @@ __device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
 }
 
 // ---- block-cooperative dense helpers (all end WITHOUT a barrier unless noted) ---------------------------------------
-// L = chol(A) (lower; reads the lower triangle of A; A != L). Upper triangle of L zeroed. Ends with a barrier.
+// L = chol(A + boost I) (lower; reads the lower triangle of A; A != L). Upper triangle of L zeroed. Ends with a barrier.
+// Left-looking, one thread per row of the current column (loads only inside the dot products, so they pipeline); a
+// single-warp right-looking variant with __syncwarp() instead of n CTA barriers was measured SLOWER (its trailing update
+// is a dependent load-FMA-store chain).  A non-positive pivot yields NaN (the reference's behaviour for non-PD input).
 template <typename T>
 __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
   FOR_T(e, n * ld) L[e] = T(0);
@@ -119,6 +122,56 @@ __device__ void chol_solve(const T* L, int n, int ld, T* B, int c, int ldb) {
     }
   }
   __syncthreads();
+}
+
+
+// ---- block-cooperative small GEMM on the FP64 tensor cores ----------------------------------------------------------
+// C(i, j) = sum_k opA(i, k) * opB(k, j), i < M, j < N, k < Kd, operands in shared memory (any T, converted to double in
+// the fragment loads), result handed element-wise to `epi(i, j, double value)`.
+//   TRANSA = false: opA(i, k) = A[i * lda + k];   true: opA(i, k) = A[k * lda + i]
+//   TRANSB = false: opB(k, j) = B[k * ldb + j];   true: opB(k, j) = B[j * ldb + k]
+// mma.sync.m8n8k4.f64 (SASS DMMA): each warp owns whole 8x8 output tiles and sweeps k in steps of 4 with two interleaved
+// accumulator sets.  Fragment layout: A (8x4) lane -> (row lane/4, col lane%4); B (4x8) lane -> (row lane%4, col lane/4);
+// C (8x8) lane -> (row lane/4, cols 2*(lane%4), +1).  Compared with one output element per thread (two shared-memory
+// operand loads per FMA) this needs 2 loads per 256 FMAs and 1/16 of the instructions.  Every thread of the CTA must
+// call it; no barrier inside (callers synchronise before the operands are read and after the epilogue writes).
+template <typename T, bool TRANSA, bool TRANSB, class Epi>
+__device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
+                                        int Kd, Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int tm = (M + 7) >> 3, tn = (N + 7) >> 3;
+  for (int t = warp; t < tm * tn; t += nwarp) {
+    const int r0 = (t / tn) << 3, c0 = (t % tn) << 3;
+    const int ia = r0 + gid, jb = c0 + gid;
+    const bool va = ia < M, vb = jb < N;
+    double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;
+    for (int k0 = 0; k0 < Kd; k0 += 8) {
+      {
+        const int k = k0 + tig;
+        const bool vk = k < Kd;
+        const double av = (va && vk) ? (double)(TRANSA ? A[k * lda + ia] : A[ia * lda + k]) : 0.0;
+        const double bv = (vb && vk) ? (double)(TRANSB ? B[jb * ldb + k] : B[k * ldb + jb]) : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(d0), "+d"(d1)
+                     : "d"(av), "d"(bv));
+      }
+      {
+        const int k = k0 + 4 + tig;
+        const bool vk = k < Kd;
+        const double av = (va && vk) ? (double)(TRANSA ? A[k * lda + ia] : A[ia * lda + k]) : 0.0;
+        const double bv = (vb && vk) ? (double)(TRANSB ? B[jb * ldb + k] : B[k * ldb + jb]) : 0.0;
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(e0), "+d"(e1)
+                     : "d"(av), "d"(bv));
+      }
+    }
+    const int i = r0 + gid, j = c0 + 2 * tig;
+    if (i < M) {
+      if (j < N) epi(i, j, d0 + e0);
+      if (j + 1 < N) epi(i, j + 1, d1 + e1);
+    }
+  }
 }
 
 }  // namespace cdk

@@ -74,16 +74,13 @@ __device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
     const T* F = c.p(L.TH);
     const T* A = ys;
     const T* Q = ys + L.nn;
-    FOR_T(e, n * n) {
+    T* FQ = c.p(L.W1);
+    mm_dmma<T, false, false>(F, ld, A, ld, n, n, n, [&](int i, int j, double v) { k[i * ld + j] = dt * (T)v; });
+    mm_dmma<T, false, false>(F, ld, Q, ld, n, n, n, [&](int i, int j, double v) { FQ[i * ld + j] = (T)v; });
+    __syncthreads();
+    FOR_T(e, n * n) {  // Q F^T = (F Q)^T for the symmetric Q
       const int i = e / n, j = e - i * n;
-      T sa = T(0), sq = T(0);
-      for (int q = 0; q < n; ++q) {
-        const T f = F[i * ld + q];
-        sa += f * A[q * ld + j];
-        sq += f * Q[q * ld + j] + Q[i * ld + q] * F[j * ld + q];
-      }
-      k[i * ld + j] = dt * sa;
-      k[L.nn + i * ld + j] = dt * (sq + lql[i * ld + j]);
+      k[L.nn + i * ld + j] = dt * ((FQ[i * ld + j] + FQ[j * ld + i]) + lql[i * ld + j]);
     }
     __syncthreads();
     return;
@@ -117,11 +114,12 @@ __device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
       }
       km[i] = dt * f;
     }
-    FOR_T(e, n * n) {
+    T* JP = c.p(L.W1);
+    mm_dmma<T, false, false>(J, ld, P, ld, n, n, n, [&](int i, int j, double v) { JP[i * ld + j] = (T)v; });
+    __syncthreads();
+    FOR_T(e, n * n) {  // P J^T = (J P)^T for the symmetric P
       const int i = e / n, j = e - i * n;
-      T s = T(0);
-      for (int q = 0; q < n; ++q) s += J[i * ld + q] * P[q * ld + j] + P[i * ld + q] * J[j * ld + q];
-      kP[i * ld + j] = dt * (s + lql[i * ld + j]);
+      kP[i * ld + j] = dt * ((JP[i * ld + j] + JP[j * ld + i]) + lql[i * ld + j]);
     }
     __syncthreads();
     return;
@@ -137,11 +135,12 @@ __device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
       for (int q = 0; q < n; ++q) s += G[i * ld + q] * (mm[q] - mf[q]);
       km[i] = -dt * s;
     }
+    T* GP = c.p(L.W1);
+    mm_dmma<T, false, false>(G, ld, P, ld, n, n, n, [&](int i, int j, double v) { GP[i * ld + j] = (T)v; });
+    __syncthreads();
     FOR_T(e, n * n) {
       const int i = e / n, j = e - i * n;
-      T s = T(0);
-      for (int q = 0; q < n; ++q) s += G[i * ld + q] * P[q * ld + j] + P[i * ld + q] * G[j * ld + q];
-      kP[i * ld + j] = -dt * (s - lql[i * ld + j]);
+      kP[i * ld + j] = -dt * ((GP[i * ld + j] + GP[j * ld + i]) - lql[i * ld + j]);
     }
     __syncthreads();
     return;
@@ -174,11 +173,12 @@ __device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
       km[j] = dt * (w0 * f0 + w * s);
     }
     const T wc = w * cs;
+    T* DL = c.p(L.J);  // dF Lc^T
+    mm_dmma<T, false, true>(dF, ld, Lc, ld, n, n, n, [&](int i, int j, double v) { DL[i * ld + j] = (T)v; });
+    __syncthreads();
     FOR_T(e, n * n) {
       const int a = e / n, b = e - a * n;
-      T s = T(0);
-      for (int i = 0; i < n; ++i) s += dF[a * ld + i] * Lc[b * ld + i] + dF[b * ld + i] * Lc[a * ld + i];
-      kP[a * ld + b] = dt * (wc * s + lql[a * ld + b]);
+      kP[a * ld + b] = dt * (wc * (DL[a * ld + b] + DL[b * ld + a]) + lql[a * ld + b]);
     }
     __syncthreads();
   }
@@ -205,22 +205,20 @@ __device__ bool ode_solve(const Ctx<T>& c, int kind, T* y, int S, T t0, T t1, T 
     }
     const T dt = tnext - tprev;
     for (int i = 0; i < tab.S; ++i) {
+      const int nz = tab.nnz[i];
       FOR_T(e, S) {
         T v = y[e];
-        if (nslots == 1) {
-          if (i > 0 && tab.a[i][i - 1] != 0.0) v += T(tab.a[i][i - 1]) * ks[e];
-        } else {
-          for (int j = 0; j < i; ++j)
-            if (tab.a[i][j] != 0.0) v += T(tab.a[i][j]) * ks[j * S + e];
-        }
+        // chain tableaux (nslots == 1) only ever reference the previous stage, which sits in slot 0
+        for (int q = 0; q < nz; ++q) v += T(tab.val[i][q]) * ks[(nslots == 1 ? 0 : tab.col[i][q] * S) + e];
         ys[e] = v;
         if (i == 0) acc[e] = v;
       }
       __syncthreads();
       T* ki = ks + (nslots == 1 ? 0 : i * S);
       ode_rhs<T>(c, kind, ys, ki, dt);
-      if (tab.b[i] != 0.0) {
-        FOR_T(e, S) acc[e] += T(tab.b[i]) * ki[e];
+      const T bi = T(tab.b[i]);
+      if (bi != T(0)) {
+        FOR_T(e, S) acc[e] += bi * ki[e];
       }
       __syncthreads();
     }
@@ -494,12 +492,7 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
       hit = ode_solve<T>(c, ODE_PUSH, A, 2 * L.nn, t0, t1, dt0, d.max_steps);
       T* AP = c.p(L.W1);
       T* mnew = c.p(L.C0);
-      FOR_T(e, n * n) {
-        const int i = e / n, j = e - i * n;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += A[i * ldn + q] * P[q * ldn + j];
-        AP[i * ldn + j] = s;
-      }
+      mm_dmma<T, false, false>(A, ldn, P, ldn, n, n, n, [&](int i, int j, double v) { AP[i * ldn + j] = (T)v; });
       FOR_T(i, n) {
         T s = T(0);
         for (int q = 0; q < n; ++q) s += A[i * ldn + q] * mu[q];
@@ -510,12 +503,7 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
         mnew[i] = s + c.p(L.BV)[i];
       }
       __syncthreads();
-      FOR_T(e, n * n) {
-        const int i = e / n, j = e - i * n;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += AP[i * ldn + q] * A[j * ldn + q];
-        P[i * ldn + j] = s + Q[i * ldn + j];
-      }
+      mm_dmma<T, false, true>(AP, ldn, A, ldn, n, n, n, [&](int i, int j, double v) { P[i * ldn + j] = (T)v + Q[i * ldn + j]; });
       FOR_T(i, n) mu[i] = mnew[i];
       __syncthreads();
     } else if (algo == ALGO_EKF_FILTER && d.state_order == CDK_ORDER_ZEROTH) {
@@ -597,19 +585,9 @@ __global__ void generic_smooth_kernel(const GArgs<T> g) {
       T* Lp = c.p(L.W3);
       T* Dm = c.p(L.J);    // Ps - Pp, then scratch
       T* rv = c.p(L.C0);
-      FOR_T(e, n * n) {
-        const int i = e / n, j = e - i * n;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += A[i * ldn + q] * Pf[q * ldn + j];
-        APf[i * ldn + j] = s;
-      }
+      mm_dmma<T, false, false>(A, ldn, Pf, ldn, n, n, n, [&](int i, int j, double v) { APf[i * ldn + j] = (T)v; });
       __syncthreads();
-      FOR_T(e, n * n) {
-        const int i = e / n, j = e - i * n;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += APf[i * ldn + q] * A[j * ldn + q];
-        Pp[i * ldn + j] = Q[i * ldn + j] + s;
-      }
+      mm_dmma<T, false, true>(APf, ldn, A, ldn, n, n, n, [&](int i, int j, double v) { Pp[i * ldn + j] = Q[i * ldn + j] + (T)v; });
       FOR_T(i, n) {
         // m_s^+ - A m_f - B u - b   (:763-766)
         T s = T(0);
@@ -631,16 +609,8 @@ __global__ void generic_smooth_kernel(const GArgs<T> g) {
       chol_solve<T>(Lp, n, ldn, APf, n, ldn);  // APf <- Ct
       const T* Ct = APf;
       T* CD = Pp;  // C (Ps - Pp)
-      FOR_T(e, n * n) {
-        const int i = e / n, j = e - i * n;
-        T s = T(0), x = T(0);
-        for (int q = 0; q < n; ++q) {
-          s += Ct[q * ldn + i] * Dm[q * ldn + j];
-          x += Ct[q * ldn + i] * Ps[q * ldn + j];
-        }
-        CD[i * ldn + j] = s;
-        Q[i * ldn + j] = x;  // C P_s^+
-      }
+      mm_dmma<T, true, false>(Ct, ldn, Dm, ldn, n, n, n, [&](int i, int j, double v) { CD[i * ldn + j] = (T)v; });
+      mm_dmma<T, true, false>(Ct, ldn, Ps, ldn, n, n, n, [&](int i, int j, double v) { Q[i * ldn + j] = (T)v; });  // C P_s^+
       T* msn = c.p(L.YS);
       FOR_T(i, n) {
         T s = T(0);
@@ -656,12 +626,7 @@ __global__ void generic_smooth_kernel(const GArgs<T> g) {
         }
       }
       __syncthreads();
-      FOR_T(e, n * n) {
-        const int i = e / n, j = e - i * n;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += CD[i * ldn + q] * Ct[q * ldn + j];
-        Ps[i * ldn + j] = Pf[i * ldn + j] + s;
-      }
+      mm_dmma<T, false, false>(CD, ldn, Ct, ldn, n, n, n, [&](int i, int j, double v) { Ps[i * ldn + j] = Pf[i * ldn + j] + (T)v; });
       FOR_T(i, n) ms[i] = msn[i];
       __syncthreads();
     } else {
