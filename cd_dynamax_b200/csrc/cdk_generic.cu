@@ -715,12 +715,4 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
 template int launch_generic<double>(int, const KArgs<double>&, cudaStream_t);
 template int launch_generic<float>(int, const KArgs<float>&, cudaStream_t);
 
-// placeholders until the dedicated kernels land
-template <typename T>
-int launch_kf_warp(int, const KArgs<T>&, cudaStream_t) {
-  return CDK_E_UNSUPPORTED;
-}
-template int launch_kf_warp<double>(int, const KArgs<double>&, cudaStream_t);
-template int launch_kf_warp<float>(int, const KArgs<float>&, cudaStream_t);
-
 }  // namespace cdk

@@ -1,0 +1,454 @@
+// cdk_kfwarp.cu -- continuous-discrete Kalman filter for n <= 16, m <= 8: ONE WARP PER TRAJECTORY on the FP64 tensor cores.
+//
+// Replaces cdlgssm_filter (src/continuous_discrete_linear_gaussian_ssm/inference.py:555-632) with compute_pushforward
+// (:105-144: dA = F A, dQ = F Q + Q F^T + L Qc L^T from (I, 0) over every gap), _predict (:185-206) and _condition_on
+// (:209-259) for BASELINE config 2 (n = 16, m = 4, N = 262,144, K = 500), fp64, chain tableaux (Euler .. RK4).
+//
+// B200 mapping:
+//  * 94 % of the work is the pushforward: 2 n^3 FMAs per RK stage.  Every 16x16 matrix of the RK state (A, Q, the stage
+//    increments, the running combination) lives in REGISTERS in the accumulator layout of mma.sync.m8n8k4.f64 (SASS DMMA):
+//    8 doubles per lane per matrix.  A stage writes its input to the warp's private shared-memory slice once (as the B
+//    operand), runs 2 x 16 DMMAs against F, forms F Q + (F Q)^T with one more shared-memory round trip, and does the
+//    y + a dt k / acc + b dt k updates lane-locally on the fragments.  Leading dimension 20 (= 4 mod 16) makes the A/B
+//    fragment loads bank-conflict free.
+//  * the warps of a CTA never synchronise with each other (only __syncwarp): like ekf_small_lw they drift out of phase, so
+//    the latency-bound measurement update of one warp hides behind the DMMA-bound pushforward of the others.
+//  * one warp = one trajectory also makes every per-step output row (n + n^2 doubles) one contiguous, coalesced store.
+//  * dimensions are padded to 16 x 16 / 8 x 16 with zeros (identity block for A), which leaves the arithmetic on the real
+//    entries unchanged.
+// Everything this fast path does not cover (Dopri5, inputs, fp32, n > 16, smoothers) stays on generic_filter_kernel.
+#include <stdlib.h>
+
+#include "cdk_common.cuh"
+
+namespace cdk {
+namespace {
+
+constexpr int KW_LD = 20;   // leading dimension (doubles) of every shared-memory matrix
+constexpr int KW_WPC = 4;   // warps (trajectories) per CTA
+constexpr int KW_MAT = 16 * KW_LD, KW_MAT8 = 8 * KW_LD;
+
+struct KwTab {
+  int S;
+  double a[6];  // chain tableau: stage i reads only stage i-1, with coefficient a[i]
+  double b[6];
+};
+
+struct F16 {
+  double v[2][2][2];  // [row block][col block][r]: element (8 rb + gid, 8 cb + 2 tig + r)
+};
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double av, double bv) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(av), "d"(bv));
+}
+
+// D[RB x CB tiles] = opA * opB over KD (multiple of 4), operands in shared memory with leading dimension KW_LD.
+template <bool TRANSA, bool TRANSB, int KD, int RB, int CB>
+__device__ __forceinline__ void mm(double (&d)[RB][CB][2], const double* __restrict__ sA, const double* __restrict__ sB) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) d[rb][cb][0] = d[rb][cb][1] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < KD / 4; ++kk) {
+    double av[RB], bv[CB];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+      av[rb] = TRANSA ? sA[(4 * kk + tig) * KW_LD + 8 * rb + gid] : sA[(8 * rb + gid) * KW_LD + 4 * kk + tig];
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb)
+      bv[cb] = TRANSB ? sB[(8 * cb + gid) * KW_LD + 4 * kk + tig] : sB[(4 * kk + tig) * KW_LD + 8 * cb + gid];
+#pragma unroll
+    for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < CB; ++cb) dmma(d[rb][cb][0], d[rb][cb][1], av[rb], bv[cb]);
+  }
+}
+
+template <int RB, int CB>
+__device__ __forceinline__ void store_c(const double (&d)[RB][CB][2], double* s) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) {
+      s[(8 * rb + gid) * KW_LD + 8 * cb + 2 * tig] = d[rb][cb][0];
+      s[(8 * rb + gid) * KW_LD + 8 * cb + 2 * tig + 1] = d[rb][cb][1];
+    }
+}
+template <int RB, int CB>
+__device__ __forceinline__ void load_c(double (&d)[RB][CB][2], const double* s) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < RB; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < CB; ++cb) {
+      d[rb][cb][0] = s[(8 * rb + gid) * KW_LD + 8 * cb + 2 * tig];
+      d[rb][cb][1] = s[(8 * rb + gid) * KW_LD + 8 * cb + 2 * tig + 1];
+    }
+}
+// d(r, c) = s(c, r)
+__device__ __forceinline__ void load_ct(double (&d)[2][2][2], const double* s) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      d[rb][cb][0] = s[(8 * cb + 2 * tig) * KW_LD + 8 * rb + gid];
+      d[rb][cb][1] = s[(8 * cb + 2 * tig + 1) * KW_LD + 8 * rb + gid];
+    }
+}
+
+// write a C-layout 16x16 fragment to a global row-major n x n matrix
+__device__ __forceinline__ void store_global(const double (&d)[2][2][2], double* __restrict__ G, int n) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      const int r = 8 * rb + gid, c = 8 * cb + 2 * tig;
+      if (r < n) {
+        if (c < n) G[r * n + c] = d[rb][cb][0];
+        if (c + 1 < n) G[r * n + c + 1] = d[rb][cb][1];
+      }
+    }
+}
+
+struct KwSmemCounts {
+  // per-warp doubles / per-model doubles
+  static constexpr int PER_WARP = 4 * KW_MAT + 3 * KW_MAT8 + 8 * 9 + 16 + 16 + 8 + 8 + 8 + 8;
+  static constexpr int PER_MODEL = 2 * KW_MAT + 2 * KW_MAT8 + 16 + 8;  // F, LQL, H, R, b, d
+};
+
+__global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<double> a, const KwTab tab, const int model_per_warp) {
+  extern __shared__ __align__(16) double kw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
+  const cdk_desc& d = a.d;
+  const int n = d.n, m = d.m, K = d.K;
+  const long long traj = (long long)blockIdx.x * KW_WPC + warp;
+  double* model = kw_smem + (model_per_warp ? warp * KwSmemCounts::PER_MODEL : 0);
+  double* wbase = kw_smem + (model_per_warp ? KW_WPC : 1) * KwSmemCounts::PER_MODEL + warp * KwSmemCounts::PER_WARP;
+  double* sF = model;
+  double* sLQL = sF + KW_MAT;
+  double* sH = sLQL + KW_MAT;
+  double* sR = sH + KW_MAT8;
+  double* sb = sR + KW_MAT8;
+  double* sd = sb + 16;
+  double* sP = wbase;
+  double* sYA = sP + KW_MAT;
+  double* sYQ = sYA + KW_MAT;
+  double* sT = sYQ + KW_MAT;
+  double* sHP = sT + KW_MAT;  // H P, then K^T in place
+  double* sSK = sHP + KW_MAT8;
+  double* sS = sSK + KW_MAT8;
+  double* sL = sS + KW_MAT8;  // [8][9] Cholesky factor
+  double* smu = sL + 72;
+  double* smn = smu + 16;
+  double* sy = smn + 16;
+  double* sr = sy + 8;
+  double* sz = sr + 8;
+  double* sllv = sz + 8;
+
+  // ---- model constants (padded with zeros); L Qc L^T hoisted (cd_linear/inference.py:121-131) ----
+  const bool loader = model_per_warp ? true : warp == 0;
+  const long long tj = traj < d.N ? traj : d.N - 1;
+  auto src = [&](int slot) { return a.in[slot] + tj * a.in_stride[slot]; };
+  if (loader) {
+    for (int e = lane; e < KwSmemCounts::PER_MODEL; e += 32) model[e] = 0.0;
+    __syncwarp();
+    double* Lm = sYA;  // scratch of this warp
+    double* Qc = sYQ;
+    double* LQ = sT;
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e - i * n;
+      sF[i * KW_LD + j] = src(CDK_IN_F)[e];
+      Lm[i * KW_LD + j] = src(CDK_IN_L)[e];
+      Qc[i * KW_LD + j] = src(CDK_IN_QC)[e];
+    }
+    for (int e = lane; e < m * n; e += 32) sH[(e / n) * KW_LD + (e % n)] = src(CDK_IN_H)[e];
+    for (int e = lane; e < m * m; e += 32) sR[(e / m) * KW_LD + (e % m)] = src(CDK_IN_R)[e];
+    for (int e = lane; e < n; e += 32) sb[e] = src(CDK_IN_B)[e];
+    for (int e = lane; e < m; e += 32) sd[e] = src(CDK_IN_D)[e];
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e - i * n;
+      double s = 0.0;
+      for (int q = 0; q < n; ++q) s += Lm[i * KW_LD + q] * Qc[q * KW_LD + j];
+      LQ[i * KW_LD + j] = s;
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+      const int i = e / n, j = e - i * n;
+      double s = 0.0;
+      for (int q = 0; q < n; ++q) s += LQ[i * KW_LD + q] * Lm[j * KW_LD + q];
+      sLQL[i * KW_LD + j] = s;
+    }
+  }
+  __syncthreads();  // the only CTA-wide barrier: the shared model block is ready
+  if (traj >= d.N) return;
+  for (int e = lane; e < KwSmemCounts::PER_WARP; e += 32) wbase[e] = 0.0;
+  __syncwarp();
+  for (int e = lane; e < n * n; e += 32) sP[(e / n) * KW_LD + (e % n)] = src(CDK_IN_P0)[e];
+  if (lane < n) smu[lane] = src(CDK_IN_M0)[lane];
+  __syncwarp();
+
+  const double* __restrict__ Y = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
+  const double* __restrict__ Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  double* FM = static_cast<double*>(a.out[CDK_OUT_FM]);
+  double* FP = static_cast<double*>(a.out[CDK_OUT_FP]);
+  double* PM = static_cast<double*>(a.out[CDK_OUT_PM]);
+  double* PP = static_cast<double*>(a.out[CDK_OUT_PP]);
+  double* LLC = static_cast<double*>(a.out[CDK_OUT_LLCUM]);
+  const long long row0 = traj * (long long)K;
+  const double dt0 = d.dt0, tol = clip_tol<double>();
+  double ll = 0.0;
+  int status = 0;
+  double y_next = lane < m ? Y[lane] : 0.0;
+  double t_cur = Tm[0];
+  double t_nxt = K > 1 ? Tm[1] : t_cur + d.dt_final;
+
+  for (int k = 0; k < K; ++k) {
+    // ================= update (cd_linear/inference.py:613-616, _condition_on :209-259) =================
+    if (lane < m) sy[lane] = y_next;
+    if (k + 1 < K && lane < m) y_next = Y[(long long)(k + 1) * m + lane];
+    const double t0 = t_cur, t1 = t_nxt;
+    t_cur = t1;
+    t_nxt = k + 2 < K ? Tm[k + 2] : t1 + d.dt_final;
+    __syncwarp();
+    {
+      double hp[1][2][2];
+      mm<false, false, 16, 1, 2>(hp, sH, sP);  // H P  [8 x 16]
+      store_c<1, 2>(hp, sHP);
+      if (lane < 8) {  // innovation r = y - d - H mu (rows >= m are zero)
+        double s = 0.0;
+        if (lane < m) {
+          s = sy[lane] - sd[lane];
+          for (int q = 0; q < n; ++q) s -= sH[lane * KW_LD + q] * smu[q];
+        }
+        sr[lane] = s;
+      }
+      __syncwarp();
+      double sf[1][1][2];
+      mm<false, true, 16, 1, 1>(sf, sHP, sH);  // H P H^T
+      {
+        const int r = gid, c = 2 * tig;
+        sS[r * KW_LD + c] = sf[0][0][0] + sR[r * KW_LD + c];
+        sS[r * KW_LD + c + 1] = sf[0][0][1] + sR[r * KW_LD + c + 1];
+      }
+      __syncwarp();
+      // MVN(H mu + d, S).log_prob(y): un-boosted Cholesky (TFP); then psd_solve: chol(sym(S) + 1e-9 I)
+      for (int pass = 0; pass < 2; ++pass) {
+        for (int j = 0; j < m; ++j) {
+          if (lane >= j && lane < m) {
+            const double boost = pass ? 1e-9 : 0.0;
+            double sjj = sS[j * KW_LD + j] + boost;
+            for (int q = 0; q < j; ++q) sjj -= sL[j * 9 + q] * sL[j * 9 + q];
+            const double dj = sqrt(sjj);
+            if (lane == j) {
+              sL[j * 9 + j] = dj;
+            } else {
+              double v = pass ? 0.5 * (sS[lane * KW_LD + j] + sS[j * KW_LD + lane]) : sS[lane * KW_LD + j];
+              for (int q = 0; q < j; ++q) v -= sL[lane * 9 + q] * sL[j * 9 + q];
+              sL[lane * 9 + j] = v / dj;
+            }
+          }
+          __syncwarp();
+        }
+        if (pass == 0) {
+          if (lane == 0) {
+            double quad = 0.0, logdet = 0.0;
+            for (int i = 0; i < m; ++i) {
+              double v = sr[i];
+              for (int q = 0; q < i; ++q) v -= sL[i * 9 + q] * sz[q];
+              v /= sL[i * 9 + i];
+              sz[i] = v;
+              quad += v * v;
+              logdet += log(sL[i * 9 + i]);
+            }
+            sllv[0] = -0.5 * quad - logdet - m * half_log_2pi<double>();
+          }
+          __syncwarp();
+        }
+      }
+      ll += sllv[0];
+      // K^T = (S + boost)^-1 H P, one column per lane, in place in sHP
+      if (lane < n) {
+        for (int i = 0; i < m; ++i) {
+          double v = sHP[i * KW_LD + lane];
+          for (int q = 0; q < i; ++q) v -= sL[i * 9 + q] * sHP[q * KW_LD + lane];
+          sHP[i * KW_LD + lane] = v / sL[i * 9 + i];
+        }
+        for (int i = m - 1; i >= 0; --i) {
+          double v = sHP[i * KW_LD + lane];
+          for (int q = i + 1; q < m; ++q) v -= sL[q * 9 + i] * sHP[q * KW_LD + lane];
+          sHP[i * KW_LD + lane] = v / sL[i * 9 + i];
+        }
+      }
+      __syncwarp();
+      const double* sKt = sHP;
+      double sk[1][2][2];
+      mm<false, false, 8, 1, 2>(sk, sS, sKt);  // S K^T  (un-boosted S, :257)
+      store_c<1, 2>(sk, sSK);
+      if (lane < n) {  // mu += K r
+        double s = 0.0;
+        for (int q = 0; q < m; ++q) s += sKt[q * KW_LD + lane] * sr[q];
+        smu[lane] += s;
+      }
+      __syncwarp();
+      F16 ksk, P;
+      mm<true, false, 8, 2, 2>(ksk.v, sKt, sSK);  // K S K^T
+      load_c<2, 2>(P.v, sP);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&P.v[0][0][0])[i] -= (&ksk.v[0][0][0])[i];
+      store_c<2, 2>(P.v, sT);
+      __syncwarp();
+      F16 Pt;
+      load_ct(Pt.v, sT);  // symmetrize (:259)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&P.v[0][0][0])[i] = 0.5 * ((&P.v[0][0][0])[i] + (&Pt.v[0][0][0])[i]);
+      store_c<2, 2>(P.v, sP);
+      if (FP) store_global(P.v, FP + (row0 + k) * n * n, n);
+      if (FM && lane < n) FM[(row0 + k) * n + lane] = smu[lane];
+      if (LLC && lane == 0) LLC[row0 + k] = ll;
+      __syncwarp();
+    }
+    // ================= pushforward (A, Q) over [t0, t1] from (I, 0)  (:105-144; diffrax ConstantStepSize) =================
+    F16 yA, yQ;
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          yA.v[rb][cb][r] = (8 * rb + gid == 8 * cb + 2 * tig + r) ? 1.0 : 0.0;
+          yQ.v[rb][cb][r] = 0.0;
+        }
+    {
+      double tprev = t0;
+      double tnext = fmin(t0 + dt0, t1);
+      int nsteps = 0;
+      while (tprev < t1) {
+        if (nsteps >= d.max_steps) {
+          status = 2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) (&yA.v[0][0][0])[i] = (&yQ.v[0][0][0])[i] = NAN;
+          break;
+        }
+        const double dt = tnext - tprev;
+        F16 accA = yA, accQ = yQ, kA, kQ;
+#pragma unroll 1
+        for (int st = 0; st < tab.S; ++st) {
+          // stage input y + a dt k_{st-1} -> shared memory (B operand)
+          F16 iA = yA, iQ = yQ;
+          if (st > 0) {
+            const double c = tab.a[st] * dt;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              (&iA.v[0][0][0])[i] = fma(c, (&kA.v[0][0][0])[i], (&iA.v[0][0][0])[i]);
+              (&iQ.v[0][0][0])[i] = fma(c, (&kQ.v[0][0][0])[i], (&iQ.v[0][0][0])[i]);
+            }
+          }
+          store_c<2, 2>(iA.v, sYA);
+          store_c<2, 2>(iQ.v, sYQ);
+          __syncwarp();
+          F16 fq;
+          mm<false, false, 16, 2, 2>(kA.v, sF, sYA);  // dA = F A
+          mm<false, false, 16, 2, 2>(fq.v, sF, sYQ);  // F Q
+          store_c<2, 2>(fq.v, sT);
+          __syncwarp();
+          F16 fqt, lq;
+          load_ct(fqt.v, sT);  // Q F^T = (F Q)^T for the symmetric Q
+          load_c<2, 2>(lq.v, sLQL);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) (&kQ.v[0][0][0])[i] = ((&fq.v[0][0][0])[i] + (&fqt.v[0][0][0])[i]) + (&lq.v[0][0][0])[i];
+          const double w = tab.b[st] * dt;
+          if (w != 0.0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              (&accA.v[0][0][0])[i] = fma(w, (&kA.v[0][0][0])[i], (&accA.v[0][0][0])[i]);
+              (&accQ.v[0][0][0])[i] = fma(w, (&kQ.v[0][0][0])[i], (&accQ.v[0][0][0])[i]);
+            }
+          }
+          __syncwarp();
+        }
+        yA = accA;
+        yQ = accQ;
+        ++nsteps;
+        tprev = tnext;
+        const double cand = tprev + dt0;
+        tnext = cand > t1 - tol ? t1 : cand;
+      }
+    }
+    // ================= discrete predict: mu = A mu + b, P = A P A^T + Q  (:204-205) =================
+    store_c<2, 2>(yA.v, sYA);
+    __syncwarp();
+    {
+      F16 ap;
+      mm<false, false, 16, 2, 2>(ap.v, sYA, sP);
+      store_c<2, 2>(ap.v, sT);
+      if (lane < 16) {
+        double s = 0.0;
+        for (int q = 0; q < n; ++q) s += sYA[lane * KW_LD + q] * smu[q];
+        smn[lane] = lane < n ? s + sb[lane] : 0.0;
+      }
+      __syncwarp();
+      F16 pn;
+      mm<false, true, 16, 2, 2>(pn.v, sT, sYA);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&pn.v[0][0][0])[i] += (&yQ.v[0][0][0])[i];
+      store_c<2, 2>(pn.v, sP);
+      if (lane < 16) smu[lane] = smn[lane];
+      if (PP) store_global(pn.v, PP + (row0 + k) * n * n, n);
+      if (PM && lane < n) PM[(row0 + k) * n + lane] = smn[lane];
+      __syncwarp();
+    }
+  }
+  if (lane == 0) {
+    if (status == 0 && !isfinite(ll)) status = 1;
+    if (a.out[CDK_OUT_LL]) static_cast<double*>(a.out[CDK_OUT_LL])[traj] = ll;
+    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
+  }
+}
+
+}  // namespace
+
+// Fast path coverage: KF filter, fp64, n <= 16, m <= 8, no inputs, chain tableaux (every solver except Dopri5).
+template <typename T>
+int launch_kf_warp(int algo, const KArgs<T>& a, cudaStream_t s) {
+  return CDK_E_UNSUPPORTED;
+}
+
+template <>
+int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
+  const cdk_desc& d = a.d;
+  static const bool disabled = []() {
+    const char* e = getenv("CDK_KF_WARP");
+    return e && e[0] == '0';
+  }();
+  if (disabled || algo != ALGO_KF_FILTER || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return CDK_E_UNSUPPORTED;
+  RtTab rt;
+  if (!fill_rt_tab(d.solver, rt)) return CDK_E_ENUM;
+  KwTab tab;
+  tab.S = rt.S;
+  for (int i = 0; i < 6; ++i) {
+    if (rt.nnz[i] > 1 || (rt.nnz[i] == 1 && rt.col[i][0] != i - 1)) return CDK_E_UNSUPPORTED;  // not a chain tableau
+    tab.a[i] = rt.nnz[i] ? rt.val[i][0] : 0.0;
+    tab.b[i] = rt.b[i];
+  }
+  const uint32_t model_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) | (1u << CDK_IN_R) |
+                              (1u << CDK_IN_B) | (1u << CDK_IN_D);
+  const int model_per_warp = (d.batched_mask & model_mask) != 0;
+  const size_t smem = sizeof(double) * ((model_per_warp ? KW_WPC : 1) * KwSmemCounts::PER_MODEL + KW_WPC * KwSmemCounts::PER_WARP);
+  const long long blocks = (d.N + KW_WPC - 1) / KW_WPC;
+  if (blocks > 2147483647LL) return CDK_E_SIZE;
+  if (cudaFuncSetAttribute(kf_warp_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(kf_warp_filter)");
+  kf_warp_filter<<<(unsigned)blocks, 32 * KW_WPC, smem, s>>>(a, tab, model_per_warp);
+  note_launch();
+  return check_launch("kf_warp_filter");
+}
+
+template int launch_kf_warp<float>(int, const KArgs<float>&, cudaStream_t);
+
+}  // namespace cdk
