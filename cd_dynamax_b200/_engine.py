@@ -49,6 +49,7 @@ def to_dev(x, dt: str, dev) -> torch.Tensor:
 
 
 def from_dev(t: Optional[torch.Tensor], kind: str):
+    """Hand a result back in the caller's array kind (`t` may already be a host tensor, see run(host_out=True))."""
     if t is None:
         return None
     if kind == "cuda":
@@ -58,67 +59,183 @@ def from_dev(t: Optional[torch.Tensor], kind: str):
     return t.cpu().numpy()
 
 
+# Host-resident batched inputs larger than this are staged in N-chunks: chunk i+1 crosses PCIe on a copy stream while the
+# kernels of earlier chunks run (and their results return on a third stream).  Trajectories are independent, so a chunk
+# is just the same entry point with offset pointers and a smaller N.  The chunk kernels go to a small pool of compute
+# streams so that they overlap EACH OTHER as well: one trajectory is a serial chain of K steps, so a chunk of N/8
+# trajectories takes almost as long as the whole batch (the GPU is a single wave either way) and back-to-back chunk
+# kernels would serialise that latency.
+STREAM_MIN_BYTES = 32 << 20
+STREAM_CHUNKS = 8
+COMPUTE_STREAMS = 4
+_side_streams: Dict[int, tuple] = {}
+
+
+def _streams(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side_streams:
+        _side_streams[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev),
+                              [torch.cuda.Stream(dev) for _ in range(COMPUTE_STREAMS)])
+    return _side_streams[key]
+
+
+def _is_host(x) -> bool:
+    if isinstance(x, torch.Tensor):
+        return not x.is_cuda
+    return not hasattr(x, "__cuda_array_interface__")
+
+
+def _host_tensor(x, dt: str) -> torch.Tensor:
+    """Host array-like -> contiguous CPU tensor of the kernel dtype (no copy when it already is one, so a pinned
+    buffer stays pinned)."""
+    if isinstance(x, torch.Tensor):
+        return x.to(dtype=_TORCH_DT[dt]).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=_NP_DT[dt]))
+
+
 def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, object], want: Sequence[int],
         desc_fields: dict, theta_core_ndim: int = 1, scross_rows: Optional[int] = None,
-        status: Optional[torch.Tensor] = None) -> Dict[int, torch.Tensor]:
+        status: Optional[torch.Tensor] = None, host_out: bool = False,
+        dev_inputs: Optional[dict] = None) -> Dict[int, torch.Tensor]:
     """Call one C-ABI entry point. `inputs` maps slot -> array-like (None = absent); a leading N marks it batched.
-    Returns slot -> device tensor for every slot in `want` (+ OUT_STATUS)."""
+    Returns slot -> tensor for every slot in `want` (+ OUT_STATUS): device tensors, or -- with `host_out`, which the
+    API shims set when the caller handed in host arrays -- pinned host tensors whose copies have completed.
+    `dev_inputs`, when given, receives slot -> staged device tensor (a smoother reuses the filter's staged inputs)."""
     lib = L.lib()
     dev = device()
     d = L.new_desc()
     d.N, d.K, d.n, d.m = N, K, n, m
     for k, v in desc_fields.items():
         setattr(d, k, v)
-    keep = []
-    in_ptrs = (ctypes.c_void_p * L.NUM_IN)()
+    tdt = _TORCH_DT[dt]
+    esz = 8 if dt == "f64" else 4
+    cur = torch.cuda.current_stream(dev)
+    # ---- classify inputs; decide whether to stream host-resident batched inputs in chunks ----
+    metas = {}
+    stream_bytes = 0
     mask = 0
     for slot in range(L.NUM_IN):
         x = inputs.get(slot)
         if x is None:
-            in_ptrs[slot] = None
             continue
-        t = to_dev(x, dt, dev)
+        shape = tuple(x.shape) if hasattr(x, "shape") else tuple(np.shape(x))
         core = _CORE_NDIM[slot] if _CORE_NDIM[slot] is not None else theta_core_ndim
-        if t.dim() == core + 1:
-            if t.shape[0] != N:
-                raise ValueError(f"input slot {slot}: leading axis {t.shape[0]} != N={N}")
+        batched = len(shape) == core + 1
+        if batched:
+            if shape[0] != N:
+                raise ValueError(f"input slot {slot}: leading axis {shape[0]} != N={N}")
             mask |= 1 << slot
-        elif t.dim() != core:
-            raise ValueError(f"input slot {slot}: expected rank {core} or {core + 1}, got shape {tuple(t.shape)}")
-        keep.append(t)
-        in_ptrs[slot] = t.data_ptr() if t.numel() > 0 else None
+        elif len(shape) != core:
+            raise ValueError(f"input slot {slot}: expected rank {core} or {core + 1}, got shape {shape}")
+        row = int(np.prod(shape[1:], dtype=np.int64)) if batched else 0
+        host = _is_host(x)
+        metas[slot] = (x, batched, row, host)
+        if batched and host:
+            stream_bytes += N * row * esz
     d.batched_mask = mask
-    tdt = _TORCH_DT[dt]
-    shapes = {
-        L.OUT_LL: (N,), L.OUT_FM: (N, K, n), L.OUT_FP: (N, K, n, n), L.OUT_PM: (N, K, n), L.OUT_PP: (N, K, n, n),
-        L.OUT_LLCUM: (N, K), L.OUT_SM: (N, K, n), L.OUT_SP: (N, K, n, n),
-        L.OUT_SCROSS: (N, max(K - 1, 0) if scross_rows is None else scross_rows, n, n),
-    }
+    nchunks = STREAM_CHUNKS if (stream_bytes >= STREAM_MIN_BYTES and N >= 2 * STREAM_CHUNKS) else 1
+    if host_out and N >= 2 * STREAM_CHUNKS:
+        out_bytes = sum(int(np.prod(_out_shape(s, N, K, n, scross_rows), dtype=np.int64)) * esz for s in want)
+        if out_bytes >= STREAM_MIN_BYTES:
+            nchunks = STREAM_CHUNKS
+    h2d, d2h, comp = _streams(dev) if (nchunks > 1 or host_out) else (None, None, None)
+    # ---- stage inputs ----
+    keep = []
+    dev_in = {}
+    staged = {}  # slot -> (host tensor, device tensor) copied chunk by chunk
+    for slot, (x, batched, row, host) in metas.items():
+        if nchunks > 1 and batched and host:
+            ht = _host_tensor(x, dt)
+            dtens = torch.empty(ht.shape, dtype=tdt, device=dev)
+            staged[slot] = (ht, dtens)
+            dev_in[slot] = dtens
+        else:
+            dev_in[slot] = to_dev(x, dt, dev)
+        keep.append(dev_in[slot])
+    if dev_inputs is not None:
+        dev_inputs.update(dev_in)
+    # ---- outputs ----
     out = {}
-    out_ptrs = (ctypes.c_void_p * L.NUM_OUT)()
-    for slot in range(L.NUM_OUT):
-        out_ptrs[slot] = None
     for slot in want:
-        t = torch.empty(shapes[slot], dtype=tdt, device=dev)
-        out[slot] = t
-        out_ptrs[slot] = t.data_ptr() if t.numel() > 0 else None
+        out[slot] = torch.empty(_out_shape(slot, N, K, n, scross_rows), dtype=tdt, device=dev)
     if status is None:
         status = torch.zeros((N,), dtype=torch.int32, device=dev)
     out[L.OUT_STATUS] = status
-    out_ptrs[L.OUT_STATUS] = status.data_ptr() if N > 0 else None
-    nscratch = lib.cdk_scratch_bytes(ctypes.byref(d), entry.encode())
-    if nscratch:
-        scratch = torch.empty((nscratch,), dtype=torch.uint8, device=dev)
-        keep.append(scratch)
-        out_ptrs[L.OUT_SCRATCH] = scratch.data_ptr()
-    stream = torch.cuda.current_stream(dev).cuda_stream
+    hout = {}
+    if host_out:
+        for slot, t in out.items():
+            hout[slot] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     fn = getattr(lib, f"{entry}_{dt}")
-    rc = fn(ctypes.byref(d), in_ptrs, out_ptrs, ctypes.c_void_p(stream))
-    L.check(rc, f"{entry}_{dt}")
+    bounds = [(N * c) // nchunks for c in range(nchunks + 1)]
+    rng_offset0 = int(d.rng_offset)
+    scratch = {}
+    if nchunks > 1:
+        h2d.wait_stream(cur)  # staged device buffers were allocated on `cur`
+        for cs in comp:
+            cs.wait_stream(cur)
+    if host_out:
+        d2h.wait_stream(cur)
+    for c in range(nchunks):
+        lo, hi = bounds[c], bounds[c + 1]
+        if hi == lo:
+            continue
+        ks = comp[c % COMPUTE_STREAMS] if nchunks > 1 else cur  # the stream this chunk's kernel runs on
+        if staged:
+            with torch.cuda.stream(h2d):
+                for ht, dtens in staged.values():
+                    dtens[lo:hi].copy_(ht[lo:hi], non_blocking=True)
+            ks.wait_stream(h2d)
+        d.N = hi - lo
+        d.rng_offset = rng_offset0 + lo
+        in_ptrs = (ctypes.c_void_p * L.NUM_IN)()
+        for slot in range(L.NUM_IN):
+            in_ptrs[slot] = None
+        for slot, t in dev_in.items():
+            if t.numel() > 0:
+                _, batched, row, _ = metas[slot]
+                in_ptrs[slot] = t.data_ptr() + (lo * row * esz if batched else 0)
+        out_ptrs = (ctypes.c_void_p * L.NUM_OUT)()
+        for slot in range(L.NUM_OUT):
+            out_ptrs[slot] = None
+        for slot, t in out.items():
+            if t.numel() > 0:
+                out_ptrs[slot] = t.data_ptr() + lo * (t.numel() // N) * t.element_size()
+        nscratch = lib.cdk_scratch_bytes(ctypes.byref(d), entry.encode())
+        if nscratch:
+            sc = scratch.get(ks)  # one scratch buffer per compute stream (chunks on one stream run in order)
+            if sc is None or sc.numel() < nscratch:
+                sc = scratch[ks] = torch.empty((nscratch,), dtype=torch.uint8, device=dev)
+                keep.append(sc)
+            out_ptrs[L.OUT_SCRATCH] = sc.data_ptr()
+        rc = fn(ctypes.byref(d), in_ptrs, out_ptrs, ctypes.c_void_p(ks.cuda_stream))
+        L.check(rc, f"{entry}_{dt}")
+        if host_out:
+            d2h.wait_stream(ks)
+            with torch.cuda.stream(d2h):
+                for slot, t in out.items():
+                    hout[slot][lo:hi].copy_(t[lo:hi], non_blocking=True)
+    if nchunks > 1:
+        for cs in comp:
+            cur.wait_stream(cs)  # the caller's stream sees the finished outputs
+    if nchunks > 1 or host_out:
+        for t in keep + list(out.values()):
+            for st in [h2d, d2h] + (comp if nchunks > 1 else []):
+                t.record_stream(st)
+    if host_out:
+        d2h.synchronize()
+        return hout
     # staged inputs / scratch were allocated on this stream: the caching allocator keeps them valid until the kernel
     # has consumed them (stream-ordered reuse), so dropping `keep` here is safe.
     del keep
     return out
+
+
+def _out_shape(slot, N, K, n, scross_rows=None):
+    return {
+        L.OUT_LL: (N,), L.OUT_FM: (N, K, n), L.OUT_FP: (N, K, n, n), L.OUT_PM: (N, K, n), L.OUT_PP: (N, K, n, n),
+        L.OUT_LLCUM: (N, K), L.OUT_SM: (N, K, n), L.OUT_SP: (N, K, n, n),
+        L.OUT_SCROSS: (N, max(K - 1, 0) if scross_rows is None else scross_rows, n, n), L.OUT_STATUS: (N,),
+    }[slot]
 
 
 def ll_sum(ll: torch.Tensor) -> torch.Tensor:

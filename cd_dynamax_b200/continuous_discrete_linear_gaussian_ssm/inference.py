@@ -113,7 +113,7 @@ def _linear_inputs(params: ParamsCDLGSSM, Y, T, U, n, m, d_u):
     return ins
 
 
-def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, want):
+def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, want, host_out=False):
     hp = filter_hyperparams if filter_hyperparams is not None else KFHyperParams()  # None crashes upstream (:585)
     Y, T, U, batched = prepare_data(emissions, t_emissions, inputs)
     N, K, m = _shape(Y)
@@ -122,8 +122,10 @@ def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, w
     dt = E.pick_dtype(emissions)
     ins = _linear_inputs(params, Y, T, U, n, m, d_u)
     fields = dict(E.parse_settings(hp.diffeqsolve_settings), dt_final=float(hp.dt_final), d_u=d_u)
-    out = E.run("cdk_kf_filter", dt, N, K, n, m, ins, want, fields, theta_core_ndim=2)
-    return out, ins, fields, (N, K, n, m, dt, batched)
+    dev_ins = {}
+    out = E.run("cdk_kf_filter", dt, N, K, n, m, ins, want, fields, theta_core_ndim=2, host_out=host_out,
+                dev_inputs=dev_ins)
+    return out, {**ins, **dev_ins}, fields, (N, K, n, m, dt, batched)
 
 
 def _sq(t, batched):
@@ -135,7 +137,8 @@ def cdlgssm_filter(params: ParamsCDLGSSM, emissions, t_emissions=None,
     """Continuous-discrete Kalman filter (cd_linear/inference.py:555-632)."""
     kind = E.kind_of(emissions)
     want = (L.OUT_LL, L.OUT_FM, L.OUT_FP, L.OUT_PM, L.OUT_PP)
-    out, _, _, (N, K, n, m, dt, batched) = _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, want)
+    out, _, _, (N, K, n, m, dt, batched) = _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs,
+                                                          want, host_out=(kind != "cuda"))
     g = lambda s: E.from_dev(_sq(out[s], batched), kind)
     return PosteriorGSSMFiltered(marginal_loglik=g(L.OUT_LL), filtered_means=g(L.OUT_FM),
                                  filtered_covariances=g(L.OUT_FP), predicted_means=g(L.OUT_PM),

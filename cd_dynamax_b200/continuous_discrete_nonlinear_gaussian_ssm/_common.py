@@ -30,7 +30,7 @@ def nonlinear_inputs(params, Y, T, n, m):
 
 
 def run_filter(entry, params, emissions, t_emissions, inputs, output_fields, desc_fields, settings_sde=False,
-               diffeqsolve_settings=None):
+               diffeqsolve_settings=None, keep_on_device=False):
     """Common driver: returns (PosteriorGSSMFiltered, device outputs dict, context)."""
     kind = E.kind_of(emissions)
     Y, T, U, batched = prepare_data(emissions, t_emissions, None)  # registry drifts ignore inputs (as upstream's do)
@@ -44,7 +44,12 @@ def run_filter(entry, params, emissions, t_emissions, inputs, output_fields, des
     if unknown:
         raise ValueError(f"unknown output_fields {unknown}")
     want = [L.OUT_LL] + [_FIELD_SLOT[f] for f in output_fields]
-    out = E.run(entry, dt, N, K, n, m, ins, want, fields)
+    # host callers get their results streamed back chunk by chunk into pinned memory, unless a smoother is going to
+    # consume them on the device (keep_on_device); either way the staged device inputs are handed on for reuse
+    dev_ins = {}
+    out = E.run(entry, dt, N, K, n, m, ins, want, fields, host_out=(kind != "cuda" and not keep_on_device),
+                dev_inputs=dev_ins)
+    ins = {**ins, **dev_ins}
     g = lambda s: E.from_dev(_sq(out[s], batched), kind) if s in out else None
     # listing "marginal_loglik" in output_fields replaces the scalar by the cumulative per-step array
     # (inference_ekf.py:313-315,322)

@@ -49,7 +49,7 @@ def extended_kalman_smoother(params, emissions, hyperparams: EKFHyperParams = EK
         raise ValueError("EKF hyperparams.smooth_order = {} not implemented yet".format(hyperparams.smooth_order))
     post, out, (ins, fields, N, K, n, m, dt, batched, kind) = run_filter(
         "cdk_ekf_filter", params, emissions, t_emissions, inputs, ["filtered_means", "filtered_covariances"],
-        _ekf_fields(hyperparams, 1), diffeqsolve_settings=hyperparams.diffeqsolve_settings)
+        _ekf_fields(hyperparams, 1), diffeqsolve_settings=hyperparams.diffeqsolve_settings, keep_on_device=True)
     fm, fp = out[L.OUT_FM], out[L.OUT_FP]
     if filtered_posterior is not None:
         # upstream uses a caller-supplied filtered posterior verbatim (:497-512)

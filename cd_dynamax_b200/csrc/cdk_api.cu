@@ -320,6 +320,7 @@ int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream)
   return check_launch("dmma_probe_kernel");
 }
 
+int cdk_debug_set_trace(void* devbuf) { return cdk::set_lw_trace(devbuf); }
 int64_t cdk_launch_count(void) { return (int64_t)g_launches.load(); }
 int cdk_version(void) { return CDK_VERSION; }
 const char* cdk_last_error(void) { return g_err; }

@@ -636,6 +636,15 @@ __global__ void __launch_bounds__(V5_TPB, 2) ekf_small_v5(const KArgs<T> a, cons
 // ======================================================================================================================
 constexpr int LW_RING = 4;
 
+// Diagnostics (scripts/trace_lw.py): when a device buffer is registered with cdk_debug_set_trace(), lane 0 of every warp
+// records {globaltimer at entry, at exit, %smid, %warpid} -- used to see how warp run times spread over SM sub-partitions.
+__device__ unsigned long long* g_lw_trace = nullptr;
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 template <typename T, int NX, int NY>
 struct alignas(128) LWSmem {
   T fm[32][2][NX];
@@ -674,6 +683,8 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
   const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0;
+  unsigned long long* const trace = g_lw_trace;
+  const unsigned long long t_entry = trace ? globaltimer() : 0ull;
 
   if ((par_batched && live) || (!par_batched && lane == 0)) {
     T* par = par_batched ? parbase + lane * NPAR : parbase;
@@ -858,6 +869,16 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
     }
   }
   if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (trace && lane == 0) {
+    unsigned smid, wid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %warpid;" : "=r"(wid));
+    unsigned long long* r = trace + 4 * (traj0 >> 5);
+    r[0] = t_entry;
+    r[1] = globaltimer();
+    r[2] = smid;
+    r[3] = wid;
+  }
   if (live) {
     ll -= T(0.5) * log(sprod);
     if (sbad) ll = T(NAN);
@@ -992,6 +1013,11 @@ int launch_ekf_small(const KArgs<T>& a, cudaStream_t s) {
   if (d.state_order == CDK_ORDER_ZEROTH) return CDK_E_UNSUPPORTED;
   if (d.drift_id == CDK_DRIFT_LORENZ63 && d.n == 3) return launch_ny<T, DriftL63>(a, s);
   return CDK_E_UNSUPPORTED;
+}
+
+int set_lw_trace(void* devbuf) {
+  unsigned long long* p = static_cast<unsigned long long*>(devbuf);
+  return cudaMemcpyToSymbol(g_lw_trace, &p, sizeof(p)) == cudaSuccess ? CDK_OK : CDK_E_CUDA;
 }
 
 template int launch_ekf_small<double>(const KArgs<double>&, cudaStream_t);

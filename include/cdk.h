@@ -181,6 +181,10 @@ int cdk_fma_probe_f32(int blocks, int iters, float* sink, cdk_stream_t stream);
  * accumulator tiles per warp; flops = 2 * 8*8*4 * 8 * iters * blocks * 8 warps. */
 int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
 
+/* Diagnostics: register (or clear, with NULL) a device buffer of 4 x uint64 per warp of 32 trajectories; the Lorenz-63
+ * EKF kernel then records {globaltimer at entry, at exit, %smid, %warpid} per warp (scripts/trace_lw.py). */
+int cdk_debug_set_trace(void* devbuf);
+
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches accounting). */
 int64_t cdk_launch_count(void);
 

@@ -332,3 +332,47 @@ def test_enkf_matches_kalman_filter_in_distribution():
     assert scaled_err(f.filtered_means, kf.filtered_means) < 0.06
     assert scaled_err(f.filtered_covariances, kf.filtered_covariances) < 0.12
     assert max_rel_err(f.marginal_loglik, kf.marginal_loglik) < 0.03
+
+
+# ---- host-resident inputs streamed in N-chunks (copy / compute / copy-back overlap) must not change a single bit ------
+def test_chunked_host_streaming_is_bit_identical(monkeypatch):
+    import torch
+    from cd_dynamax_b200 import _engine as E
+    cd = api()
+    N, K = 203, 24  # N not divisible by the chunk count
+    t, y = c3_problem(N, K)
+    g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]),
+             L=np.eye(3), Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))
+    # one batched parameter (vmap over parameter samples): per-trajectory initial means
+    m0 = np.random.default_rng(5).standard_normal((N, 3))
+    p = nonlinear_params_api(dict(g, m0=m0))
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    dev = lambda a: torch.as_tensor(a).cuda()
+    p_dev = nonlinear_params_api(dict(g, m0=dev(m0)))
+    ref = cd.cdnlgssm_filter(p_dev, dev(y), dev(t)[..., None], hp)  # resident: one launch
+    monkeypatch.setattr(E, "STREAM_MIN_BYTES", 1)
+    for yy, tt in ((y, t[..., None]), (torch.as_tensor(y).pin_memory(), torch.as_tensor(t).pin_memory()[..., None])):
+        f = cd.cdnlgssm_filter(p, yy, tt, hp)
+        for fld in ["marginal_loglik"] + FIELDS:
+            a = getattr(f, fld)
+            a = a.numpy() if isinstance(a, torch.Tensor) else a
+            assert np.array_equal(a, getattr(ref, fld).cpu().numpy()), fld
+    # EnKF: the random stream is indexed by the global trajectory number, so chunking must not change it either
+    ge, te, ye, dt0 = _enkf_case("l63", 37, 12, 64)
+    pe = nonlinear_params_api(ge)
+    hpe = cd.EnKFHyperParams(N_particles=64, key=99, diffeqsolve_settings={"solver": "euler", "dt0": dt0})
+    f_chunked = cd.cdnlgssm_filter(pe, ye, te[..., None], hpe)
+    monkeypatch.setattr(E, "STREAM_MIN_BYTES", 1 << 60)
+    f_once = cd.cdnlgssm_filter(pe, ye, te[..., None], hpe)
+    for fld in ["marginal_loglik"] + FIELDS:
+        assert np.array_equal(getattr(f_chunked, fld), getattr(f_once, fld)), fld
+    # linear smoother from host arrays: filter inputs staged once, reused by the backward pass
+    gl = load_golden("kf_tracking_c1")
+    monkeypatch.setattr(E, "STREAM_MIN_BYTES", 1)
+    y1, t1 = gl["y"][0], gl["t"][0]
+    Yb, Tb = np.repeat(y1[None], 20, 0), np.repeat(t1[None], 20, 0)
+    kh = cd.KFHyperParams(dt_final=float(gl["dt_final"]), diffeqsolve_settings=settings_api(gl))
+    s_chunked = cd.cdlgssm_smoother(linear_params_api(gl), Yb, Tb[..., None], kh)
+    s_one = cd.cdlgssm_smoother(linear_params_api(gl), y1, t1[:, None], kh)
+    assert np.array_equal(s_chunked.smoothed_means[7], s_one.smoothed_means)
+    assert np.array_equal(s_chunked.smoothed_covariances[19], s_one.smoothed_covariances)
