@@ -115,13 +115,131 @@ __device__ __forceinline__ void store_global(const double (&d)[2][2][2], double*
     }
 }
 
+// (A, Q) over [t0, t1] from (I, 0): dA = F A, dQ = F Q + Q F^T + L Qc L^T (cd_linear/inference.py:105-144) with the diffrax
+// ConstantStepSize stepping rule.  Results stay in registers (C-fragment layout); sYA / sYQ / sT are the warp's stage
+// buffers.  Returns true when max_steps was exceeded (results are NaN then, as in the reference).
+__device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, const double tol, const int max_steps,
+                                            const double t0, const double t1, const double* sF, const double* sLQL,
+                                            double* sYA, double* sYQ, double* sT, F16& yA, F16& yQ) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  bool hit = false;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        yA.v[rb][cb][r] = (8 * rb + gid == 8 * cb + 2 * tig + r) ? 1.0 : 0.0;
+        yQ.v[rb][cb][r] = 0.0;
+      }
+  double tprev = t0;
+  double tnext = fmin(t0 + dt0, t1);
+  int nsteps = 0;
+  while (tprev < t1) {
+    if (nsteps >= max_steps) {
+      hit = true;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&yA.v[0][0][0])[i] = (&yQ.v[0][0][0])[i] = NAN;
+      break;
+    }
+    const double dt = tnext - tprev;
+    F16 accA = yA, accQ = yQ, kA, kQ;
+#pragma unroll 1
+    for (int st = 0; st < tab.S; ++st) {
+      // stage input y + a dt k_{st-1} -> shared memory (B operand)
+      F16 iA = yA, iQ = yQ;
+      if (st > 0) {
+        const double c = tab.a[st] * dt;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          (&iA.v[0][0][0])[i] = fma(c, (&kA.v[0][0][0])[i], (&iA.v[0][0][0])[i]);
+          (&iQ.v[0][0][0])[i] = fma(c, (&kQ.v[0][0][0])[i], (&iQ.v[0][0][0])[i]);
+        }
+      }
+      store_c<2, 2>(iA.v, sYA);
+      store_c<2, 2>(iQ.v, sYQ);
+      __syncwarp();
+      F16 fq;
+      mm<false, false, 16, 2, 2>(kA.v, sF, sYA);  // dA = F A
+      mm<false, false, 16, 2, 2>(fq.v, sF, sYQ);  // F Q
+      store_c<2, 2>(fq.v, sT);
+      __syncwarp();
+      F16 fqt, lq;
+      load_ct(fqt.v, sT);  // Q F^T = (F Q)^T for the symmetric Q
+      load_c<2, 2>(lq.v, sLQL);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&kQ.v[0][0][0])[i] = ((&fq.v[0][0][0])[i] + (&fqt.v[0][0][0])[i]) + (&lq.v[0][0][0])[i];
+      const double w = tab.b[st] * dt;
+      if (w != 0.0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          (&accA.v[0][0][0])[i] = fma(w, (&kA.v[0][0][0])[i], (&accA.v[0][0][0])[i]);
+          (&accQ.v[0][0][0])[i] = fma(w, (&kQ.v[0][0][0])[i], (&accQ.v[0][0][0])[i]);
+        }
+      }
+      __syncwarp();
+    }
+    yA = accA;
+    yQ = accQ;
+    ++nsteps;
+    tprev = tnext;
+    const double cand = tprev + dt0;
+    tnext = cand > t1 - tol ? t1 : cand;
+  }
+  return hit;
+}
+
+// Model constants (padded with zeros) into the CTA's or the warp's model block; L Qc L^T hoisted
+// (cd_linear/inference.py:121-131).  scr0..2 are three 16 x KW_LD scratch matrices of the calling warp.
+__device__ __forceinline__ void load_model_kw(const KArgs<double>& a, const long long tj, double* model, double* scr0,
+                                              double* scr1, double* scr2) {
+  const int lane = threadIdx.x & 31;
+  const int n = a.d.n, m = a.d.m;
+  double* sF = model;
+  double* sLQL = sF + KW_MAT;
+  double* sH = sLQL + KW_MAT;
+  double* sR = sH + KW_MAT8;
+  double* sb = sR + KW_MAT8;
+  double* sd = sb + 16;
+  auto src = [&](int slot) { return a.in[slot] + tj * a.in_stride[slot]; };
+  for (int e = lane; e < 2 * KW_MAT + 2 * KW_MAT8 + 16 + 8; e += 32) model[e] = 0.0;
+  __syncwarp();
+  double* Lm = scr0;
+  double* Qc = scr1;
+  double* LQ = scr2;
+  for (int e = lane; e < n * n; e += 32) {
+    const int i = e / n, j = e - i * n;
+    sF[i * KW_LD + j] = src(CDK_IN_F)[e];
+    Lm[i * KW_LD + j] = src(CDK_IN_L)[e];
+    Qc[i * KW_LD + j] = src(CDK_IN_QC)[e];
+  }
+  for (int e = lane; e < m * n; e += 32) sH[(e / n) * KW_LD + (e % n)] = src(CDK_IN_H)[e];
+  for (int e = lane; e < m * m; e += 32) sR[(e / m) * KW_LD + (e % m)] = src(CDK_IN_R)[e];
+  for (int e = lane; e < n; e += 32) sb[e] = src(CDK_IN_B)[e];
+  for (int e = lane; e < m; e += 32) sd[e] = src(CDK_IN_D)[e];
+  __syncwarp();
+  for (int e = lane; e < n * n; e += 32) {
+    const int i = e / n, j = e - i * n;
+    double s = 0.0;
+    for (int q = 0; q < n; ++q) s += Lm[i * KW_LD + q] * Qc[q * KW_LD + j];
+    LQ[i * KW_LD + j] = s;
+  }
+  __syncwarp();
+  for (int e = lane; e < n * n; e += 32) {
+    const int i = e / n, j = e - i * n;
+    double s = 0.0;
+    for (int q = 0; q < n; ++q) s += LQ[i * KW_LD + q] * Lm[j * KW_LD + q];
+    sLQL[i * KW_LD + j] = s;
+  }
+}
+
 struct KwSmemCounts {
   // per-warp doubles / per-model doubles
   static constexpr int PER_WARP = 4 * KW_MAT + 3 * KW_MAT8 + 8 * 9 + 16 + 16 + 8 + 8 + 8 + 8;
   static constexpr int PER_MODEL = 2 * KW_MAT + 2 * KW_MAT8 + 16 + 8;  // F, LQL, H, R, b, d
 };
 
-__global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<double> a, const KwTab tab, const int model_per_warp) {
+__global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp) {
   extern __shared__ __align__(16) double kw_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
   const cdk_desc& d = a.d;
@@ -315,71 +433,7 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
     }
     // ================= pushforward (A, Q) over [t0, t1] from (I, 0)  (:105-144; diffrax ConstantStepSize) =================
     F16 yA, yQ;
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-      for (int cb = 0; cb < 2; ++cb)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          yA.v[rb][cb][r] = (8 * rb + gid == 8 * cb + 2 * tig + r) ? 1.0 : 0.0;
-          yQ.v[rb][cb][r] = 0.0;
-        }
-    {
-      double tprev = t0;
-      double tnext = fmin(t0 + dt0, t1);
-      int nsteps = 0;
-      while (tprev < t1) {
-        if (nsteps >= d.max_steps) {
-          status = 2;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) (&yA.v[0][0][0])[i] = (&yQ.v[0][0][0])[i] = NAN;
-          break;
-        }
-        const double dt = tnext - tprev;
-        F16 accA = yA, accQ = yQ, kA, kQ;
-#pragma unroll 1
-        for (int st = 0; st < tab.S; ++st) {
-          // stage input y + a dt k_{st-1} -> shared memory (B operand)
-          F16 iA = yA, iQ = yQ;
-          if (st > 0) {
-            const double c = tab.a[st] * dt;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              (&iA.v[0][0][0])[i] = fma(c, (&kA.v[0][0][0])[i], (&iA.v[0][0][0])[i]);
-              (&iQ.v[0][0][0])[i] = fma(c, (&kQ.v[0][0][0])[i], (&iQ.v[0][0][0])[i]);
-            }
-          }
-          store_c<2, 2>(iA.v, sYA);
-          store_c<2, 2>(iQ.v, sYQ);
-          __syncwarp();
-          F16 fq;
-          mm<false, false, 16, 2, 2>(kA.v, sF, sYA);  // dA = F A
-          mm<false, false, 16, 2, 2>(fq.v, sF, sYQ);  // F Q
-          store_c<2, 2>(fq.v, sT);
-          __syncwarp();
-          F16 fqt, lq;
-          load_ct(fqt.v, sT);  // Q F^T = (F Q)^T for the symmetric Q
-          load_c<2, 2>(lq.v, sLQL);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) (&kQ.v[0][0][0])[i] = ((&fq.v[0][0][0])[i] + (&fqt.v[0][0][0])[i]) + (&lq.v[0][0][0])[i];
-          const double w = tab.b[st] * dt;
-          if (w != 0.0) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              (&accA.v[0][0][0])[i] = fma(w, (&kA.v[0][0][0])[i], (&accA.v[0][0][0])[i]);
-              (&accQ.v[0][0][0])[i] = fma(w, (&kQ.v[0][0][0])[i], (&accQ.v[0][0][0])[i]);
-            }
-          }
-          __syncwarp();
-        }
-        yA = accA;
-        yQ = accQ;
-        ++nsteps;
-        tprev = tnext;
-        const double cand = tprev + dt0;
-        tnext = cand > t1 - tol ? t1 : cand;
-      }
-    }
+    if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) status = 2;
     // ================= discrete predict: mu = A mu + b, P = A P A^T + Q  (:204-205) =================
     store_c<2, 2>(yA.v, sYA);
     __syncwarp();
@@ -411,9 +465,191 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
   }
 }
 
+
+// ======================================================================================================================
+// Backward pass of cdlgssm_smoother, smoother_type 'cd_smoother_1' (cd_linear/inference.py:746-773, Sarkka Alg. 3.17):
+// for k = K-2 .. 0 re-integrate the pushforward (A, Q) over [t_k, t_{k+1}] (:753), then
+//   C = psd_solve(A P_f A^T + Q, A P_f)^T,  m_s = m_f + C (m_s^+ - A m_f - b),  P_s = P_f + C (P_s^+ - A P_f A^T - Q) C^T,
+//   cross = C P_s^+ + m_s m_s^{+T}.
+// Same mapping as the filter: one warp per trajectory, every n x n product on the FP64 tensor cores, the 16 x 16 Cholesky
+// and the two triangular solves warp-cooperative in shared memory (one lane per row / per right-hand-side column).
+// ======================================================================================================================
+constexpr int KS_WPC = 6;  // 6 warps x 16 KB + model: two CTAs (12 trajectories) per SM
+struct KsSmemCounts {
+  static constexpr int PER_WARP = 6 * KW_MAT + 5 * 16;
+};
+
+__global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp) {
+  extern __shared__ __align__(16) double kw_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const cdk_desc& d = a.d;
+  const int n = d.n, K = d.K;
+  const long long traj = (long long)blockIdx.x * KS_WPC + warp;
+  double* model = kw_smem + (model_per_warp ? warp * KwSmemCounts::PER_MODEL : 0);
+  double* wbase = kw_smem + (model_per_warp ? KS_WPC : 1) * KwSmemCounts::PER_MODEL + warp * KsSmemCounts::PER_WARP;
+  double* sF = model;
+  double* sLQL = sF + KW_MAT;
+  double* sb = sLQL + KW_MAT + 2 * KW_MAT8;
+  double* sPs = wbase;        // smoothed covariance of step k+1
+  double* sPf = sPs + KW_MAT;  // filtered covariance of step k
+  double* sYA = sPf + KW_MAT;  // stage buffer, then A
+  double* sYQ = sYA + KW_MAT;  // stage buffer, then sym(P_pred) -> its Cholesky factor -> C (P_s^+ - P_pred)
+  double* sT = sYQ + KW_MAT;   // stage buffer, then A P_f -> C^T
+  double* sDm = sT + KW_MAT;   // P_s^+ - P_pred
+  double* sms = sDm + KW_MAT;
+  double* smf = sms + 16;
+  double* srv = smf + 16;
+  double* smn = srv + 16;
+  double* sinv = smn + 16;
+
+  const long long tj = traj < d.N ? traj : d.N - 1;
+  if (model_per_warp || warp == 0) load_model_kw(a, tj, model, sYA, sYQ, sT);
+  __syncthreads();  // the only CTA-wide barrier: the shared model block is ready
+  if (traj >= d.N) return;
+  for (int e = lane; e < KsSmemCounts::PER_WARP; e += 32) wbase[e] = 0.0;
+  __syncwarp();
+
+  const double* __restrict__ Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  const double* __restrict__ FMg = a.in[CDK_IN_FM] + traj * a.in_stride[CDK_IN_FM];
+  const double* __restrict__ FPg = a.in[CDK_IN_FP] + traj * a.in_stride[CDK_IN_FP];
+  double* __restrict__ SMg = static_cast<double*>(a.out[CDK_OUT_SM]) + traj * (long long)K * n;
+  double* __restrict__ SPg = static_cast<double*>(a.out[CDK_OUT_SP]) + traj * (long long)K * n * n;
+  double* __restrict__ SCg =
+      a.out[CDK_OUT_SCROSS] ? static_cast<double*>(a.out[CDK_OUT_SCROSS]) + traj * (long long)(K - 1) * n * n : nullptr;
+  const double dt0 = d.dt0, tol = clip_tol<double>();
+  int status = 0;
+
+  // last step: smoothed = filtered (:813-814)
+  for (int e = lane; e < n * n; e += 32) {
+    const double v = FPg[(long long)(K - 1) * n * n + e];
+    sPs[(e / n) * KW_LD + (e % n)] = v;
+    SPg[(long long)(K - 1) * n * n + e] = v;
+  }
+  if (lane < n) {
+    const double v = FMg[(long long)(K - 1) * n + lane];
+    sms[lane] = v;
+    SMg[(long long)(K - 1) * n + lane] = v;
+  }
+  __syncwarp();
+
+  for (int k = K - 2; k >= 0; --k) {
+    for (int e = lane; e < n * n; e += 32) sPf[(e / n) * KW_LD + (e % n)] = FPg[(long long)k * n * n + e];
+    if (lane < n) smf[lane] = FMg[(long long)k * n + lane];
+    const double t0 = Tm[k], t1 = Tm[k + 1];
+    F16 yA, yQ;
+    if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) status = 2;
+    store_c<2, 2>(yA.v, sYA);
+    __syncwarp();
+    {
+      F16 ap;
+      mm<false, false, 16, 2, 2>(ap.v, sYA, sPf);  // A P_f
+      store_c<2, 2>(ap.v, sT);
+      if (lane < 16) {  // rv = m_s^+ - A m_f - b   (:763-766)
+        double s = 0.0;
+        for (int q = 0; q < n; ++q) s += sYA[lane * KW_LD + q] * smf[q];
+        srv[lane] = lane < n ? sms[lane] - s - sb[lane] : 0.0;
+      }
+      __syncwarp();
+      F16 pp, ps, ppt;
+      mm<false, true, 16, 2, 2>(pp.v, sT, sYA);  // A P_f A^T
+      load_c<2, 2>(ps.v, sPs);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        (&pp.v[0][0][0])[i] += (&yQ.v[0][0][0])[i];                      // P_pred = A P_f A^T + Q
+        (&ps.v[0][0][0])[i] -= (&pp.v[0][0][0])[i];                      // P_s^+ - P_pred
+      }
+      store_c<2, 2>(ps.v, sDm);
+      store_c<2, 2>(pp.v, sYQ);
+      __syncwarp();
+      load_ct(ppt.v, sYQ);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&pp.v[0][0][0])[i] = 0.5 * ((&pp.v[0][0][0])[i] + (&ppt.v[0][0][0])[i]);  // symmetrize
+      store_c<2, 2>(pp.v, sYQ);
+      __syncwarp();
+    }
+    // ---- psd_solve: Cholesky of sym(P_pred) + 1e-9 I, in place (lower triangle of sYQ), lane = row ----
+    for (int j = 0; j < n; ++j) {
+      if (lane >= j && lane < n) {
+        double sjj = sYQ[j * KW_LD + j] + 1e-9;
+        for (int q = 0; q < j; ++q) sjj -= sYQ[j * KW_LD + q] * sYQ[j * KW_LD + q];
+        const double dj = sqrt(sjj);
+        const double idj = 1.0 / dj;
+        if (lane == j) {
+          sinv[j] = idj;
+        } else {
+          double v = sYQ[lane * KW_LD + j];
+          for (int q = 0; q < j; ++q) v -= sYQ[lane * KW_LD + q] * sYQ[j * KW_LD + q];
+          sYQ[lane * KW_LD + j] = v * idj;
+        }
+      }
+      __syncwarp();
+    }
+    // ---- C^T = (P_pred + boost)^-1 A P_f: one right-hand-side column per lane, in place in sT ----
+    if (lane < n) {
+      for (int i = 0; i < n; ++i) {
+        double v = sT[i * KW_LD + lane];
+        for (int q = 0; q < i; ++q) v -= sYQ[i * KW_LD + q] * sT[q * KW_LD + lane];
+        sT[i * KW_LD + lane] = v * sinv[i];
+      }
+      for (int i = n - 1; i >= 0; --i) {
+        double v = sT[i * KW_LD + lane];
+        for (int q = i + 1; q < n; ++q) v -= sYQ[q * KW_LD + i] * sT[q * KW_LD + lane];
+        sT[i * KW_LD + lane] = v * sinv[i];
+      }
+    }
+    __syncwarp();
+    {
+      const double* sCt = sT;
+      F16 cd, cps;
+      mm<true, false, 16, 2, 2>(cd.v, sCt, sDm);   // C (P_s^+ - P_pred)
+      mm<true, false, 16, 2, 2>(cps.v, sCt, sPs);  // C P_s^+
+      if (lane < 16) {  // m_s = m_f + C rv
+        double s = 0.0;
+        for (int q = 0; q < n; ++q) s += sCt[q * KW_LD + lane] * srv[q];
+        smn[lane] = lane < n ? smf[lane] + s : 0.0;
+      }
+      __syncwarp();
+      store_c<2, 2>(cd.v, sYQ);  // the Cholesky factor is no longer needed
+      if (SCg) {                 // cross = C P_s^+ + m_s m_s^{+T}   (:771)
+        const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+          for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const int i = 8 * rb + gid, j = 8 * cb + 2 * tig + r;
+              cps.v[rb][cb][r] += smn[i] * sms[j];
+            }
+        store_global(cps.v, SCg + (long long)k * n * n, n);
+      }
+      __syncwarp();
+      F16 pn, pf;
+      mm<false, false, 16, 2, 2>(pn.v, sYQ, sCt);  // C (P_s^+ - P_pred) C^T
+      load_c<2, 2>(pf.v, sPf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&pn.v[0][0][0])[i] += (&pf.v[0][0][0])[i];
+      __syncwarp();
+      store_c<2, 2>(pn.v, sPs);
+      store_global(pn.v, SPg + (long long)k * n * n, n);
+      if (lane < 16) sms[lane] = smn[lane];
+      if (lane < n) SMg[(long long)k * n + lane] = smn[lane];
+      __syncwarp();
+    }
+  }
+  if (lane == 0 && a.out[CDK_OUT_STATUS]) {
+    bool bad = false;
+    for (int i = 0; i < n; ++i) bad |= !isfinite(sms[i]);
+    if (status == 0 && bad) status = 1;
+    if (status != 0) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;  // keep the filter's status otherwise
+  }
+}
+
 }  // namespace
 
-// Fast path coverage: KF filter, fp64, n <= 16, m <= 8, no inputs, chain tableaux (every solver except Dopri5).
+// Fast path coverage: KF filter and type-1 smoother, fp64, n <= 16, m <= 8, no inputs, chain tableaux (every solver
+// except Dopri5).
 template <typename T>
 int launch_kf_warp(int algo, const KArgs<T>& a, cudaStream_t s) {
   return CDK_E_UNSUPPORTED;
@@ -426,7 +662,9 @@ int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
     const char* e = getenv("CDK_KF_WARP");
     return e && e[0] == '0';
   }();
-  if (disabled || algo != ALGO_KF_FILTER || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return CDK_E_UNSUPPORTED;
+  const bool smooth = algo == ALGO_KF_SMOOTH;
+  if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return CDK_E_UNSUPPORTED;
+  if (smooth && d.smoother_type != 1) return CDK_E_UNSUPPORTED;  // type 2 (backward ODE) stays on the generic kernel
   RtTab rt;
   if (!fill_rt_tab(d.solver, rt)) return CDK_E_ENUM;
   KwTab tab;
@@ -439,6 +677,16 @@ int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
   const uint32_t model_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) | (1u << CDK_IN_R) |
                               (1u << CDK_IN_B) | (1u << CDK_IN_D);
   const int model_per_warp = (d.batched_mask & model_mask) != 0;
+  if (smooth) {
+    const size_t smem = sizeof(double) * ((model_per_warp ? KS_WPC : 1) * KwSmemCounts::PER_MODEL + KS_WPC * KsSmemCounts::PER_WARP);
+    const long long blocks = (d.N + KS_WPC - 1) / KS_WPC;
+    if (blocks > 2147483647LL) return CDK_E_SIZE;
+    if (cudaFuncSetAttribute(kf_warp_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(kf_warp_smooth)");
+    kf_warp_smooth<<<(unsigned)blocks, 32 * KS_WPC, smem, s>>>(a, tab, model_per_warp);
+    note_launch();
+    return check_launch("kf_warp_smooth");
+  }
   const size_t smem = sizeof(double) * ((model_per_warp ? KW_WPC : 1) * KwSmemCounts::PER_MODEL + KW_WPC * KwSmemCounts::PER_WARP);
   const long long blocks = (d.N + KW_WPC - 1) / KW_WPC;
   if (blocks > 2147483647LL) return CDK_E_SIZE;

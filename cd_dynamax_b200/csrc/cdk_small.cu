@@ -20,6 +20,8 @@
 //    by step parity) -- with coalesced stores, instead of 24 lane-scattered 8-byte stores per step (32 L1 wavefronts
 //    each).  The worker critical path is update + substeps + ONE barrier per step.
 //  * 256-thread CTAs, 2 per SM: 148 * 2 * 224 = 66,304 >= 65,536 trajectories in ONE wave (128 registers/thread).
+#include <type_traits>
+
 #include "cdk_common.cuh"
 
 #include <cuda.h>
@@ -89,8 +91,12 @@ __device__ __forceinline__ void rk_step(const T* th, const T* lql, St<T, Drift::
   using TB = Tab<SOLVER>;
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
+  // The weighted stage sum is accumulated relative to the first non-zero weight, ksum = sum_i (b_i / b_i0) k_i, and added
+  // with ONE in-place fma y += (b_i0 dt) ksum: the same operation count as accumulating y + dt b_i k_i stage by stage, but
+  // the new state is written straight into the registers of the old one (no register copies at the loop back-edge).
+  constexpr int I0 = TB::b(0) != 0.0 ? 0 : (TB::S > 1 && TB::b(1) != 0.0 ? 1 : (TB::S > 2 && TB::b(2) != 0.0 ? 2 : 3));
   St<T, NX> k[TB::S];
-  St<T, NX> acc = y;
+  St<T, NX> ksum;
 #pragma unroll
   for (int i = 0; i < TB::S; ++i) {
     St<T, NX> yi = y;
@@ -105,15 +111,28 @@ __device__ __forceinline__ void rk_step(const T* th, const T* lql, St<T, Drift::
       }
     }
     ekf_rhs<T, Drift>(th, lql, yi, k[i]);
-    if (TB::b(i) != 0.0) {
-      const T c = T(TB::b(i)) * dt;
+    if (i == I0) {
+      ksum = k[i];
+    } else if (TB::b(i) != 0.0) {
+      const T c = T(TB::b(i) / TB::b(I0));
+      if (TB::b(i) == TB::b(I0)) {
 #pragma unroll
-      for (int e = 0; e < NX; ++e) acc.m[e] = fma(c, k[i].m[e], acc.m[e]);
+        for (int e = 0; e < NX; ++e) ksum.m[e] += k[i].m[e];
 #pragma unroll
-      for (int e = 0; e < NP; ++e) acc.P[e] = fma(c, k[i].P[e], acc.P[e]);
+        for (int e = 0; e < NP; ++e) ksum.P[e] += k[i].P[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < NX; ++e) ksum.m[e] = fma(c, k[i].m[e], ksum.m[e]);
+#pragma unroll
+        for (int e = 0; e < NP; ++e) ksum.P[e] = fma(c, k[i].P[e], ksum.P[e]);
+      }
     }
   }
-  y = acc;
+  const T w = T(TB::b(I0)) * dt;
+#pragma unroll
+  for (int e = 0; e < NX; ++e) y.m[e] = fma(w, ksum.m[e], y.m[e]);
+#pragma unroll
+  for (int e = 0; e < NP; ++e) y.P[e] = fma(w, ksum.P[e], y.P[e]);
 }
 
 // Measurement update + log-likelihood increment (inference_ekf.py:285-289, :153-199; psd_solve utils.py:202-207).
@@ -656,11 +675,32 @@ struct alignas(128) LWSmem {
   // followed by the model constants: NPAR values (shared) or 32 * NPAR (one block per lane when batched)
 };
 
-constexpr int LW_WPC = 7;  // independent warps per CTA: 293 CTAs of 224 trajectories = 2 CTAs / SM in one wave
+// Write one staging row (LEN elements of step parity ROW) of this lane's [2][LEN] block.  fp64: the block starts 16-byte
+// aligned (lane stride 16 LEN bytes), so all but at most one element go out as 128-bit stores (conflict-free per quarter
+// warp) -- 14 shared-memory stores per step instead of 24.
+template <int ROW, int LEN, typename T>
+__device__ __forceinline__ void stage_row(T* lane_block, const T (&v)[LEN]) {
+  T* p = lane_block + ROW * LEN;
+  if constexpr (sizeof(T) == 8) {
+    constexpr int FIRST = (ROW * LEN) & 1;
+    if (FIRST) p[0] = v[0];
+#pragma unroll
+    for (int e = FIRST; e + 1 < LEN; e += 2) *reinterpret_cast<double2*>(p + e) = make_double2(v[e], v[e + 1]);
+    if ((LEN - FIRST) & 1) p[LEN - 1] = v[LEN - 1];
+  } else {
+#pragma unroll
+    for (int e = 0; e < LEN; ++e) p[e] = v[e];
+  }
+}
 
-template <typename T, class Drift, int NY, int SOLVER>
-__global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps,
-                                                               const int warp_bytes) {
+// Warps per CTA: 7 (two CTAs per SM, <= 128 registers) or 14 (ONE CTA per SM, <= 144 registers: the drift parameters and
+// L Qc L^T then live in registers instead of being re-read from shared memory every substep).  Either way 65,536
+// trajectories are one wave of 2,048 warps over 148 SMs.  CDK_LW_WPC selects; CDK_LW_SYNC=p adds a CTA-wide barrier every p
+// steps (keeps the warps of an SM sub-partition progressing together instead of two of them finishing early).
+template <typename T, class Drift, int NY, int SOLVER, int WPC>
+__global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
+    ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps, const int warp_bytes, const int sync_period,
+                 const int use_token) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
@@ -674,18 +714,35 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
   const long long N = a.d.N;
   const int K = a.d.K;
   const int lane = threadIdx.x & 31;
-  const long long traj0 = ((long long)blockIdx.x * LW_WPC + warp) * 32;
-  if (traj0 >= N) return;  // whole warp out of range (warps never synchronise with each other)
+  const long long cta0 = (long long)blockIdx.x * WPC * 32;
+  const long long traj0 = cta0 + warp * 32;
+  // FP64-pipe token (one FIFO ticket lock per SM sub-partition).  A single warp inside the RK substep loop already keeps
+  // the FP64 pipe 97 % busy (scripts/micro/rk4_pipe.cu: 456 cycles per substep alone, 444.5 when shared), so sharing the
+  // loop between the 3-4 warps of a sub-partition gains nothing -- and it synchronises them: while one warp is in its
+  // latency-bound measurement update the others get its pipe share and catch up, so phase differences halve every step
+  // until all warps update at the same time and the pipe idles (measured: 14,300 cycles per step on a 4-warp
+  // sub-partition against 4 x 2,670 of substep work).  With the token exactly one warp per sub-partition integrates while
+  // the others update, stage outputs and issue their TMA stores; FIFO order keeps them a quarter period apart.
+  __shared__ unsigned lw_token[4][2];  // [sub-partition][next ticket, now serving]
+  if (threadIdx.x < 8) (&lw_token[0][0])[threadIdx.x] = 0u;
+  __syncthreads();
+  if (traj0 >= N) return;  // whole warp out of range (warps never wait for it: see live_threads)
+  unsigned hw_warp;
+  asm volatile("mov.u32 %0, %warpid;" : "=r"(hw_warp));
+  volatile unsigned* const tok = &lw_token[hw_warp & 3][0];
+  const long long rem_cta = N - cta0;
+  const int live_threads = 32 * (int)(rem_cta >= 32 * WPC ? WPC : (rem_cta + 31) / 32);
   const long long traj = traj0 + lane;
   const bool live = traj < N;
   const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0;
+  // log-likelihood-only calls (output_fields = []) skip the staging stores and the output flush altogether
+  const bool any_out = a.out[CDK_OUT_FM] || a.out[CDK_OUT_FP] || a.out[CDK_OUT_PM] || a.out[CDK_OUT_PP];
+  const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0 && any_out;
   unsigned long long* const trace = g_lw_trace;
   const unsigned long long t_entry = trace ? globaltimer() : 0ull;
-
   if ((par_batched && live) || (!par_batched && lane == 0)) {
     T* par = par_batched ? parbase + lane * NPAR : parbase;
     const long long tj = par_batched ? traj : 0;
@@ -740,8 +797,14 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
   }
   __syncwarp();
   const T* par = par_batched ? parbase + lane * NPAR : parbase;
-  const T* th = par;
-  const T* lql = par + NTH;
+  // WPC == 14: theta and L Qc L^T stay in registers for the whole kernel; WPC == 7: re-read from shared memory
+  T th_r[NTH], lql_r[NP];
+#pragma unroll
+  for (int i = 0; i < NTH; ++i) th_r[i] = par[i];
+#pragma unroll
+  for (int i = 0; i < NP; ++i) lql_r[i] = par[NTH + i];
+  const T* th = WPC == 7 ? par : th_r;
+  const T* lql = WPC == 7 ? par + NTH : lql_r;
   const T* Hs = par + NTH + NP;
   const T* ds = Hs + NY * NX;
   const T* Rs = ds + NY;
@@ -766,9 +829,35 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   };
+  // one RK step with the diffrax stepping rule (tnext = tprev + dt0, clipped to t1 within tol)
+  auto substep = [&](T& tprev, T& tnext, const T t1) {
+    rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
+    tprev = tnext;
+    const T cand = tprev + dt0;
+    tnext = cand > t1 - tol ? t1 : cand;
+  };
+  auto poison = [&]() {
+    status = 2;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
+  };
 
-  for (int k = 0; k < K; ++k) {
-    const int row = k & 1;
+  // current mean / full covariance -> this lane's staging rows of step parity `row`
+  auto stage = [&](auto rowc, T* mrow, T* prow) {
+    constexpr int row = decltype(rowc)::value;
+    T full[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) full[i * NX + j] = s.P[pidx<NX>(i, j)];
+    stage_row<row, NX>(mrow, s.m);
+    stage_row<row, NX * NX>(prow, full);
+  };
+  // one observation step; `row` (= k & 1, the staging row) is a compile-time constant: the k loop is unrolled by two
+  auto step = [&](auto rowc, const int k) {
+    constexpr int row = decltype(rowc)::value;
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // own loads of steps <= k+1 have landed
     T tprev = T(0), t1 = T(0);
     if (live) {
@@ -802,50 +891,39 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
-    if (live) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) sm.fm[lane][row][i] = s.m[i];
-#pragma unroll
-      for (int i = 0; i < NX; ++i)
-#pragma unroll
-        for (int j = 0; j < NX; ++j) sm.fp[lane][row][i * NX + j] = s.P[pidx<NX>(i, j)];
-    }
+    if (live && any_out) stage(rowc, &sm.fm[lane][0][0], &sm.fp[lane][0][0]);
     if (use_tma && row == 1) {  // the filtered rows of this block are complete: store them while the gap is integrated
       __syncwarp();
       if (lane == 0) tma_pair(0, k - 1);
     }
+    unsigned ticket = 0;
+    if (use_token) {
+      if (lane == 0) {
+        ticket = atomicAdd(const_cast<unsigned*>(tok), 1u);
+        while (tok[1] != ticket) {
+        }
+      }
+      __syncwarp();
+    }
     if (live) {
       T tnext = fmin(tprev + dt0, t1);
       int nsteps = 0;
-      while (tprev < t1) {
-        if (nsteps >= max_steps) {
-          status = 2;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
-#pragma unroll
-          for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
-          break;
-        }
-        rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
+      while (tprev < t1 && nsteps < max_steps) {
+        substep(tprev, tnext, t1);
         ++nsteps;
-        tprev = tnext;
-        const T cand = tprev + dt0;
-        tnext = cand > t1 - tol ? t1 : cand;
       }
+      if (tprev < t1) poison();  // diffrax max_steps exceeded: the reference result is NaN
+    }
+    if (use_token) {
+      __syncwarp();
+      if (lane == 0) tok[1] = ticket + 1u;
     }
     if (use_tma && row == 0 && k > 0) {  // the PM/PP store of the previous block was issued one whole step ago
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
-    if (live) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) sm.pm[lane][row][i] = s.m[i];
-#pragma unroll
-      for (int i = 0; i < NX; ++i)
-#pragma unroll
-        for (int j = 0; j < NX; ++j) sm.pp[lane][row][i * NX + j] = s.P[pidx<NX>(i, j)];
-    }
-    if (row == 1 || k == K - 1) {
+    if (live && any_out) stage(rowc, &sm.pm[lane][0][0], &sm.pp[lane][0][0]);
+    if (any_out && (row == 1 || k == K - 1)) {
       __syncwarp();
       if (use_tma) {
         if (lane == 0) tma_pair(2, k - 1);
@@ -867,6 +945,13 @@ __global__ void __launch_bounds__(32 * LW_WPC, 2) ekf_small_lw(const KArgs<T> a,
         __syncwarp();
       }
     }
+  };
+
+  for (int k = 0; k < K; k += 2) {
+    step(std::integral_constant<int, 0>{}, k);
+    if (k + 1 < K) step(std::integral_constant<int, 1>{}, k + 1);
+    if (sync_period > 0 && ((k >> 1) + 1) % sync_period == 0)
+      asm volatile("bar.sync 1, %0;" ::"r"(live_threads) : "memory");
   }
   if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (trace && lane == 0) {
@@ -958,17 +1043,31 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   V5Maps maps;
   if (mode == 2) {
     using SW = LWSmem<T, NX, NY>;
+    static const int wpc_env = []() {
+      const char* e = getenv("CDK_LW_WPC");
+      return e && atoi(e) == 7 ? 7 : 14;
+    }();
+    static const int sync_period = []() {
+      const char* e = getenv("CDK_LW_SYNC");
+      return e ? atoi(e) : 0;
+    }();
     const int warp_bytes = (int)((sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1) + 127) & ~size_t(127));
-    const size_t smw = (size_t)warp_bytes * LW_WPC;
-    const long long wblocks = (a.d.N + 32 * LW_WPC - 1) / (32 * LW_WPC);
+    const int wpc = (size_t)warp_bytes * wpc_env > 227 * 1024 ? 7 : wpc_env;  // per-lane parameter blocks: 2 CTAs of 7 warps
+    const size_t smw = (size_t)warp_bytes * wpc;
+    const long long wblocks = (a.d.N + 32 * wpc - 1) / (32 * wpc);
     if (wblocks > 2147483647LL) return CDK_E_SIZE;
     make_maps<T>(a, NX, 32, maps);
-    auto kw = ekf_small_lw<T, Drift, NY, SOLVER>;
+    auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7> : ekf_small_lw<T, Drift, NY, SOLVER, 14>;
     if (smw > 48 * 1024) {
       if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw) != cudaSuccess)
         return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
     }
-    kw<<<(unsigned)wblocks, 32 * LW_WPC, smw, s>>>(a, maps, warp_bytes);
+    static const int token_env = []() {
+      const char* e = getenv("CDK_LW_TOKEN");
+      return e ? atoi(e) : 1;
+    }();
+    const int use_token = wpc == 14 ? token_env : 0;  // with two CTAs per SM the lock would have to span CTAs
+    kw<<<(unsigned)wblocks, 32 * wpc, smw, s>>>(a, maps, warp_bytes, sync_period, use_token);
     note_launch();
     return check_launch("ekf_small_lw");
   }

@@ -24,6 +24,7 @@ ap.add_argument("--n", type=int, default=65536)
 ap.add_argument("--k", type=int, default=1000)
 ap.add_argument("--out", default="gpurun_out/trace_lw.json")
 ap.add_argument("--regular", action="store_true", help="regular grid: every gap has exactly 4 substeps")
+ap.add_argument("--no-outputs", action="store_true", help="log-likelihood only (output_fields=[])")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, K = a.n, a.k
@@ -43,15 +44,16 @@ params = cd.ParamsCDNLGSSM(
                                          emission_cov=cd.LearnableMatrix(T(np.eye(1)))))
 hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
 lib = L.lib()
+kw = dict(output_fields=[]) if a.no_outputs else {}
 nw = (N + 31) // 32
 buf = torch.zeros(nw * 4, dtype=torch.int64, device=dev)
 for _ in range(2):
-    cd.cdnlgssm_filter(params, y, t[..., None], hp)
+    cd.cdnlgssm_filter(params, y, t[..., None], hp, **kw)
 torch.cuda.synchronize()
 L.check(lib.cdk_debug_set_trace(ctypes.c_void_p(buf.data_ptr())), "set_trace")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-cd.cdnlgssm_filter(params, y, t[..., None], hp)
+cd.cdnlgssm_filter(params, y, t[..., None], hp, **kw)
 e1.record()
 torch.cuda.synchronize()
 L.check(lib.cdk_debug_set_trace(None), "clear_trace")

@@ -376,3 +376,35 @@ def test_chunked_host_streaming_is_bit_identical(monkeypatch):
     s_one = cd.cdlgssm_smoother(linear_params_api(gl), y1, t1[:, None], kh)
     assert np.array_equal(s_chunked.smoothed_means[7], s_one.smoothed_means)
     assert np.array_equal(s_chunked.smoothed_covariances[19], s_one.smoothed_covariances)
+
+
+# ---- CD-KF warp kernels (DMMA, one warp per trajectory): seeded oracle parity at ragged shapes ----------------------
+@pytest.mark.parametrize("N,K,n,m,solver,batched_model", [
+    (1, 1, 16, 4, "rk4", False), (7, 2, 16, 4, "rk4", False), (13, 9, 5, 2, "heun", False),
+    (25, 12, 16, 8, "bosh3", True), (6, 5, 3, 1, "euler", False)])
+def test_kf_warp_filter_and_smoother_vs_oracle(N, K, n, m, solver, batched_model):
+    cd = api()
+    rng = np.random.default_rng(100 + N + K)
+    lead = (N,) if batched_model else ()
+    F = -0.5 * np.eye(n) + 0.3 * rng.standard_normal(lead + (n, n)) / np.sqrt(n)
+    Lm = np.eye(n) + 0.1 * rng.standard_normal((n, n))
+    A = rng.standard_normal((m, m))
+    g = dict(m0=rng.standard_normal(n), P0=np.eye(n) * 0.7, F=F, b=0.1 * rng.standard_normal(n), B=None, L=Lm,
+             Qc=0.1 * np.eye(n) + 0.01, H=rng.standard_normal((m, n)), d=0.2 * rng.standard_normal(m), D=None,
+             R=0.1 * (A @ A.T + np.eye(m)))
+    gaps = 0.04 * rng.uniform(0.5, 1.5, size=(N, K))
+    gaps[:, 0] = 0.0
+    t = np.cumsum(gaps, axis=1)
+    y = rng.standard_normal((N, K, m))
+    hp = cd.KFHyperParams(dt_final=0.03, diffeqsolve_settings={"solver": solver, "dt0": 0.01})
+    s = cd.cdlgssm_smoother(linear_params_api(g), y, t[..., None], hp)
+    f = cd.cdlgssm_filter(linear_params_api(g), y, t[..., None], hp)
+    po = o.LinearParams(m0=g["m0"], P0=g["P0"], F=F, L=Lm, Qc=g["Qc"], H=g["H"], R=g["R"], b=g["b"], d=g["d"])
+    r = o.cdlgssm_smoother(po, y, t, dt_final=0.03, settings=o.SolverSettings(solver, 0.01))
+    assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < TOL
+    for fld in FIELDS:
+        assert scaled_err(getattr(f, fld), r[fld]) < TOL, fld
+    for fld in ("smoothed_means", "smoothed_covariances", "smoothed_cross_covariances"):
+        if r[fld].size:
+            assert scaled_err(getattr(s, fld), r[fld]) < 1e-8, fld
+    assert s.smoothed_cross_covariances.shape == (N, K - 1, n, n)
