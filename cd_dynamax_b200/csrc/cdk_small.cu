@@ -716,14 +716,13 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   const int lane = threadIdx.x & 31;
   const long long cta0 = (long long)blockIdx.x * WPC * 32;
   const long long traj0 = cta0 + warp * 32;
-  // FP64-pipe token (one FIFO ticket lock per SM sub-partition).  A single warp inside the RK substep loop already keeps
-  // the FP64 pipe 97 % busy (scripts/micro/rk4_pipe.cu: 456 cycles per substep alone, 444.5 when shared), so sharing the
-  // loop between the 3-4 warps of a sub-partition gains nothing -- and it synchronises them: while one warp is in its
-  // latency-bound measurement update the others get its pipe share and catch up, so phase differences halve every step
-  // until all warps update at the same time and the pipe idles (measured: 14,300 cycles per step on a 4-warp
-  // sub-partition against 4 x 2,670 of substep work).  With the token exactly one warp per sub-partition integrates while
-  // the others update, stage outputs and issue their TMA stores; FIFO order keeps them a quarter period apart.
-  __shared__ unsigned lw_token[4][2];  // [sub-partition][next ticket, now serving]
+  // Optional FP64-pipe semaphore (CDK_LW_TOKEN = permits, default off): at most `permits` warps of an SM sub-partition are
+  // inside the RK substep loop at a time (FIFO tickets), the others update / stage / store.  Built to break the convoy
+  // that forms because warps sharing a pipe equally re-synchronise their phases; measured no gain (7.2-7.5 ms with 2-3
+  // permits, 8.1 ms with 1, 7.3 ms without), because the loop is bound by register-file bandwidth, not latency: a DFMA
+  // with three distinct register operands issues every 3 cycles, not 2 (scripts/micro/fp64_regs.cu), and the update phase
+  // of one warp already hides behind the substeps of the others.  Kept for experiments.
+  __shared__ unsigned lw_token[4][2];  // [sub-partition][next ticket, tenures completed]
   if (threadIdx.x < 8) (&lw_token[0][0])[threadIdx.x] = 0u;
   __syncthreads();
   if (traj0 >= N) return;  // whole warp out of range (warps never wait for it: see live_threads)
@@ -897,13 +896,11 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
       if (lane == 0) tma_pair(0, k - 1);
     }
     unsigned ticket = 0;
-    if (use_token) {
-      if (lane == 0) {
-        ticket = atomicAdd(const_cast<unsigned*>(tok), 1u);
-        while (tok[1] != ticket) {
-        }
+    if (use_token) {  // warp-uniform spin: every lane polls the same shared-memory word (a broadcast read)
+      if (lane == 0) ticket = atomicAdd(const_cast<unsigned*>(tok), 1u);
+      ticket = __shfl_sync(0xffffffffu, ticket, 0);
+      while ((int)(ticket - tok[1]) >= use_token) {  // use_token = permits: warps inside the substep loop at a time
       }
-      __syncwarp();
     }
     if (live) {
       T tnext = fmin(tprev + dt0, t1);
@@ -916,7 +913,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     }
     if (use_token) {
       __syncwarp();
-      if (lane == 0) tok[1] = ticket + 1u;
+      if (lane == 0) atomicAdd(const_cast<unsigned*>(tok + 1), 1u);
     }
     if (use_tma && row == 0 && k > 0) {  // the PM/PP store of the previous block was issued one whole step ago
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -1064,7 +1061,7 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
     }
     static const int token_env = []() {
       const char* e = getenv("CDK_LW_TOKEN");
-      return e ? atoi(e) : 1;
+      return e ? atoi(e) : 0;
     }();
     const int use_token = wpc == 14 ? token_env : 0;  // with two CTAs per SM the lock would have to span CTAs
     kw<<<(unsigned)wblocks, 32 * wpc, smw, s>>>(a, maps, warp_bytes, sync_period, use_token);
