@@ -14,7 +14,7 @@ ORDERS = {"zeroth": 0, "first": 1, "second": 2}
 ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
-                 "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
+                 "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
                  "cdk_last_error"]
 
 
@@ -69,6 +69,8 @@ def lib():
         fn = getattr(L, name)
         fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         fn.restype = ctypes.c_int
+    L.cdk_fma3_probe_f64.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.cdk_fma3_probe_f64.restype = ctypes.c_int
     L.cdk_debug_set_trace.argtypes = [ctypes.c_void_p]
     L.cdk_debug_set_trace.restype = ctypes.c_int
     L.cdk_launch_count.restype = ctypes.c_int64

@@ -970,6 +970,317 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   }
 }
 
+// ======================================================================================================================
+// Variant C: TRAJECTORY POOL PER WARP.  The two structural losses of variant B are (i) lock-step gaps -- every gap of a
+// warp's 32 trajectories runs to the warp-wide maximum substep count (6 on the benchmark grid against a mean of 4.5) --
+// and (ii) 2,048 warps over 592 sub-partitions: 272 of them hold four warps, the rest three, and the kernel ends with
+// the slowest.  Here a CTA is 12 warps (three per sub-partition, one CTA per SM) and a warp owns a POOL of up to 40
+// trajectories (37 on the benchmark: 148 x 12 x 37 >= 65,536) whose canonical state lives in its private shared memory.
+// The warp is a tiny scheduler: a lane holds one trajectory for the length of one gap, integrates it one RK substep per
+// loop iteration and hands it back; trajectories whose gap is complete queue up (FIFO, so nobody falls behind) and are
+// processed -- `thresh` or more at a time -- by an UPDATE PASS in which lane i takes the i-th waiting trajectory at
+// whatever observation index it has reached (measurement update, log-likelihood, output rows), after which free lanes
+// pick them up again.  Lanes never idle through somebody else's longer gap, nothing ever synchronises across warps, and
+// the per-trajectory arithmetic is exactly that of variant B (bit-identical results).
+// Outputs go straight from registers to HBM in the update pass: a lane writes the prediction row of step k-1 and the
+// filtered row of step k of ITS trajectory with 128-bit stores (rows are 24 / 72 bytes, so at most one 8-byte store per
+// row); the 126 MB L2 merges the rows of consecutive steps into full lines before they reach DRAM.
+// Observations: y_{k+1} and t_{k+2} are prefetched with cp.async into a two-deep per-trajectory ring during pass k.
+// ======================================================================================================================
+constexpr int PL_WPC = 12;  // warps per CTA
+constexpr int PL_PP = 40;   // largest pool per warp
+
+template <int NX, int NY>
+struct alignas(16) PoolSmem {
+  double cm[NX][PL_PP];                                   // canonical mean, structure-of-arrays
+  double cP[NX * (NX + 1) / 2][PL_PP];                    // canonical covariance (packed upper triangle)
+  double ct0[PL_PP], ct1[PL_PP], cll[PL_PP], csp[PL_PP];  // gap start / end, log-likelihood, running product of S
+  double py[2][NY][PL_PP], pt[2][PL_PP];                  // prefetched y_k and t_{k+1}, ring slot k & 1
+  int ck[PL_PP];                                          // next observation index
+  int cflag[PL_PP];                                       // bits 0..1 status, bit 2 "S was not positive"
+  unsigned char rq[64], nq[64];                           // FIFO rings: ready for a lane / waiting for an update pass
+};
+
+// One output row (LEN doubles at row index `row` of a [rows][LEN] array whose base is 16-byte aligned): 128-bit stores
+// wherever the address allows (row * LEN * 8 is 16-byte aligned iff row is even for odd LEN).
+template <int LEN>
+__device__ __forceinline__ void store_row_f64(double* __restrict__ base, long long row, const double (&v)[LEN]) {
+  double* p = base + row * LEN;
+  if ((LEN & 1) == 0 || (row & 1) == 0) {
+#pragma unroll
+    for (int e = 0; e + 1 < LEN; e += 2) *reinterpret_cast<double2*>(p + e) = make_double2(v[e], v[e + 1]);
+    if (LEN & 1) p[LEN - 1] = v[LEN - 1];
+  } else {
+    p[0] = v[0];
+#pragma unroll
+    for (int e = 1; e + 1 < LEN; e += 2) *reinterpret_cast<double2*>(p + e) = make_double2(v[e], v[e + 1]);
+  }
+}
+
+template <class Drift, int NY, int SOLVER>
+__global__ void __launch_bounds__(32 * PL_WPC, 1)
+    ekf_small_pool(const KArgs<double> a, const int pool, const int thresh, const int vec_out) {
+  using T = double;
+  constexpr int NX = Drift::NX;
+  constexpr int NP = St<T, NX>::NP;
+  constexpr int NTH = Drift::NTHETA;
+  using S = PoolSmem<NX, NY>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S& sm = *reinterpret_cast<S*>(smem_raw + (size_t)warp * sizeof(S));
+  const long long N = a.d.N;
+  const int K = a.d.K;
+  const long long gw = (long long)blockIdx.x * PL_WPC + warp;
+  const long long traj0 = gw * pool;
+  if (traj0 >= N) return;
+  const int np = (int)((N - traj0) < pool ? (N - traj0) : pool);  // trajectories in this warp's pool
+  unsigned long long* const trace = g_lw_trace;
+  const unsigned long long t_entry = trace ? globaltimer() : 0ull;
+
+  // model constants: shared by all trajectories (per-trajectory parameter blocks take variant B), kept in registers
+  T th[NTH], lql[NP], Hs[NY * NX], ds[NY], Rs[NY * NY];
+  {
+    const T* thg = a.in[CDK_IN_F];
+    const T* Lm = a.in[CDK_IN_L];
+    const T* Qc = a.in[CDK_IN_QC];
+#pragma unroll
+    for (int i = 0; i < NTH; ++i) th[i] = thg[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        T acc = T(0);
+        for (int p = 0; p < NX; ++p) {
+          T lq = T(0);
+          for (int q = 0; q < NX; ++q) lq += Lm[i * NX + q] * Qc[q * NX + p];
+          acc += lq * Lm[j * NX + p];
+        }
+        lql[pidx<NX>(i, j)] = acc;
+      }
+#pragma unroll
+    for (int i = 0; i < NY * NX; ++i) Hs[i] = a.in[CDK_IN_H][i];
+#pragma unroll
+    for (int i = 0; i < NY; ++i) ds[i] = a.in[CDK_IN_D][i];
+#pragma unroll
+    for (int i = 0; i < NY * NY; ++i) Rs[i] = a.in[CDK_IN_R][i];
+  }
+  const T* __restrict__ Yg = a.in[CDK_IN_Y] + traj0 * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Tg = a.in[CDK_IN_T] + traj0 * a.in_stride[CDK_IN_T];
+  const long long ystride = a.in_stride[CDK_IN_Y], tstride = a.in_stride[CDK_IN_T];
+  // canonical state of every pool member = the prior; all of them queue for their first update
+  for (int u = lane; u < np; u += 32) {
+    const long long tj = traj0 + u;
+    const T* m0 = a.in[CDK_IN_M0] + tj * a.in_stride[CDK_IN_M0];
+    const T* P0 = a.in[CDK_IN_P0] + tj * a.in_stride[CDK_IN_P0];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) sm.cm[i][u] = m0[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) sm.cP[pidx<NX>(i, j)][u] = P0[i * NX + j];
+    sm.ct0[u] = T(0);
+    sm.ct1[u] = Tg[u * tstride];  // "end of the previous gap" of step 0 = t_0
+    sm.cll[u] = T(0);
+    sm.csp[u] = T(1);
+#pragma unroll
+    for (int c = 0; c < NY; ++c) sm.py[0][c][u] = Yg[u * ystride + c];
+    sm.pt[0][u] = K > 1 ? Tg[u * tstride + 1] : T(0);
+    sm.ck[u] = 0;
+    sm.cflag[u] = 0;
+    sm.nq[u] = (unsigned char)u;
+  }
+  __syncwarp();
+  T* const FM = static_cast<T*>(a.out[CDK_OUT_FM]);
+  T* const FP = static_cast<T*>(a.out[CDK_OUT_FP]);
+  T* const PM = static_cast<T*>(a.out[CDK_OUT_PM]);
+  T* const PP = static_cast<T*>(a.out[CDK_OUT_PP]);
+  T* const LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
+  const T dt0 = T(a.d.dt0), dtf = T(a.d.dt_final), tol = clip_tol<T>();
+  const int max_steps = a.d.max_steps, num_iter = a.d.num_iter;
+
+  // FIFO rings (indices are warp-uniform registers, entries live in shared memory)
+  unsigned nq_head = 0, nq_cnt = (unsigned)np;  // waiting for an update pass
+  unsigned rq_head = 0, rq_cnt = 0;             // updated, waiting for a lane
+  int slot = -1;                                // pool member this lane integrates, or -1
+  int nsteps = 0;
+  St<T, NX> s;
+  T tprev = T(0), tnext = T(0), t1 = T(0);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) s.m[i] = T(0);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) s.P[i] = T(0);
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  for (;;) {
+    // ---- (A) free lanes pick up ready trajectories, oldest first ----
+    if (rq_cnt != 0u) {
+      const unsigned free_m = __ballot_sync(0xffffffffu, slot < 0);
+      if (free_m != 0u) {
+        const unsigned nfree = __popc(free_m);
+        const unsigned ntake = nfree < rq_cnt ? nfree : rq_cnt;
+        const unsigned myrank = __popc(free_m & lt_mask);
+        if (slot < 0 && myrank < ntake) {
+          const int mine = sm.rq[(rq_head + myrank) & 63u];
+          slot = mine;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) s.m[i] = sm.cm[i][mine];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) s.P[i] = sm.cP[i][mine];
+          tprev = sm.ct0[mine];
+          t1 = sm.ct1[mine];
+          tnext = fmin(tprev + dt0, t1);
+          nsteps = 0;
+        }
+        rq_head += ntake;
+        rq_cnt -= ntake;
+      }
+    }
+    const unsigned act_m = __ballot_sync(0xffffffffu, slot >= 0);
+    if (nq_cnt >= (unsigned)thresh || (act_m == 0u && nq_cnt != 0u)) {
+      // ---- (C) update pass: lane i takes the i-th waiting trajectory ----
+      const unsigned ntake = nq_cnt < 32u ? nq_cnt : 32u;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // observation prefetches issued by earlier passes have landed
+      __syncwarp();
+      const bool has = (unsigned)lane < ntake;
+      bool again = false;  // the trajectory goes back to the ready ring (it has observations left)
+      int us = -1;
+      if (has) {
+        us = sm.nq[(nq_head + lane) & 63u];
+        const long long tj = traj0 + us;
+        const int k = sm.ck[us];
+        St<T, NX> u;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) u.m[i] = sm.cm[i][us];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) u.P[i] = sm.cP[i][us];
+        const long long row = tj * (long long)K + k;
+        if (vec_out && k > 0) {  // the state before the update is the prediction made at step k - 1
+          T full[NX * NX];
+#pragma unroll
+          for (int i = 0; i < NX; ++i)
+#pragma unroll
+            for (int j = 0; j < NX; ++j) full[i * NX + j] = u.P[pidx<NX>(i, j)];
+          if (PM) store_row_f64<NX>(PM, row - 1, u.m);
+          if (PP) store_row_f64<NX * NX>(PP, row - 1, full);
+        }
+        T ll = sm.cll[us];
+        int flag = sm.cflag[us];
+        if (k < K) {
+          T y[NY];
+#pragma unroll
+          for (int c = 0; c < NY; ++c) y[c] = sm.py[k & 1][c][us];
+          const T tk = sm.ct1[us];  // t_k is the end of the previous gap, bit for bit
+          const T tk1 = k + 1 < K ? sm.pt[k & 1][us] : tk + dtf;
+          if (k + 1 < K) {  // prefetch y_{k+1}, t_{k+2} into the other ring slot
+#pragma unroll
+            for (int c = 0; c < NY; ++c)
+              cp_async_elem(&sm.py[(k + 1) & 1][c][us], Yg + us * ystride + (long long)(k + 1) * NY + c);
+            if (k + 2 < K) cp_async_elem(&sm.pt[(k + 1) & 1][us], Tg + us * tstride + k + 2);
+          }
+          T sprod = sm.csp[us];
+          if (NY == 1 && !LLC) {
+            T Sk;
+            ll += ekf_update<T, NX, NY>(Hs, ds, Rs, u, y, num_iter, &Sk);
+            if (!(Sk > T(0))) flag |= 4;
+            if (Sk > T(1e-8) && Sk < T(1e8)) {
+              sprod *= Sk;
+            } else {
+              ll -= T(0.5) * log(Sk);
+            }
+            if ((k & 7) == 7) {
+              ll -= T(0.5) * log(sprod);
+              sprod = T(1);
+            }
+          } else {
+            ll += ekf_update<T, NX, NY>(Hs, ds, Rs, u, y, num_iter);
+            if (LLC) LLC[row] = ll;
+          }
+          if (vec_out) {
+            T full[NX * NX];
+#pragma unroll
+            for (int i = 0; i < NX; ++i)
+#pragma unroll
+              for (int j = 0; j < NX; ++j) full[i * NX + j] = u.P[pidx<NX>(i, j)];
+            if (FM) store_row_f64<NX>(FM, row, u.m);
+            if (FP) store_row_f64<NX * NX>(FP, row, full);
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) sm.cm[i][us] = u.m[i];
+#pragma unroll
+          for (int i = 0; i < NP; ++i) sm.cP[i][us] = u.P[i];
+          sm.ct0[us] = tk;
+          sm.ct1[us] = tk1;
+          sm.cll[us] = ll;
+          sm.csp[us] = sprod;
+          sm.ck[us] = k + 1;
+          sm.cflag[us] = flag;
+        } else {
+          // k == K: the last prediction has been written above; finish the trajectory
+          ll -= T(0.5) * log(sm.csp[us]);
+          if (flag & 4) ll = T(NAN);
+          int status = flag & 3;
+          if (status == 0 && !isfinite(ll)) status = 1;
+          if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[tj] = ll;
+          if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[tj] = status;
+        }
+        again = k < K;
+      }
+      cp_async_commit();
+      const unsigned again_m = __ballot_sync(0xffffffffu, again);  // push onto the ready ring in pass order
+      if (again) sm.rq[(rq_head + rq_cnt + __popc(again_m & lt_mask)) & 63u] = (unsigned char)us;
+      rq_cnt += __popc(again_m);
+      nq_head += ntake;
+      nq_cnt -= ntake;
+      __syncwarp();
+      continue;
+    }
+    if (act_m == 0u) break;  // nothing integrating, nothing waiting: the pool is finished
+    // ---- (B) one RK substep for every lane that holds a trajectory ----
+    bool fin = false;
+    if (slot >= 0) {
+      if (tprev < t1 && nsteps < max_steps) {
+        rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
+        ++nsteps;
+        tprev = tnext;
+        const T cand = tprev + dt0;
+        tnext = cand > t1 - tol ? t1 : cand;
+      }
+      fin = !(tprev < t1) || nsteps >= max_steps;
+    }
+    const unsigned fin_m = __ballot_sync(0xffffffffu, fin);
+    if (fin_m != 0u) {
+      if (fin) {
+        if (tprev < t1) {  // diffrax max_steps exceeded: the reference result is NaN
+          sm.cflag[slot] = (sm.cflag[slot] & ~3) | 2;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+#pragma unroll
+          for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) sm.cm[i][slot] = s.m[i];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) sm.cP[i][slot] = s.P[i];
+        sm.nq[(nq_head + nq_cnt + __popc(fin_m & lt_mask)) & 63u] = (unsigned char)slot;
+        slot = -1;
+      }
+      nq_cnt += __popc(fin_m);
+      __syncwarp();
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (trace && lane == 0) {
+    unsigned smid, wid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %warpid;" : "=r"(wid));
+    unsigned long long* r = trace + 4 * gw;
+    r[0] = t_entry;
+    r[1] = globaltimer();
+    r[2] = smid;
+    r[3] = wid;
+  }
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1029,16 +1340,48 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   if (blocks == 0) return CDK_OK;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
   // CDK_EKF_MODE=regroup : CTA-wide per-step regrouping (ekf_small_v5);  lockstep : same kernel, fixed assignment;
-  //              warp    : independent warps (ekf_small_lw).
+  //              warp    : independent warps (ekf_small_lw);  pool : trajectory pool per warp (ekf_small_pool).
   static const int mode = []() {
     const char* e = getenv("CDK_EKF_MODE");
     if (e && e[0] == 'r') return 0;
     if (e && e[0] == 'l') return 1;
     if (e && e[0] == 'w') return 2;
+    if (e && e[0] == 'p') return 3;
     return CDK_EKF_DEFAULT_MODE;
   }();
   V5Maps maps;
-  if (mode == 2) {
+  if constexpr (sizeof(T) == 8) {
+    // Variant C (trajectory pool per warp): fp64, parameters shared by all trajectories, 16-byte aligned output bases
+    // (128-bit row stores).
+    const bool any_out = a.out[CDK_OUT_FM] || a.out[CDK_OUT_FP] || a.out[CDK_OUT_PM] || a.out[CDK_OUT_PP];
+    bool aligned = true;
+    for (int sl : {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP})
+      if (a.out[sl] && (reinterpret_cast<uintptr_t>(a.out[sl]) & 15)) aligned = false;
+    if (mode == 3 && !par_batched && aligned) {
+      using SP = PoolSmem<NX, NY>;
+      static const int thresh = []() {
+        const char* e = getenv("CDK_POOL_T");
+        const int v = e ? atoi(e) : 16;
+        return v < 1 ? 1 : (v > 32 ? 32 : v);
+      }();
+      int dev = 0, nsm = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+      long long pool = (a.d.N + (long long)nsm * PL_WPC - 1) / ((long long)nsm * PL_WPC);  // one wave when it fits
+      pool = pool < 32 ? 32 : (pool > PL_PP ? PL_PP : pool);
+      const long long pblocks = (a.d.N + pool * PL_WPC - 1) / (pool * PL_WPC);
+      if (pblocks > 2147483647LL) return CDK_E_SIZE;
+      const size_t smp = sizeof(SP) * PL_WPC;
+      auto kp = ekf_small_pool<Drift, NY, SOLVER>;
+      if (smp > 48 * 1024 &&
+          cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp) != cudaSuccess)
+        return check_launch("cudaFuncSetAttribute(ekf_small_pool)");
+      kp<<<(unsigned)pblocks, 32 * PL_WPC, smp, s>>>(a, (int)pool, thresh, any_out ? 1 : 0);
+      note_launch();
+      return check_launch("ekf_small_pool");
+    }
+  }
+  if (mode == 2 || mode == 3) {
     using SW = LWSmem<T, NX, NY>;
     static const int wpc_env = []() {
       const char* e = getenv("CDK_LW_WPC");

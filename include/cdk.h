@@ -177,6 +177,10 @@ void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque
  * flops = 2 * 16 * iters * blocks * 256.  Returns 0 / CDK_E_CUDA. */
 int cdk_fma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
 int cdk_fma_probe_f32(int blocks, int iters, float* sink, cdk_stream_t stream);
+/* The same FMA probe with three DISTINCT vector-register operands per FMA (seed: 256 finite doubles on the device):
+ * flops = 2 * 16 * iters * blocks * 256.  On B200 this runs at 2/3 of cdk_fma_probe_f64 (register-file read bandwidth:
+ * a three-register DFMA issues every 3 cycles per SM sub-partition, not 2) -- the attainable rate of filter arithmetic. */
+int cdk_fma3_probe_f64(int blocks, int iters, double* sink, const double* seed, cdk_stream_t stream);
 /* FP64 tensor-core probe (mma.sync m8n8k4 f64, the path the EnKF ensemble contractions use): 8 independent
  * accumulator tiles per warp; flops = 2 * 8*8*4 * 8 * iters * blocks * 8 warps. */
 int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
