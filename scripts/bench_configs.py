@@ -138,7 +138,7 @@ def c5(scale):
 
 
 if __name__ == "__main__":
-    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    args = [a for a in sys.argv[1:] if a in ("c1", "c2", "c3", "c4", "c5")]
     scale = float(sys.argv[sys.argv.index("--scale") + 1]) if "--scale" in sys.argv else 1.0
     for name in (args or ["c1", "c2", "c3", "c4", "c5"]):
         t0 = time.time()
