@@ -82,28 +82,55 @@ __device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
 
 // ---- block-cooperative dense helpers (all end WITHOUT a barrier unless noted) ---------------------------------------
 // L = chol(A + boost I) (lower; reads the lower triangle of A; A != L). Upper triangle of L zeroed. Ends with a barrier.
-// Left-looking, one thread per row of the current column (loads only inside the dot products, so they pipeline); a
-// single-warp right-looking variant with __syncwarp() instead of n CTA barriers was measured SLOWER (its trailing update
-// is a dependent load-FMA-store chain).  A non-positive pivot yields NaN (the reference's behaviour for non-PD input).
+// Left-looking and SINGLE-WARP: lane r owns rows r and r + 32 (n <= 64), columns are separated by __syncwarp() only, and
+// the rest of the CTA waits at the one barrier at the end.  The critical path of a Cholesky is the dependent chain
+// dot product -> sqrt -> divide of every column; the first version (one thread per row, two CTA barriers per column, a
+// scalar k-loop whose every iteration waited for its own shared-memory load) spent ~1,400 cycles per column on it -- 62 %
+// of the UKF's time, which factors P at every RK stage (profiles/r01_generic_ukf_n40.txt).  Here the k-loop is unrolled
+// by four with all loads of a block issued before its FMAs, both rows of a lane and the pivot share the loads of row j,
+// and every sum runs on two interleaved accumulators.  A non-positive pivot yields NaN (the reference's behaviour for
+// non-PD input).
 template <typename T>
 __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
-  FOR_T(e, n * ld) L[e] = T(0);
-  __syncthreads();
-  for (int j = 0; j < n; ++j) {
-    for (int i = j + threadIdx.x; i < n; i += blockDim.x) {
-      T sjj = A[j * ld + j] + boost;
-      for (int k = 0; k < j; ++k) sjj -= L[j * ld + k] * L[j * ld + k];
-      const T dj = sqrt(sjj);
-      if (i == j) {
-        L[j * ld + j] = dj;
-      } else {
-        T v = A[i * ld + j];
-        for (int k = 0; k < j; ++k) v -= L[i * ld + k] * L[j * ld + k];
-        L[i * ld + j] = v / dj;
-      }
-    }
-    __syncthreads();
+  FOR_T(e, n * ld) {
+    const int i = e / ld, j = e - i * ld;
+    if (j > i) L[e] = T(0);
   }
+  __syncthreads();  // A may have been produced by other threads just before the call
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const int r0 = lane, r1 = lane + 32;
+    const T* L0 = L + (r0 < n ? r0 : 0) * ld;  // rows outside the matrix alias row 0 and are discarded
+    const T* L1 = L + (r1 < n ? r1 : 0) * ld;
+    for (int j = 0; j < n; ++j) {
+      const T* Lj = L + j * ld;
+      T s0 = A[j * ld + j] + boost, s1 = T(0);
+      T a0 = (r0 > j && r0 < n) ? A[r0 * ld + j] : T(0), a1 = T(0);
+      T b0 = (r1 > j && r1 < n) ? A[r1 * ld + j] : T(0), b1 = T(0);
+      int k = 0;
+      for (; k + 3 < j; k += 4) {
+        const T p0 = Lj[k], p1 = Lj[k + 1], p2 = Lj[k + 2], p3 = Lj[k + 3];
+        const T x0 = L0[k], x1 = L0[k + 1], x2 = L0[k + 2], x3 = L0[k + 3];
+        const T y0 = L1[k], y1 = L1[k + 1], y2 = L1[k + 2], y3 = L1[k + 3];
+        s0 -= p0 * p0; s1 -= p1 * p1; s0 -= p2 * p2; s1 -= p3 * p3;
+        a0 -= x0 * p0; a1 -= x1 * p1; a0 -= x2 * p2; a1 -= x3 * p3;
+        b0 -= y0 * p0; b1 -= y1 * p1; b0 -= y2 * p2; b1 -= y3 * p3;
+      }
+      for (; k < j; ++k) {
+        const T p0 = Lj[k];
+        s0 -= p0 * p0;
+        a0 -= L0[k] * p0;
+        b0 -= L1[k] * p0;
+      }
+      const T dj = sqrt(s0 + s1);
+      if (r0 == j) L[j * ld + j] = dj;
+      if (r1 == j) L[j * ld + j] = dj;
+      if (r0 > j && r0 < n) L[r0 * ld + j] = (a0 + a1) / dj;
+      if (r1 > j && r1 < n) L[r1 * ld + j] = (b0 + b1) / dj;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
 }
 
 // Solve (L L^T) X = B in place, B is [n x c] with leading dimension ldb; one thread per column. Ends with a barrier.
