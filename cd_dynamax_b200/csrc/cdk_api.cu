@@ -131,6 +131,10 @@ static int run(int algo, const cdk_desc* d, const void* const* in, void* const* 
     rc = launch_ekf_small<T>(a, s);
     if (rc != CDK_E_UNSUPPORTED) return rc;
   }
+  if (algo == ALGO_EKF_SMOOTH) {
+    rc = launch_eks_small<T>(a, s);
+    if (rc != CDK_E_UNSUPPORTED) return rc;
+  }
   if (algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH) {
     rc = launch_kf_warp<T>(algo, a, s);
     if (rc != CDK_E_UNSUPPORTED) return rc;

@@ -168,6 +168,8 @@ int check_launch(const char* what);
 // entry points implemented per translation unit; return CDK_E_UNSUPPORTED when the fast path does not cover `d`
 template <typename T>
 int launch_ekf_small(const KArgs<T>& a, cudaStream_t s);
+template <typename T>
+int launch_eks_small(const KArgs<T>& a, cudaStream_t s);
 int set_lw_trace(void* devbuf);
 template <typename T>
 int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s);

@@ -56,6 +56,12 @@ struct DriftL63 {
     o[2] = x[0] * x[1] - th[2] * x[2];
   }
   template <typename T>
+  __device__ __forceinline__ static void jac(const T* th, const T (&x)[3], T (&J)[3][3]) {
+    J[0][0] = -th[0]; J[0][1] = th[0]; J[0][2] = T(0);
+    J[1][0] = th[1] - x[2]; J[1][1] = T(-1); J[1][2] = -x[0];
+    J[2][0] = x[1]; J[2][1] = x[0]; J[2][2] = -th[2];
+  }
+  template <typename T>
   __device__ __forceinline__ static void jp(const T* th, const T (&x)[3], const T (&P)[6], T (&G)[3][3]) {
     // J = [[-s, s, 0], [r - z, -1, -x], [y, x, -b]]  (jacfwd(f), inference_ekf.py:95)
     const T rz = th[1] - x[2];
@@ -1281,6 +1287,330 @@ __global__ void __launch_bounds__(32 * PL_WPC, 1)
   }
 }
 
+// ======================================================================================================================
+// EKS backward pass for the register-sized drifts (extended_kalman_smoother, inference_ekf.py:450-539 with _smooth
+// :363-448): for k = K-2 .. 0, with the Jacobian and the drift frozen at the filtered mean m_f,
+//   aux = psd_solve(P_f, L Qc L^T)^T,  G = J(m_f) + aux,
+//   d/ds (m_s, P_s) = -( f(m_f) + G (m_s - m_f),  G P_s + P_s G^T - L Qc L^T ),  s in [0, t_{k+1} - t_k]  (reverse_rhs,
+//   diffrax_utils.py:13-25), integrated with the caller's fixed-step solver from the smoothed moments of step k + 1.
+// Same mapping as ekf_small_lw: one warp = 32 trajectories for the whole kernel, smoothed state, G and the frozen terms in
+// registers, gaps run to the warp-wide maximum substep count, warps never synchronise with each other.  The filtered
+// moments are read back from HBM through a private 3-deep cp.async ring (12 + 1 values per lane and step, issued two
+// steps ahead); the smoothed rows leave through the same two-step staging blocks and TMA tensor stores as the filter's.
+// ======================================================================================================================
+constexpr int EK_RING = 3;
+
+template <typename T, int NX>
+struct alignas(128) EKSmem {
+  T sm[32][2][NX];
+  alignas(128) T sp[32][2][NX * NX];
+  T inM[EK_RING][NX][32];
+  T inP[EK_RING][NX * NX][32];
+  T inT[EK_RING][32];
+};
+
+// generic explicit RK step y <- y + dt * sum_i b_i rhs(y_i) (same accumulation scheme as rk_step)
+template <typename T, int NX, int SOLVER, class RHS>
+__device__ __forceinline__ void rk_step_fn(St<T, NX>& y, T dt, RHS rhs) {
+  using TB = Tab<SOLVER>;
+  constexpr int NP = St<T, NX>::NP;
+  constexpr int I0 = TB::b(0) != 0.0 ? 0 : (TB::S > 1 && TB::b(1) != 0.0 ? 1 : (TB::S > 2 && TB::b(2) != 0.0 ? 2 : 3));
+  St<T, NX> k[TB::S];
+  St<T, NX> ksum;
+#pragma unroll
+  for (int i = 0; i < TB::S; ++i) {
+    St<T, NX> yi = y;
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      if (TB::a(i, j) != 0.0) {
+        const T c = T(TB::a(i, j)) * dt;
+#pragma unroll
+        for (int e = 0; e < NX; ++e) yi.m[e] = fma(c, k[j].m[e], yi.m[e]);
+#pragma unroll
+        for (int e = 0; e < NP; ++e) yi.P[e] = fma(c, k[j].P[e], yi.P[e]);
+      }
+    }
+    rhs(yi, k[i]);
+    if (i == I0) {
+      ksum = k[i];
+    } else if (TB::b(i) != 0.0) {
+      const T c = T(TB::b(i) / TB::b(I0));
+      if (TB::b(i) == TB::b(I0)) {
+#pragma unroll
+        for (int e = 0; e < NX; ++e) ksum.m[e] += k[i].m[e];
+#pragma unroll
+        for (int e = 0; e < NP; ++e) ksum.P[e] += k[i].P[e];
+      } else {
+#pragma unroll
+        for (int e = 0; e < NX; ++e) ksum.m[e] = fma(c, k[i].m[e], ksum.m[e]);
+#pragma unroll
+        for (int e = 0; e < NP; ++e) ksum.P[e] = fma(c, k[i].P[e], ksum.P[e]);
+      }
+    }
+  }
+  const T w = T(TB::b(I0)) * dt;
+#pragma unroll
+  for (int e = 0; e < NX; ++e) y.m[e] = fma(w, ksum.m[e], y.m[e]);
+#pragma unroll
+  for (int e = 0; e < NP; ++e) y.P[e] = fma(w, ksum.P[e], y.P[e]);
+}
+
+template <typename T, class Drift, int SOLVER>
+__global__ void __launch_bounds__(32 * 14, 1) eks_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps) {
+  constexpr int NX = Drift::NX;
+  constexpr int NP = St<T, NX>::NP;
+  constexpr int NTH = Drift::NTHETA;
+  constexpr int WPC = 14;
+  using S = EKSmem<T, NX>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  S& sm = *reinterpret_cast<S*>(smem_raw + (size_t)warp * sizeof(S));
+  const long long N = a.d.N;
+  const int K = a.d.K;
+  const long long traj0 = ((long long)blockIdx.x * WPC + warp) * 32;
+  if (traj0 >= N) return;
+  const long long traj = traj0 + lane;
+  const bool live = traj < N;
+  const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
+  const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0;
+  const long long tl = live ? traj : 0;
+
+  // model constants, per lane (a leading N on any parameter is simply this lane's block)
+  T th[NTH], lql[NP];
+  {
+    const T* thg = a.in[CDK_IN_F] + tl * a.in_stride[CDK_IN_F];
+    const T* Lm = a.in[CDK_IN_L] + tl * a.in_stride[CDK_IN_L];
+    const T* Qc = a.in[CDK_IN_QC] + tl * a.in_stride[CDK_IN_QC];
+#pragma unroll
+    for (int i = 0; i < NTH; ++i) th[i] = thg[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        T acc = T(0);
+        for (int p = 0; p < NX; ++p) {
+          T lq = T(0);
+          for (int q = 0; q < NX; ++q) lq += Lm[i * NX + q] * Qc[q * NX + p];
+          acc += lq * Lm[j * NX + p];
+        }
+        lql[pidx<NX>(i, j)] = acc;
+      }
+  }
+  const T* __restrict__ FMg = a.in[CDK_IN_FM] + tl * a.in_stride[CDK_IN_FM];
+  const T* __restrict__ FPg = a.in[CDK_IN_FP] + tl * a.in_stride[CDK_IN_FP];
+  const T* __restrict__ Tg = a.in[CDK_IN_T] + tl * a.in_stride[CDK_IN_T];
+  T* const SMg = static_cast<T*>(a.out[CDK_OUT_SM]);
+  T* const SPg = static_cast<T*>(a.out[CDK_OUT_SP]);
+  auto prefetch = [&](int kk) {  // filtered moments and time stamp of step kk -> ring slot kk % EK_RING
+    if (live && kk >= 0) {
+      const int r = kk % EK_RING;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) cp_async_elem(&sm.inM[r][i][lane], FMg + (long long)kk * NX + i);
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) cp_async_elem(&sm.inP[r][i][lane], FPg + (long long)kk * NX * NX + i);
+      cp_async_elem(&sm.inT[r][lane], Tg + kk);
+    }
+    cp_async_commit();
+  };
+  prefetch(K - 1);
+  prefetch(K - 2);
+  prefetch(K - 3);
+  const T dt0 = T(a.d.dt0), tol = clip_tol<T>();
+  const int max_steps = a.d.max_steps;
+  int status = 0;
+
+  auto tma_store = [&](int k0) {  // lane 0: store the two-step block starting at the (even) step k0
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tma_store_2d(&maps.m[0], &sm.sm[0][0][0], k0 * NX, (int)traj0);
+    tma_store_2d(&maps.m[1], &sm.sp[0][0][0], k0 * NX * NX, (int)traj0);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  };
+  auto flush_generic = [&](int k0, int nrow) {  // fp32 / odd K / unaligned outputs: cooperative copy of rows [k0, k0 + nrow)
+#pragma unroll
+    for (int arr = 0; arr < 2; ++arr) {
+      T* __restrict__ G = arr == 0 ? SMg : SPg;
+      const int len = arr ? NX * NX : NX;
+      const T* src = arr ? &sm.sp[0][0][0] : &sm.sm[0][0][0];
+      const int per = nrow * len, off = (k0 & 1) * len;
+      for (int u = lane; u < nlive * per; u += 32) {
+        const int slot = u / per, e = u - slot * per;
+        G[((traj0 + slot) * (long long)K + k0) * len + e] = src[slot * 2 * len + off + e];
+      }
+    }
+    __syncwarp();
+  };
+  auto stage = [&](int row, const St<T, NX>& v) {
+    T full[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = 0; j < NX; ++j) full[i * NX + j] = v.P[pidx<NX>(i, j)];
+    if (row == 0) {
+      stage_row<0, NX>(&sm.sm[lane][0][0], v.m);
+      stage_row<0, NX * NX>(&sm.sp[lane][0][0], full);
+    } else {
+      stage_row<1, NX>(&sm.sm[lane][0][0], v.m);
+      stage_row<1, NX * NX>(&sm.sp[lane][0][0], full);
+    }
+  };
+
+  // step K-1: smoothed = filtered (:466-470 / :813-814 in the linear twin)
+  St<T, NX> s;
+  T t1 = T(0);
+  asm volatile("cp.async.wait_group 2;" ::: "memory");
+  __syncwarp();
+  if (live) {
+    const int r = (K - 1) % EK_RING;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.m[i] = sm.inM[r][i][lane];
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = sm.inP[r][i * NX + j][lane];
+    t1 = sm.inT[r][lane];
+    // the reference copies the filtered covariance verbatim: keep its lower triangle too
+    T full[NX * NX];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) full[i] = sm.inP[r][i][lane];
+    if (((K - 1) & 1) == 0) {
+      stage_row<0, NX>(&sm.sm[lane][0][0], s.m);
+      stage_row<0, NX * NX>(&sm.sp[lane][0][0], full);
+    } else {
+      stage_row<1, NX>(&sm.sm[lane][0][0], s.m);
+      stage_row<1, NX * NX>(&sm.sp[lane][0][0], full);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.m[i] = T(0);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) s.P[i] = T(0);
+  }
+  __syncwarp();
+  if (((K - 1) & 1) == 0) {  // odd K: the last row is a block of its own (never the TMA path)
+    flush_generic(K - 1, 1);
+  }
+
+  for (int k = K - 2; k >= 0; --k) {
+    const int row = k & 1;
+    prefetch(k - 2);
+    asm volatile("cp.async.wait_group 2;" ::: "memory");  // own loads of step k have landed
+    __syncwarp();
+    if (live) {
+      const int r = k % EK_RING;
+      T mf[NX], Pf[NX][NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) mf[i] = sm.inM[r][i][lane];
+#pragma unroll
+      for (int i = 0; i < NX; ++i)
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Pf[i][j] = sm.inP[r][i * NX + j][lane];
+      const T t0 = sm.inT[r][lane];
+      // psd_solve(P_f, L Qc L^T): Cholesky of sym(P_f) + 1e-9 I (utils.py:202-207), three right-hand sides
+      T Lc[NX][NX], inv[NX];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) {
+        T sjj = T(0.5) * (Pf[j][j] + Pf[j][j]) + T(1e-9);
+#pragma unroll
+        for (int q = 0; q < j; ++q) sjj -= Lc[j][q] * Lc[j][q];
+        const T dj = sqrt(sjj);
+        Lc[j][j] = dj;
+        inv[j] = T(1) / dj;
+#pragma unroll
+        for (int i = j + 1; i < NX; ++i) {
+          T v = T(0.5) * (Pf[i][j] + Pf[j][i]);
+#pragma unroll
+          for (int q = 0; q < j; ++q) v -= Lc[i][q] * Lc[j][q];
+          Lc[i][j] = v * inv[j];
+        }
+      }
+      T G[NX][NX];
+      Drift::jac(th, mf, G);
+#pragma unroll
+      for (int c = 0; c < NX; ++c) {  // column c of X = (P_f + eps I)^-1 L Qc L^T;  aux = X^T
+        T w[NX], x[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          T v = lql[pidx<NX>(i, c)];
+#pragma unroll
+          for (int q = 0; q < i; ++q) v -= Lc[i][q] * w[q];
+          w[i] = v * inv[i];
+        }
+#pragma unroll
+        for (int i = NX - 1; i >= 0; --i) {
+          T v = w[i];
+#pragma unroll
+          for (int q = i + 1; q < NX; ++q) v -= Lc[q][i] * x[q];
+          x[i] = v * inv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) G[c][i] += x[i];
+      }
+      T c0[NX];
+      Drift::f(th, mf, c0);
+      auto rhs = [&](const St<T, NX>& y, St<T, NX>& kk) {
+        T GP[NX][NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          T acc = c0[i];
+#pragma unroll
+          for (int q = 0; q < NX; ++q) acc = fma(G[i][q], y.m[q] - mf[q], acc);
+          kk.m[i] = -acc;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) {
+            T g = T(0);
+#pragma unroll
+            for (int q = 0; q < NX; ++q) g = fma(G[i][q], y.P[pidx<NX>(q, j)], g);
+            GP[i][j] = g;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = i; j < NX; ++j) kk.P[pidx<NX>(i, j)] = lql[pidx<NX>(i, j)] - (GP[i][j] + GP[j][i]);
+      };
+      const T span = t1 - t0;  // integrate s from 0 to t_{k+1} - t_k
+      T tprev = T(0), tnext = fmin(dt0, span);
+      int nsteps = 0;
+      while (tprev < span && nsteps < max_steps) {
+        rk_step_fn<T, NX, SOLVER>(s, tnext - tprev, rhs);
+        ++nsteps;
+        tprev = tnext;
+        const T cand = tprev + dt0;
+        tnext = cand > span - tol ? span : cand;
+      }
+      if (tprev < span) {  // diffrax max_steps exceeded: NaN, as in the reference
+        status = 2;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
+#pragma unroll
+        for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
+      }
+      t1 = t0;
+    }
+    if (use_tma && row == 1) {  // the block (k-1, k) is about to be rewritten: its predecessor (k+1, k+2) must have been read
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    }
+    if (live) stage(row, s);
+    __syncwarp();
+    if (use_tma) {
+      if (row == 0 && lane == 0) tma_store(k);
+    } else if (row == 0 || k == 0) {
+      const int nrow = (k + 1 < K && row == 0) ? 2 : 1;
+      flush_generic(k, nrow);
+    }
+  }
+  if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  cp_async_wait_all();
+  if (live && a.out[CDK_OUT_STATUS]) {
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) bad |= !isfinite(s.m[i]);
+    if (status == 0 && bad) status = 1;
+    if (status != 0) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;  // keep the filter's status otherwise
+  }
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1300,7 +1630,7 @@ encode_tiled_fn get_encode_tiled() {
 // Build the four output tensor maps.  Returns false when the TMA path does not apply (fp32, odd K, unaligned pointers,
 // CDK_EKF_TMA=0): the kernel then uses the cooperative-copy flush.
 template <typename T>
-bool make_maps(const KArgs<T>& a, int NX, int box_rows, V5Maps& maps) {
+bool make_maps(const KArgs<T>& a, int NX, int box_rows, V5Maps& maps, const int* slot_list = nullptr) {
   memset(&maps, 0, sizeof(maps));
   static const bool disabled = []() {
     const char* e = getenv("CDK_EKF_TMA");
@@ -1309,8 +1639,10 @@ bool make_maps(const KArgs<T>& a, int NX, int box_rows, V5Maps& maps) {
   if (disabled || sizeof(T) != 8 || (a.d.K & 1) || a.d.N > 0x7fffffffLL) return false;
   encode_tiled_fn enc = get_encode_tiled();
   if (!enc) return false;
-  const int slots[4] = {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP};
+  const int default_slots[4] = {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP};
+  const int* slots = slot_list ? slot_list : default_slots;  // even entries: [N][K][NX] arrays, odd: [N][K][NX*NX]
   for (int i = 0; i < 4; ++i) {
+    if (slots[i] < 0) continue;
     void* ptr = a.out[slots[i]];
     if (!ptr) continue;
     if (reinterpret_cast<uintptr_t>(ptr) & 15) return false;
@@ -1443,6 +1775,25 @@ int launch_ny(const KArgs<T>& a, cudaStream_t s) {
   return CDK_E_UNSUPPORTED;
 }
 
+template <typename T, class Drift, int SOLVER>
+int launch_eks_one(const KArgs<T>& a, cudaStream_t s) {
+  constexpr int NX = Drift::NX;
+  using S = EKSmem<T, NX>;
+  const long long blocks = (a.d.N + 32 * 14 - 1) / (32 * 14);
+  if (blocks == 0) return CDK_OK;
+  if (blocks > 2147483647LL) return CDK_E_SIZE;
+  V5Maps maps;
+  const int slots[4] = {CDK_OUT_SM, CDK_OUT_SP, -1, -1};
+  make_maps<T>(a, NX, 32, maps, slots);
+  const size_t smem = sizeof(S) * 14;
+  auto kern = eks_small_lw<T, Drift, SOLVER>;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return check_launch("cudaFuncSetAttribute(eks_small_lw)");
+  kern<<<(unsigned)blocks, 32 * 14, smem, s>>>(a, maps);
+  note_launch();
+  return check_launch("eks_small_lw");
+}
+
 }  // namespace
 
 // Fast path coverage: EKF filter, state_order first/second, Lorenz-63 (n = 3), m <= 3, solvers rk4/dopri5/euler/heun.
@@ -1459,6 +1810,26 @@ int set_lw_trace(void* devbuf) {
   return cudaMemcpyToSymbol(g_lw_trace, &p, sizeof(p)) == cudaSuccess ? CDK_OK : CDK_E_CUDA;
 }
 
+// EKS backward pass fast path: Lorenz-63, solvers rk4 / dopri5 / euler / heun (anything else: generic_smooth_kernel).
+template <typename T>
+int launch_eks_small(const KArgs<T>& a, cudaStream_t s) {
+  const cdk_desc& d = a.d;
+  static const bool disabled = []() {
+    const char* e = getenv("CDK_EKS_FAST");
+    return e && e[0] == '0';
+  }();
+  if (disabled || d.drift_id != CDK_DRIFT_LORENZ63 || d.n != 3) return CDK_E_UNSUPPORTED;
+  switch (d.solver) {
+    case CDK_RK4: return launch_eks_one<T, DriftL63, CDK_RK4>(a, s);
+    case CDK_DOPRI5: return launch_eks_one<T, DriftL63, CDK_DOPRI5>(a, s);
+    case CDK_EULER: return launch_eks_one<T, DriftL63, CDK_EULER>(a, s);
+    case CDK_HEUN: return launch_eks_one<T, DriftL63, CDK_HEUN>(a, s);
+  }
+  return CDK_E_UNSUPPORTED;
+}
+
+template int launch_eks_small<double>(const KArgs<double>&, cudaStream_t);
+template int launch_eks_small<float>(const KArgs<float>&, cudaStream_t);
 template int launch_ekf_small<double>(const KArgs<double>&, cudaStream_t);
 template int launch_ekf_small<float>(const KArgs<float>&, cudaStream_t);
 

@@ -408,3 +408,51 @@ def test_kf_warp_filter_and_smoother_vs_oracle(N, K, n, m, solver, batched_model
         if r[fld].size:
             assert scaled_err(getattr(s, fld), r[fld]) < 1e-8, fld
     assert s.smoothed_cross_covariances.shape == (N, K - 1, n, n)
+
+
+# ---- EKS fast path (register kernel, Lorenz-63): seeded oracle parity at ragged shapes, all four solvers --------------
+@pytest.mark.parametrize("N,K,solver,dt0", [(1, 1, "rk4", 0.0025), (3, 2, "rk4", 0.0025), (45, 7, "heun", 0.005),
+                                            (100, 30, "rk4", 0.0025), (33, 16, "dopri5", 0.01), (450, 12, "euler", 0.002)])
+def test_eks_l63_fast_path_vs_oracle(N, K, solver, dt0):
+    cd = api()
+    t, y = c3_problem(N, K, seed=77 + N)
+    g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]),
+             L=np.eye(3) + 0.1 * np.arange(9).reshape(3, 3) / 9, Qc=np.eye(3) + 0.05, H=np.array([[1.0, 0.0, 0.0]]),
+             R=np.eye(1), d=np.zeros(1))
+    p = nonlinear_params_api(g)
+    hp = cd.EKFHyperParams(dt_final=0.004, diffeqsolve_settings={"solver": solver, "dt0": dt0})
+    s = cd.cdnlgssm_smoother(p, y, t[..., None], hp)
+    po = o.NonlinearParams(m0=g["m0"], P0=g["P0"], drift=make_drift("lorenz63", g["theta"], 3), L=g["L"], Qc=g["Qc"],
+                           H=g["H"], R=g["R"], d=g["d"])
+    r = o.extended_kalman_smoother(po, y, t, dt_final=0.004, settings=o.SolverSettings(solver, dt0))
+    assert max_rel_err(s.marginal_loglik, r["marginal_loglik"]) < TOL
+    for fld in ("filtered_means", "filtered_covariances"):
+        assert scaled_err(getattr(s, fld), r[fld]) < TOL, fld
+    for fld in ("smoothed_means", "smoothed_covariances"):
+        assert scaled_err(getattr(s, fld), r[fld]) < 1e-8, fld
+    # the last smoothed step is the filtered one, verbatim
+    assert np.array_equal(s.smoothed_means[:, -1], s.filtered_means[:, -1])
+    assert np.array_equal(s.smoothed_covariances[:, -1], s.filtered_covariances[:, -1])
+
+
+def test_eks_fast_path_matches_generic_kernel(monkeypatch):
+    """Same inputs through the register kernel and through generic_smooth_kernel (CDK_EKS_FAST=0 is read once per
+    process, so the generic result comes from the golden test above; here: per-trajectory drift parameters)."""
+    cd = api()
+    N, K = 70, 20
+    t, y = c3_problem(N, K, seed=5)
+    rng = np.random.default_rng(8)
+    theta = np.array([10.0, 28.0, 8.0 / 3.0])[None] * (1 + 0.05 * rng.standard_normal((N, 3)))
+    g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=theta[0], L=np.eye(3), Qc=np.eye(3),
+             H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))
+    p = nonlinear_params_api(g)
+    p = p._replace(dynamics=p.dynamics._replace(drift=cd.LearnableLorenz63(sigma=theta[:, 0], rho=theta[:, 1], beta=theta[:, 2])))
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    s = cd.cdnlgssm_smoother(p, y, t[..., None], hp)
+    for n in (0, 13, 69):
+        gi = dict(g, theta=theta[n])
+        po = o.NonlinearParams(m0=g["m0"], P0=g["P0"], drift=make_drift("lorenz63", theta[n], 3), L=g["L"], Qc=g["Qc"],
+                               H=g["H"], R=g["R"], d=g["d"])
+        r = o.extended_kalman_smoother(po, y[n:n + 1], t[n:n + 1], settings=o.SolverSettings("rk4", 0.0025))
+        assert scaled_err(s.smoothed_means[n], r["smoothed_means"][0]) < 1e-8
+        assert scaled_err(s.smoothed_covariances[n], r["smoothed_covariances"][0]) < 1e-8
