@@ -66,6 +66,36 @@ __device__ __forceinline__ void mm(double (&d)[RB][CB][2], const double* __restr
   }
 }
 
+// D1 = A * B1 and D2 = A * B2 (all 16 x 16, row-major in shared memory, leading dimension KW_LD) in one sweep: the
+// fragments of A are loaded once per k-step and the eight DMMAs of a k-step are mutually independent, so the dependent
+// accumulation chain of every output tile is eight tensor instructions apart.
+__device__ __forceinline__ void mm2_shared_a(double (&d1)[2][2][2], double (&d2)[2][2][2], const double* __restrict__ sA,
+                                             const double* __restrict__ sB1, const double* __restrict__ sB2) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) d1[rb][cb][0] = d1[rb][cb][1] = d2[rb][cb][0] = d2[rb][cb][1] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    double av[2], b1[2], b2[2];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) av[rb] = sA[(8 * rb + gid) * KW_LD + 4 * kk + tig];
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      b1[cb] = sB1[(4 * kk + tig) * KW_LD + 8 * cb + gid];
+      b2[cb] = sB2[(4 * kk + tig) * KW_LD + 8 * cb + gid];
+    }
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        dmma(d1[rb][cb][0], d1[rb][cb][1], av[rb], b1[cb]);
+        dmma(d2[rb][cb][0], d2[rb][cb][1], av[rb], b2[cb]);
+      }
+  }
+}
+
 template <int RB, int CB>
 __device__ __forceinline__ void store_c(const double (&d)[RB][CB][2], double* s) {
   const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
@@ -160,8 +190,7 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
       store_c<2, 2>(iQ.v, sYQ);
       __syncwarp();
       F16 fq;
-      mm<false, false, 16, 2, 2>(kA.v, sF, sYA);  // dA = F A
-      mm<false, false, 16, 2, 2>(fq.v, sF, sYQ);  // F Q
+      mm2_shared_a(kA.v, fq.v, sF, sYA, sYQ);  // dA = F A and F Q
       store_c<2, 2>(fq.v, sT);
       __syncwarp();
       F16 fqt, lq;
