@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small KF (n=16) / UKF (n=40) launches for ncu: python scripts/profile_generic.py kf|ukf"""
+"""Small KF (n=16) / UKF (n=40) / EnKF (n=40, E=1024) launches for ncu: python scripts/profile_generic.py kf|ukf|enkf"""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -22,6 +22,13 @@ if which == "kf":
     hp = cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
     for _ in range(2):
         cd.cdlgssm_filter(p, y, t[..., None], hp)
+elif which == "enkf":
+    n, m, K, N, E = 40, 20, 20, 37, 1024
+    p = bc.nl_params(n, m, cd.LearnableLorenz96(forcing=torch.tensor(8.0, **bc.f64)), 0.1, 1.0, m0=8 + 0.5 * np.random.default_rng(5).standard_normal(n))
+    t = bc.times(N, K, 0.02, 5); y = 8 + 2 * torch.randn(N, K, m, **bc.f64)
+    hp = cd.EnKFHyperParams(N_particles=E, key=1234, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
+    for _ in range(2):
+        cd.cdnlgssm_filter(p, y, t[..., None], hp)
 else:
     n, m, K, N = 40, 20, 20, 296
     p = bc.nl_params(n, m, cd.LearnableLorenz96(forcing=torch.tensor(8.0, **bc.f64)), 0.1, 1.0, m0=8 + 0.5 * np.random.default_rng(4).standard_normal(n))
