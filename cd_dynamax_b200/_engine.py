@@ -96,17 +96,23 @@ def _host_tensor(x, dt: str) -> torch.Tensor:
 def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, object], want: Sequence[int],
         desc_fields: dict, theta_core_ndim: int = 1, scross_rows: Optional[int] = None,
         status: Optional[torch.Tensor] = None, host_out: bool = False,
-        dev_inputs: Optional[dict] = None) -> Dict[int, torch.Tensor]:
+        dev_inputs: Optional[dict] = None, scratch: Optional[torch.Tensor] = None) -> Dict[int, torch.Tensor]:
     """Call one C-ABI entry point. `inputs` maps slot -> array-like (None = absent); a leading N marks it batched.
     Returns slot -> tensor for every slot in `want` (+ OUT_STATUS): device tensors, or -- with `host_out`, which the
     API shims set when the caller handed in host arrays -- pinned host tensors whose copies have completed.
-    `dev_inputs`, when given, receives slot -> staged device tensor (a smoother reuses the filter's staged inputs)."""
+    `dev_inputs`, when given, receives slot -> staged device tensor (a smoother reuses the filter's staged inputs).
+    `desc_fields["flags"]` sets the CDK_FLAG_* bits (desc.reserved[2]); when the entry point then asks for device scratch
+    (cdk_scratch_bytes, sized per trajectory) it is allocated here -- or taken from `scratch`, which is how the type-1
+    smoother gets the pushforward cache its filter wrote -- and returned as out[OUT_SCRATCH]."""
     lib = L.lib()
     dev = device()
     d = L.new_desc()
     d.N, d.K, d.n, d.m = N, K, n, m
     for k, v in desc_fields.items():
-        setattr(d, k, v)
+        if k == "flags":
+            d.reserved[2] = int(v)
+        else:
+            setattr(d, k, v)
     tdt = _TORCH_DT[dt]
     esz = 8 if dt == "f64" else 4
     cur = torch.cuda.current_stream(dev)
@@ -166,9 +172,16 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
         for slot, t in out.items():
             hout[slot] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
     fn = getattr(lib, f"{entry}_{dt}")
+    # device scratch is sized per trajectory (today: the CD-KF pushforward cache), so chunks just offset into it
+    d.N = 1
+    scratch_row = int(lib.cdk_scratch_bytes(ctypes.byref(d), entry.encode())) if N > 0 else 0
+    d.N = N
+    if scratch_row:
+        if scratch is None or scratch.numel() < N * scratch_row:
+            scratch = torch.empty((N * scratch_row,), dtype=torch.uint8, device=dev)
+        keep.append(scratch)
     bounds = [(N * c) // nchunks for c in range(nchunks + 1)]
     rng_offset0 = int(d.rng_offset)
-    scratch = {}
     if nchunks > 1:
         h2d.wait_stream(cur)  # staged device buffers were allocated on `cur`
         for cs in comp:
@@ -200,13 +213,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
         for slot, t in out.items():
             if t.numel() > 0:
                 out_ptrs[slot] = t.data_ptr() + lo * (t.numel() // N) * t.element_size()
-        nscratch = lib.cdk_scratch_bytes(ctypes.byref(d), entry.encode())
-        if nscratch:
-            sc = scratch.get(ks)  # one scratch buffer per compute stream (chunks on one stream run in order)
-            if sc is None or sc.numel() < nscratch:
-                sc = scratch[ks] = torch.empty((nscratch,), dtype=torch.uint8, device=dev)
-                keep.append(sc)
-            out_ptrs[L.OUT_SCRATCH] = sc.data_ptr()
+        if scratch_row:
+            out_ptrs[L.OUT_SCRATCH] = scratch.data_ptr() + lo * scratch_row
         rc = fn(ctypes.byref(d), in_ptrs, out_ptrs, ctypes.c_void_p(ks.cuda_stream))
         L.check(rc, f"{entry}_{dt}")
         if host_out:
@@ -223,10 +231,14 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
                 t.record_stream(st)
     if host_out:
         d2h.synchronize()
+        if scratch_row:
+            hout[L.OUT_SCRATCH] = scratch
         return hout
     # staged inputs / scratch were allocated on this stream: the caching allocator keeps them valid until the kernel
     # has consumed them (stream-ordered reuse), so dropping `keep` here is safe.
     del keep
+    if scratch_row:
+        out[L.OUT_SCRATCH] = scratch
     return out
 
 

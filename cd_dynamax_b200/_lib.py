@@ -11,6 +11,7 @@ NUM_IN, NUM_OUT = 16, 11
 SOLVERS = {"euler": 0, "heun": 1, "midpoint": 2, "ralston": 3, "bosh3": 4, "rk4": 5, "dopri5": 6}
 DRIFT_LINEAR, DRIFT_LORENZ63, DRIFT_LORENZ96, DRIFT_QUADRATIC = 0, 1, 2, 3
 ORDERS = {"zeroth": 0, "first": 1, "second": 2}
+FLAG_KEEP_PUSHFORWARD = 1  # CDK_FLAG_KEEP_PUSHFORWARD (desc.reserved[2])
 ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",

@@ -113,7 +113,7 @@ def _linear_inputs(params: ParamsCDLGSSM, Y, T, U, n, m, d_u):
     return ins
 
 
-def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, want, host_out=False):
+def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, want, host_out=False, flags=0):
     hp = filter_hyperparams if filter_hyperparams is not None else KFHyperParams()  # None crashes upstream (:585)
     Y, T, U, batched = prepare_data(emissions, t_emissions, inputs)
     N, K, m = _shape(Y)
@@ -122,6 +122,11 @@ def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, w
     dt = E.pick_dtype(emissions)
     ins = _linear_inputs(params, Y, T, U, n, m, d_u)
     fields = dict(E.parse_settings(hp.diffeqsolve_settings), dt_final=float(hp.dt_final), d_u=d_u)
+    if flags and dt == "f64" and K > 1:
+        # keep (A_k, Q_k) of every gap for the type-1 smoother when the cache is affordable (a quarter of the free HBM)
+        free, _ = torch.cuda.mem_get_info()
+        if N * (K - 1) * 2 * n * n * 8 <= free // 4:
+            fields["flags"] = flags
     dev_ins = {}
     out = E.run("cdk_kf_filter", dt, N, K, n, m, ins, want, fields, theta_core_ndim=2, host_out=host_out,
                 dev_inputs=dev_ins)
@@ -154,13 +159,16 @@ def cdlgssm_smoother(params: ParamsCDLGSSM, emissions, t_emissions=None,
         raise ValueError("CD Kalman Smoother type = {} not implemented yet".format(smoother_type))  # :798-799
     kind = E.kind_of(emissions)
     want = (L.OUT_LL, L.OUT_FM, L.OUT_FP)
-    out, ins, fields, (N, K, n, m, dt, batched) = _filter_device(params, emissions, t_emissions, filter_hyperparams,
-                                                                 inputs, want)
+    out, ins, fields, (N, K, n, m, dt, batched) = _filter_device(
+        params, emissions, t_emissions, filter_hyperparams, inputs, want,
+        flags=L.FLAG_KEEP_PUSHFORWARD if smoother_type == "cd_smoother_1" else 0)
     ins = dict(ins)
     ins[L.IN_FM], ins[L.IN_FP] = out[L.OUT_FM], out[L.OUT_FP]
     fields = dict(fields, smoother_type=1 if smoother_type == "cd_smoother_1" else 2)
+    if L.OUT_SCRATCH not in out:
+        fields.pop("flags", None)  # the filter kept nothing (not the warp kernel): the smoother re-integrates
     sm = E.run("cdk_kf_smooth", dt, N, K, n, m, ins, (L.OUT_SM, L.OUT_SP, L.OUT_SCROSS), fields, theta_core_ndim=2,
-               status=out[L.OUT_STATUS])
+               status=out[L.OUT_STATUS], scratch=out.get(L.OUT_SCRATCH))
     g = lambda t: E.from_dev(_sq(t, batched), kind)
     return PosteriorGSSMSmoothed(marginal_loglik=g(out[L.OUT_LL]), filtered_means=g(out[L.OUT_FM]),
                                  filtered_covariances=g(out[L.OUT_FP]), smoothed_means=g(sm[L.OUT_SM]),

@@ -281,7 +281,13 @@ CDK_DEF(cdk_enkf_filter_f32, float, ALGO_ENKF_FILTER)
 
 size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point) {
   if (!d || !entry_point) return 0;
-  // no entry point needs device scratch today: the EnKF keeps its ensemble in (distributed) shared memory
+  // the EnKF keeps its ensemble in (distributed) shared memory; the only device scratch is the optional pushforward
+  // cache shared by the CD-KF filter and its type-1 smoother (CDK_FLAG_KEEP_PUSHFORWARD)
+  const bool kf = strstr(entry_point, "kf_filter") != nullptr && strstr(entry_point, "ekf") == nullptr &&
+                  strstr(entry_point, "ukf") == nullptr && strstr(entry_point, "enkf") == nullptr;
+  const bool ks = strstr(entry_point, "kf_smooth") != nullptr && strstr(entry_point, "ekf") == nullptr;
+  if ((kf || ks) && (d->reserved[2] & CDK_FLAG_KEEP_PUSHFORWARD) && cdk::kf_warp_eligible(*d, ks) && d->K > 1)
+    return (size_t)d->N * (size_t)(d->K - 1) * 2u * (size_t)d->n * (size_t)d->n * sizeof(double);
   return 0;
 }
 

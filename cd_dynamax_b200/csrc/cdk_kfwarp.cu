@@ -262,6 +262,19 @@ __device__ __forceinline__ void load_model_kw(const KArgs<double>& a, const long
   }
 }
 
+// read a C-layout 16x16 fragment from a global row-major n x n matrix (zero padding outside n x n)
+__device__ __forceinline__ void load_global(double (&d)[2][2][2], const double* __restrict__ G, int n) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      const int r = 8 * rb + gid, c = 8 * cb + 2 * tig;
+      d[rb][cb][0] = (r < n && c < n) ? G[r * n + c] : 0.0;
+      d[rb][cb][1] = (r < n && c + 1 < n) ? G[r * n + c + 1] : 0.0;
+    }
+}
+
 struct KwSmemCounts {
   // per-warp doubles / per-model doubles
   static constexpr int PER_WARP = 4 * KW_MAT + 3 * KW_MAT8 + 8 * 9 + 16 + 16 + 8 + 8 + 8 + 8;
@@ -347,6 +360,7 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
   double* PM = static_cast<double*>(a.out[CDK_OUT_PM]);
   double* PP = static_cast<double*>(a.out[CDK_OUT_PP]);
   double* LLC = static_cast<double*>(a.out[CDK_OUT_LLCUM]);
+  double* AQ = (d.reserved[2] & CDK_FLAG_KEEP_PUSHFORWARD) ? static_cast<double*>(a.out[CDK_OUT_SCRATCH]) : nullptr;
   const long long row0 = traj * (long long)K;
   const double dt0 = d.dt0, tol = clip_tol<double>();
   double ll = 0.0;
@@ -463,6 +477,11 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
     // ================= pushforward (A, Q) over [t0, t1] from (I, 0)  (:105-144; diffrax ConstantStepSize) =================
     F16 yA, yQ;
     if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) status = 2;
+    if (AQ && k + 1 < K) {  // CDK_FLAG_KEEP_PUSHFORWARD: the type-1 smoother will read (A_k, Q_k) back
+      double* dst = AQ + ((traj * (long long)(K - 1) + k) * 2) * n * n;
+      store_global(yA.v, dst, n);
+      store_global(yQ.v, dst + n * n, n);
+    }
     // ================= discrete predict: mu = A mu + b, P = A P A^T + Q  (:204-205) =================
     store_c<2, 2>(yA.v, sYA);
     __syncwarp();
@@ -547,6 +566,8 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
       a.out[CDK_OUT_SCROSS] ? static_cast<double*>(a.out[CDK_OUT_SCROSS]) + traj * (long long)(K - 1) * n * n : nullptr;
   const double dt0 = d.dt0, tol = clip_tol<double>();
   int status = 0;
+  const double* AQ =
+      (d.reserved[2] & CDK_FLAG_KEEP_PUSHFORWARD) ? static_cast<const double*>(a.out[CDK_OUT_SCRATCH]) : nullptr;
 
   // last step: smoothed = filtered (:813-814)
   for (int e = lane; e < n * n; e += 32) {
@@ -566,7 +587,13 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
     if (lane < n) smf[lane] = FMg[(long long)k * n + lane];
     const double t0 = Tm[k], t1 = Tm[k + 1];
     F16 yA, yQ;
-    if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) status = 2;
+    if (AQ) {  // the filter kept (A_k, Q_k) of this gap (bit-identical to re-integrating it)
+      const double* src = AQ + ((traj * (long long)(K - 1) + k) * 2) * n * n;
+      load_global(yA.v, src, n);
+      load_global(yQ.v, src + n * n, n);  // (zero padding: the padded rows of P_f are zero, so A's identity pad is moot)
+    } else if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) {
+      status = 2;
+    }
     store_c<2, 2>(yA.v, sYA);
     __syncwarp();
     {
@@ -684,16 +711,25 @@ int launch_kf_warp(int algo, const KArgs<T>& a, cudaStream_t s) {
   return CDK_E_UNSUPPORTED;
 }
 
-template <>
-int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
-  const cdk_desc& d = a.d;
+bool kf_warp_eligible(const cdk_desc& d, bool smooth) {
   static const bool disabled = []() {
     const char* e = getenv("CDK_KF_WARP");
     return e && e[0] == '0';
   }();
+  if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return false;
+  if (smooth && d.smoother_type != 1) return false;  // type 2 (backward ODE) stays on the generic kernel
+  RtTab rt;
+  if (!fill_rt_tab(d.solver, rt)) return false;
+  for (int i = 0; i < 6; ++i)
+    if (rt.nnz[i] > 1 || (rt.nnz[i] == 1 && rt.col[i][0] != i - 1)) return false;  // not a chain tableau
+  return true;
+}
+
+template <>
+int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
+  const cdk_desc& d = a.d;
   const bool smooth = algo == ALGO_KF_SMOOTH;
-  if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return CDK_E_UNSUPPORTED;
-  if (smooth && d.smoother_type != 1) return CDK_E_UNSUPPORTED;  // type 2 (backward ODE) stays on the generic kernel
+  if (!kf_warp_eligible(d, smooth)) return CDK_E_UNSUPPORTED;
   RtTab rt;
   if (!fill_rt_tab(d.solver, rt)) return CDK_E_ENUM;
   KwTab tab;

@@ -125,8 +125,14 @@ typedef struct cdk_desc {
   double alpha, beta, kappa;    /* ukf (inference_ukf.py:31-33) */
   uint64_t rng_seed;      /* enkf: Philox4x32-10 key */
   uint64_t rng_offset;    /* enkf: added to the trajectory index in the counter (sharding across GPUs) */
-  int32_t reserved[4];
+  int32_t reserved[4];    /* [0], [1]: absent-slot masks of the XLA adaptor; [2]: CDK_FLAG_* bits; [3]: 0 */
 } cdk_desc;
+
+/* reserved[2] bit 0: keep the pushforward.  cdk_kf_filter_f64 then also writes (A_k, Q_k) of every gap k < K-1 into
+ * out[CDK_OUT_SCRATCH] ([N][K-1][2][n][n], cdk_scratch_bytes() bytes) and cdk_kf_smooth_f64 (smoother_type 1) called with
+ * the same flag and buffer reads them back instead of re-integrating them (cd_linear/inference.py:753 recomputes; the
+ * values are bit-identical).  cdk_scratch_bytes() returns 0 when the request is not served by the warp kernels. */
+#define CDK_FLAG_KEEP_PUSHFORWARD 1
 
 #define CDK_MAX_N 64
 #define CDK_MAX_M 64

@@ -45,6 +45,13 @@ def load():
     return _lib
 
 
+def _has_openmp():
+    try:
+        return b"GOMP" in open(SO, "rb").read()
+    except OSError:
+        return False
+
+
 def _host_tag():
     try:
         for line in open("/proc/cpuinfo"):
@@ -93,13 +100,20 @@ def time_ekf_l63(n_traj, K, cfg, steps=2, warmup=1):
     args = dict(m0=np.zeros(3), P0=5 * np.eye(3), theta=np.array([10.0, 28.0, 8.0 / 3.0]), Lm=np.eye(3), Qc=np.eye(3),
                 H=np.array([[1.0, 0.0, 0.0]]), d=np.zeros(1), R=np.eye(1), drift_id=1, solver=cfg["solver"],
                 dt0=cfg["dt0"])
+    # all the host threads this process may use, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers,
+    # which would silently turn the multi-threaded baseline into a single-core one at N > 1 GPUs
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
     for _ in range(warmup):
-        filter_c("ekf", Y, T, **args)
+        filter_c("ekf", Y, T, threads=cores, **args)
     t0 = time.perf_counter()
     for _ in range(steps):
-        r = filter_c("ekf", Y, T, **args)
+        r = filter_c("ekf", Y, T, threads=cores, **args)
     el = time.perf_counter() - t0
-    cores = L.cdo_max_threads()
+    if L.cdo_max_threads() == 1 and cores > 1 and not _has_openmp():
+        cores = 1  # serial fallback build (no libgomp)
     return {"value": n_traj * K * steps / el, "ms_per_step": 1e3 * el / steps, "cores": cores, "kind": "port",
             "sample": f"N={n_traj} of the workload's trajectories x K={K}, {steps} passes, C + OpenMP "
                       f"({cores} threads), naive dense arithmetic as in the reference"}
