@@ -83,3 +83,24 @@ def test_settings_mapping():
         pass
     with pytest.raises(NotImplementedError):
         E.parse_settings({"stepsize_controller": PIDController()})
+
+
+def test_scratch_bytes_of_the_pushforward_cache(lib):
+    """cdk_scratch_bytes is pure host logic: the only device scratch is the optional CD-KF pushforward cache."""
+    from cd_dynamax_b200 import _lib
+    d = _lib.new_desc()
+    d.N, d.K, d.n, d.m, d.solver = 10, 50, 16, 4, _lib.SOLVERS["rk4"]
+    for entry in (b"cdk_kf_filter", b"cdk_kf_smooth", b"cdk_ekf_filter", b"cdk_ukf_filter", b"cdk_enkf_filter"):
+        assert lib.cdk_scratch_bytes(ctypes.byref(d), entry) == 0  # flag not set
+    d.reserved[2] = _lib.FLAG_KEEP_PUSHFORWARD
+    want = 10 * 49 * 2 * 16 * 16 * 8  # [N][K-1][2][n][n] doubles
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == want
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_smooth") == want
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_ekf_filter") == 0
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_ekf_smooth") == 0
+    d.solver = _lib.SOLVERS["dopri5"]  # not a chain tableau: the warp kernels (and with them the cache) do not apply
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == 0
+    d.solver, d.n = _lib.SOLVERS["rk4"], 17
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == 0
+    d.n, d.smoother_type = 16, 2  # the backward-ODE smoother never reads the cache
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_smooth") == 0
