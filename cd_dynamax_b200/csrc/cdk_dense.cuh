@@ -122,11 +122,12 @@ __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
         a0 -= L0[k] * p0;
         b0 -= L1[k] * p0;
       }
-      const T dj = sqrt(s0 + s1);
-      if (r0 == j) L[j * ld + j] = dj;
-      if (r1 == j) L[j * ld + j] = dj;
-      if (r0 > j && r0 < n) L[r0 * ld + j] = (a0 + a1) / dj;
-      if (r1 > j && r1 < n) L[r1 * ld + j] = (b0 + b1) / dj;
+      // one rsqrt instead of sqrt + divide on the critical path (<= 2 ulp apart; NaN / inf propagate the same way)
+      const T sjj = s0 + s1;
+      const T rinv = rsqrt(sjj);
+      if (r0 == j || r1 == j) L[j * ld + j] = sjj * rinv;
+      if (r0 > j && r0 < n) L[r0 * ld + j] = (a0 + a1) * rinv;
+      if (r1 > j && r1 < n) L[r1 * ld + j] = (b0 + b1) * rinv;
       __syncwarp();
     }
   }
