@@ -82,56 +82,70 @@ __device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
 
 // ---- block-cooperative dense helpers (all end WITHOUT a barrier unless noted) ---------------------------------------
 // L = chol(A + boost I) (lower; reads the lower triangle of A; A != L). Upper triangle of L zeroed. Ends with a barrier.
-// Left-looking and SINGLE-WARP: lane r owns rows r and r + 32 (n <= 64), columns are separated by __syncwarp() only, and
-// the rest of the CTA waits at the one barrier at the end.  The critical path of a Cholesky is the dependent chain
-// dot product -> sqrt -> divide of every column; the first version (one thread per row, two CTA barriers per column, a
-// scalar k-loop whose every iteration waited for its own shared-memory load) spent ~1,400 cycles per column on it -- 62 %
-// of the UKF's time, which factors P at every RK stage (profiles/r01_generic_ukf_n40.txt).  Here the k-loop is unrolled
-// by four with all loads of a block issued before its FMAs, both rows of a lane and the pivot share the loads of row j,
-// and every sum runs on two interleaved accumulators.  A non-positive pivot yields NaN (the reference's behaviour for
-// non-PD input).
+// BLOCKED right-looking, panels of 8 columns, in place in L.  The critical path of a Cholesky is the dependent chain
+// dot product -> pivot -> scale of every column; the UKF factors P at every RK stage, so this chain was 62 % of its time
+// (profiles/r01_generic_ukf_n40*.txt).  History: one thread per row with two CTA barriers per column and a scalar k-loop,
+// ~1,400 cycles per column; one warp (lane = rows r and r + 32, __syncwarp between columns, left-looking over all
+// previous columns), ~1,000; + rsqrt pivots, ~750.  Now warp 0 factors an 8-column panel with dot products over the
+// panel's own columns only (<= 7 terms), then the whole CTA subtracts panel * panel^T from the trailing matrix on the FP64
+// tensor cores (mm_dmma) -- two CTA barriers per PANEL.  The pivot is one rsqrt (<= 2 ulp from sqrt + divide; NaN for a
+// negative pivot, as the reference's non-PD behaviour).  mm_dmma is declared below.
+template <typename T, bool TRANSA, bool TRANSB, class Epi>
+__device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
+                                        int Kd, Epi epi);
+
 template <typename T>
 __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
   FOR_T(e, n * ld) {
     const int i = e / ld, j = e - i * ld;
-    if (j > i) L[e] = T(0);
-  }
-  __syncthreads();  // A may have been produced by other threads just before the call
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    const int r0 = lane, r1 = lane + 32;
-    const T* L0 = L + (r0 < n ? r0 : 0) * ld;  // rows outside the matrix alias row 0 and are discarded
-    const T* L1 = L + (r1 < n ? r1 : 0) * ld;
-    for (int j = 0; j < n; ++j) {
-      const T* Lj = L + j * ld;
-      T s0 = A[j * ld + j] + boost, s1 = T(0);
-      T a0 = (r0 > j && r0 < n) ? A[r0 * ld + j] : T(0), a1 = T(0);
-      T b0 = (r1 > j && r1 < n) ? A[r1 * ld + j] : T(0), b1 = T(0);
-      int k = 0;
-      for (; k + 3 < j; k += 4) {
-        const T p0 = Lj[k], p1 = Lj[k + 1], p2 = Lj[k + 2], p3 = Lj[k + 3];
-        const T x0 = L0[k], x1 = L0[k + 1], x2 = L0[k + 2], x3 = L0[k + 3];
-        const T y0 = L1[k], y1 = L1[k + 1], y2 = L1[k + 2], y3 = L1[k + 3];
-        s0 -= p0 * p0; s1 -= p1 * p1; s0 -= p2 * p2; s1 -= p3 * p3;
-        a0 -= x0 * p0; a1 -= x1 * p1; a0 -= x2 * p2; a1 -= x3 * p3;
-        b0 -= y0 * p0; b1 -= y1 * p1; b0 -= y2 * p2; b1 -= y3 * p3;
-      }
-      for (; k < j; ++k) {
-        const T p0 = Lj[k];
-        s0 -= p0 * p0;
-        a0 -= L0[k] * p0;
-        b0 -= L1[k] * p0;
-      }
-      // one rsqrt instead of sqrt + divide on the critical path (<= 2 ulp apart; NaN / inf propagate the same way)
-      const T sjj = s0 + s1;
-      const T rinv = rsqrt(sjj);
-      if (r0 == j || r1 == j) L[j * ld + j] = sjj * rinv;
-      if (r0 > j && r0 < n) L[r0 * ld + j] = (a0 + a1) * rinv;
-      if (r1 > j && r1 < n) L[r1 * ld + j] = (b0 + b1) * rinv;
-      __syncwarp();
-    }
+    L[e] = j < i ? A[e] : (j == i ? A[e] + boost : T(0));  // working copy of the lower triangle
   }
   __syncthreads();
+  for (int j0 = 0; j0 < n; j0 += 8) {
+    const int bs = n - j0 < 8 ? n - j0 : 8;
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      const int r0 = j0 + lane, r1 = r0 + 32;
+      T* L0 = L + (r0 < n ? r0 : j0) * ld + j0;  // rows outside the matrix alias the panel's first row and are discarded
+      T* L1 = L + (r1 < n ? r1 : j0) * ld + j0;
+      for (int jj = 0; jj < bs; ++jj) {
+        const T* Lj = L + (j0 + jj) * ld + j0;
+        T s = Lj[jj], a = L0[jj], b = L1[jj];
+        T s1 = T(0), a1 = T(0), b1 = T(0);
+        int q = 0;
+        for (; q + 1 < jj; q += 2) {
+          const T p0 = Lj[q], p1 = Lj[q + 1];
+          const T x0 = L0[q], x1 = L0[q + 1], y0 = L1[q], y1 = L1[q + 1];
+          s -= p0 * p0; s1 -= p1 * p1;
+          a -= x0 * p0; a1 -= x1 * p1;
+          b -= y0 * p0; b1 -= y1 * p1;
+        }
+        if (q < jj) {
+          const T p0 = Lj[q];
+          s -= p0 * p0;
+          a -= L0[q] * p0;
+          b -= L1[q] * p0;
+        }
+        const T sjj = s + s1;
+        const T rinv = rsqrt(sjj);
+        __syncwarp();  // every lane has read column jj of the working copy before it is overwritten
+        if (lane == jj) L[(j0 + jj) * ld + j0 + jj] = sjj * rinv;
+        if (r0 > j0 + jj && r0 < n) L0[jj] = (a + a1) * rinv;
+        if (r1 > j0 + jj && r1 < n) L1[jj] = (b + b1) * rinv;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    const int M = n - j0 - bs;
+    if (M > 0) {  // trailing update: W[j0+bs.., j0+bs..] -= panel * panel^T (lower triangle only)
+      const T* Pn = L + (j0 + bs) * ld + j0;
+      T* W = L + (j0 + bs) * ld + (j0 + bs);
+      mm_dmma<T, false, true>(Pn, ld, Pn, ld, M, M, bs, [&](int i, int c, double v) {
+        if (c <= i) W[i * ld + c] -= (T)v;
+      });
+      __syncthreads();
+    }
+  }
 }
 
 // Solve (L L^T) X = B in place, B is [n x c] with leading dimension ldb; one thread per column. Ends with a barrier.
