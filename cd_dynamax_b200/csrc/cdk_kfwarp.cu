@@ -27,6 +27,8 @@ namespace {
 constexpr int KW_LD = 20;   // leading dimension (doubles) of every shared-memory matrix
 constexpr int KW_WPC = 4;   // warps (trajectories) per CTA
 constexpr int KW_MAT = 16 * KW_LD, KW_MAT8 = 8 * KW_LD;
+constexpr int KW_MODEL = 3 * KW_MAT + 2 * KW_MAT8 + 16 + 8;  // F, LQL, H, R, b, d, Rk (the RK map of one full step)
+constexpr int KW_RK_OFF = 2 * KW_MAT + 2 * KW_MAT8 + 16 + 8;  // offset of Rk inside the model block
 
 struct KwTab {
   int S;
@@ -150,7 +152,8 @@ __device__ __forceinline__ void store_global(const double (&d)[2][2][2], double*
 // buffers.  Returns true when max_steps was exceeded (results are NaN then, as in the reference).
 __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, const double tol, const int max_steps,
                                             const double t0, const double t1, const double* sF, const double* sLQL,
-                                            double* sYA, double* sYQ, double* sT, F16& yA, F16& yQ) {
+                                            const double* sRk, double* sYA, double* sYQ, double* sT, F16& yA, F16& yQ,
+                                            const bool direct_t = false) {
   const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   bool hit = false;
 #pragma unroll
@@ -164,6 +167,7 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
       }
   double tprev = t0;
   double tnext = fmin(t0 + dt0, t1);
+  bool full = t0 + dt0 < t1;  // this substep has the nominal length dt0 (not clipped to the end of the gap)
   int nsteps = 0;
   while (tprev < t1) {
     if (nsteps >= max_steps) {
@@ -173,7 +177,18 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
       break;
     }
     const double dt = tnext - tprev;
+    // dA = F A is linear with constant coefficients, so one explicit RK step of length dt0 maps A to Rk A with the SAME
+    // matrix Rk for every full-length substep of every gap (Rk = the RK step applied to the identity, computed once per
+    // model by rk_map): one product instead of one per stage.  Clipped substeps (and Q, whose step map is not a
+    // similarity transform of the truncated polynomial) take the stages.  Same result as stepping A up to rounding.
+    const bool fastA = full && sRk != nullptr;
     F16 accA = yA, accQ = yQ, kA, kQ;
+    if (fastA) {
+      store_c<2, 2>(yA.v, sYA);
+      __syncwarp();
+      mm<false, false, 16, 2, 2>(accA.v, sRk, sYA);
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int st = 0; st < tab.S; ++st) {
       // stage input y + a dt k_{st-1} -> shared memory (B operand)
@@ -182,19 +197,27 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
         const double c = tab.a[st] * dt;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          (&iA.v[0][0][0])[i] = fma(c, (&kA.v[0][0][0])[i], (&iA.v[0][0][0])[i]);
+          if (!fastA) (&iA.v[0][0][0])[i] = fma(c, (&kA.v[0][0][0])[i], (&iA.v[0][0][0])[i]);
           (&iQ.v[0][0][0])[i] = fma(c, (&kQ.v[0][0][0])[i], (&iQ.v[0][0][0])[i]);
         }
       }
-      store_c<2, 2>(iA.v, sYA);
+      if (!fastA) store_c<2, 2>(iA.v, sYA);
       store_c<2, 2>(iQ.v, sYQ);
       __syncwarp();
       F16 fq;
-      mm2_shared_a(kA.v, fq.v, sF, sYA, sYQ);  // dA = F A and F Q
-      store_c<2, 2>(fq.v, sT);
-      __syncwarp();
+      if (fastA) {
+        mm<false, false, 16, 2, 2>(fq.v, sF, sYQ);  // F Q
+      } else {
+        mm2_shared_a(kA.v, fq.v, sF, sYA, sYQ);  // dA = F A and F Q
+      }
       F16 fqt, lq;
-      load_ct(fqt.v, sT);  // Q F^T = (F Q)^T for the symmetric Q
+      if (direct_t) {
+        mm<false, true, 16, 2, 2>(fqt.v, sYQ, sF);  // Q F^T on the tensor cores: no shared-memory round trip
+      } else {
+        store_c<2, 2>(fq.v, sT);
+        __syncwarp();
+        load_ct(fqt.v, sT);  // Q F^T = (F Q)^T for the symmetric Q
+      }
       load_c<2, 2>(lq.v, sLQL);
 #pragma unroll
       for (int i = 0; i < 8; ++i) (&kQ.v[0][0][0])[i] = ((&fq.v[0][0][0])[i] + (&fqt.v[0][0][0])[i]) + (&lq.v[0][0][0])[i];
@@ -202,7 +225,7 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
       if (w != 0.0) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          (&accA.v[0][0][0])[i] = fma(w, (&kA.v[0][0][0])[i], (&accA.v[0][0][0])[i]);
+          if (!fastA) (&accA.v[0][0][0])[i] = fma(w, (&kA.v[0][0][0])[i], (&accA.v[0][0][0])[i]);
           (&accQ.v[0][0][0])[i] = fma(w, (&kQ.v[0][0][0])[i], (&accQ.v[0][0][0])[i]);
         }
       }
@@ -213,9 +236,41 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
     ++nsteps;
     tprev = tnext;
     const double cand = tprev + dt0;
-    tnext = cand > t1 - tol ? t1 : cand;
+    full = !(cand > t1 - tol);
+    tnext = full ? cand : t1;
   }
   return hit;
+}
+
+// Rk = one explicit RK step of length dt0 of dA = F A applied to the identity (chain tableau), into sRk.
+__device__ __forceinline__ void rk_map(const KwTab& tab, const double dt0, const double* sF, double* sRk, double* sYA) {
+  const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
+  F16 eye, acc, kA;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) eye.v[rb][cb][r] = (8 * rb + gid == 8 * cb + 2 * tig + r) ? 1.0 : 0.0;
+  acc = eye;
+#pragma unroll 1
+  for (int st = 0; st < tab.S; ++st) {
+    F16 iA = eye;
+    if (st > 0) {
+      const double c = tab.a[st] * dt0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) (&iA.v[0][0][0])[i] = fma(c, (&kA.v[0][0][0])[i], (&iA.v[0][0][0])[i]);
+    }
+    store_c<2, 2>(iA.v, sYA);
+    __syncwarp();
+    mm<false, false, 16, 2, 2>(kA.v, sF, sYA);
+    const double w = tab.b[st] * dt0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) (&acc.v[0][0][0])[i] = fma(w, (&kA.v[0][0][0])[i], (&acc.v[0][0][0])[i]);
+    __syncwarp();
+  }
+  store_c<2, 2>(acc.v, sRk);
+  __syncwarp();
 }
 
 // Model constants (padded with zeros) into the CTA's or the warp's model block; L Qc L^T hoisted
@@ -231,7 +286,7 @@ __device__ __forceinline__ void load_model_kw(const KArgs<double>& a, const long
   double* sb = sR + KW_MAT8;
   double* sd = sb + 16;
   auto src = [&](int slot) { return a.in[slot] + tj * a.in_stride[slot]; };
-  for (int e = lane; e < 2 * KW_MAT + 2 * KW_MAT8 + 16 + 8; e += 32) model[e] = 0.0;
+  for (int e = lane; e < KW_MODEL; e += 32) model[e] = 0.0;
   __syncwarp();
   double* Lm = scr0;
   double* Qc = scr1;
@@ -278,10 +333,10 @@ __device__ __forceinline__ void load_global(double (&d)[2][2][2], const double* 
 struct KwSmemCounts {
   // per-warp doubles / per-model doubles
   static constexpr int PER_WARP = 4 * KW_MAT + 3 * KW_MAT8 + 8 * 9 + 16 + 16 + 8 + 8 + 8 + 8;
-  static constexpr int PER_MODEL = 2 * KW_MAT + 2 * KW_MAT8 + 16 + 8;  // F, LQL, H, R, b, d
+  static constexpr int PER_MODEL = KW_MODEL;  // F, LQL, H, R, b, d, Rk
 };
 
-__global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp) {
+__global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp, const int use_rk) {
   extern __shared__ __align__(16) double kw_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
   const cdk_desc& d = a.d;
@@ -295,6 +350,7 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
   double* sR = sH + KW_MAT8;
   double* sb = sR + KW_MAT8;
   double* sd = sb + 16;
+  const double* sRk = (use_rk & 1) ? model + KW_RK_OFF : nullptr;
   double* sP = wbase;
   double* sYA = sP + KW_MAT;
   double* sYQ = sYA + KW_MAT;
@@ -344,6 +400,8 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
       for (int q = 0; q < n; ++q) s += LQ[i * KW_LD + q] * Lm[j * KW_LD + q];
       sLQL[i * KW_LD + j] = s;
     }
+    __syncwarp();
+    rk_map(tab, d.dt0, sF, model + KW_RK_OFF, sYA);
   }
   __syncthreads();  // the only CTA-wide barrier: the shared model block is ready
   if (traj >= d.N) return;
@@ -476,7 +534,7 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
     }
     // ================= pushforward (A, Q) over [t0, t1] from (I, 0)  (:105-144; diffrax ConstantStepSize) =================
     F16 yA, yQ;
-    if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) status = 2;
+    if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sRk, sYA, sYQ, sT, yA, yQ, (use_rk & 2) != 0)) status = 2;
     if (AQ && k + 1 < K) {  // CDK_FLAG_KEEP_PUSHFORWARD: the type-1 smoother will read (A_k, Q_k) back
       double* dst = AQ + ((traj * (long long)(K - 1) + k) * 2) * n * n;
       store_global(yA.v, dst, n);
@@ -527,7 +585,7 @@ struct KsSmemCounts {
   static constexpr int PER_WARP = 6 * KW_MAT + 5 * 16;
 };
 
-__global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp) {
+__global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp, const int use_rk) {
   extern __shared__ __align__(16) double kw_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const cdk_desc& d = a.d;
@@ -538,6 +596,7 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
   double* sF = model;
   double* sLQL = sF + KW_MAT;
   double* sb = sLQL + KW_MAT + 2 * KW_MAT8;
+  const double* sRk = (use_rk & 1) ? model + KW_RK_OFF : nullptr;
   double* sPs = wbase;        // smoothed covariance of step k+1
   double* sPf = sPs + KW_MAT;  // filtered covariance of step k
   double* sYA = sPf + KW_MAT;  // stage buffer, then A
@@ -551,7 +610,11 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
   double* sinv = smn + 16;
 
   const long long tj = traj < d.N ? traj : d.N - 1;
-  if (model_per_warp || warp == 0) load_model_kw(a, tj, model, sYA, sYQ, sT);
+  if (model_per_warp || warp == 0) {
+    load_model_kw(a, tj, model, sYA, sYQ, sT);
+    __syncwarp();
+    rk_map(tab, d.dt0, sF, model + KW_RK_OFF, sYA);
+  }
   __syncthreads();  // the only CTA-wide barrier: the shared model block is ready
   if (traj >= d.N) return;
   for (int e = lane; e < KsSmemCounts::PER_WARP; e += 32) wbase[e] = 0.0;
@@ -591,7 +654,7 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
       const double* src = AQ + ((traj * (long long)(K - 1) + k) * 2) * n * n;
       load_global(yA.v, src, n);
       load_global(yQ.v, src + n * n, n);  // (zero padding: the padded rows of P_f are zero, so A's identity pad is moot)
-    } else if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sYA, sYQ, sT, yA, yQ)) {
+    } else if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sRk, sYA, sYQ, sT, yA, yQ, (use_rk & 2) != 0)) {
       status = 2;
     }
     store_c<2, 2>(yA.v, sYA);
@@ -742,13 +805,17 @@ int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
   const uint32_t model_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) | (1u << CDK_IN_R) |
                               (1u << CDK_IN_B) | (1u << CDK_IN_D);
   const int model_per_warp = (d.batched_mask & model_mask) != 0;
+  static const int use_rk = []() {  // CDK_KF_RKMAP=0: step A through the RK stages like Q (A/B testing)
+    const char* e = getenv("CDK_KF_RKMAP");
+    return e ? atoi(e) : 1;  // bit 0: RK map for A; bit 1: Q F^T as a second tensor-core product
+  }();
   if (smooth) {
     const size_t smem = sizeof(double) * ((model_per_warp ? KS_WPC : 1) * KwSmemCounts::PER_MODEL + KS_WPC * KsSmemCounts::PER_WARP);
     const long long blocks = (d.N + KS_WPC - 1) / KS_WPC;
     if (blocks > 2147483647LL) return CDK_E_SIZE;
     if (cudaFuncSetAttribute(kf_warp_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(kf_warp_smooth)");
-    kf_warp_smooth<<<(unsigned)blocks, 32 * KS_WPC, smem, s>>>(a, tab, model_per_warp);
+    kf_warp_smooth<<<(unsigned)blocks, 32 * KS_WPC, smem, s>>>(a, tab, model_per_warp, use_rk);
     note_launch();
     return check_launch("kf_warp_smooth");
   }
@@ -757,7 +824,7 @@ int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
   if (blocks > 2147483647LL) return CDK_E_SIZE;
   if (cudaFuncSetAttribute(kf_warp_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(kf_warp_filter)");
-  kf_warp_filter<<<(unsigned)blocks, 32 * KW_WPC, smem, s>>>(a, tab, model_per_warp);
+  kf_warp_filter<<<(unsigned)blocks, 32 * KW_WPC, smem, s>>>(a, tab, model_per_warp, use_rk);
   note_launch();
   return check_launch("kf_warp_filter");
 }
