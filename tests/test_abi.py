@@ -104,3 +104,31 @@ def test_scratch_bytes_of_the_pushforward_cache(lib):
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == 0
     d.n, d.smoother_type = 16, 2  # the backward-ODE smoother never reads the cache
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_smooth") == 0
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/cdk.h must compile as C (no C++ / torch / CUDA types) and every
+    declared entry point must link against libcdk.so from a C translation unit."""
+    import subprocess
+    from cd_dynamax_b200 import _lib
+    src = tmp_path / "use_cdk.c"
+    src.write_text(
+        '#include "cdk.h"\n'
+        "int main(void) {\n"
+        "  cdk_desc d; cdk_desc_init(&d);\n"
+        "  const void* in[CDK_NUM_IN] = {0}; void* out[CDK_NUM_OUT] = {0};\n"
+        "  d.N = 0; d.K = 1; d.n = 3; d.m = 1; d.drift_id = CDK_DRIFT_LORENZ63; d.n_theta = 3;\n"
+        "  /* N = 0 is a legal no-op: validates the descriptor on the host and returns without touching the GPU */\n"
+        "  int rc = cdk_ekf_filter_f64(&d, in, out, (cdk_stream_t)0);\n"
+        "  return (rc == CDK_OK && d.struct_size == (int)sizeof(cdk_desc) && cdk_version() >= 1 &&\n"
+        "          cdk_scratch_bytes(&d, \"cdk_kf_filter\") == 0) ? 0 : 1;\n"
+        "}\n")
+    exe = tmp_path / "use_cdk"
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lcdk", f"-Wl,-rpath,{libdir}", "-Wl,--allow-shlib-undefined"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stderr)
