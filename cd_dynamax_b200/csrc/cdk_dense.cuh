@@ -86,9 +86,9 @@ __device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
 // dot product -> pivot -> scale of every column; the UKF factors P at every RK stage, so this chain was 62 % of its time
 // (profiles/r01_generic_ukf_n40*.txt).  History: one thread per row with two CTA barriers per column and a scalar k-loop,
 // ~1,400 cycles per column; one warp (lane = rows r and r + 32, __syncwarp between columns, left-looking over all
-// previous columns), ~1,000; + rsqrt pivots, ~750.  Now warp 0 factors an 8-column panel with dot products over the
-// panel's own columns only (<= 7 terms), then the whole CTA subtracts panel * panel^T from the trailing matrix on the FP64
-// tensor cores (mm_dmma) -- two CTA barriers per PANEL.  The pivot is one rsqrt (<= 2 ulp from sqrt + divide; NaN for a
+// previous columns), ~1,000; + rsqrt pivots, ~750.  Now warp 0 factors an 8-column panel IN REGISTERS (dot products over
+// the panel's own <= 7 columns, pivot rows broadcast with shuffles), then the whole CTA subtracts panel * panel^T from the
+// trailing matrix on the FP64 tensor cores (mm_dmma) -- two CTA barriers per PANEL.  The pivot is one rsqrt (<= 2 ulp from sqrt + divide; NaN for a
 // negative pivot, as the reference's non-PD behaviour).  mm_dmma is declared below.
 template <typename T, bool TRANSA, bool TRANSB, class Epi>
 __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
@@ -104,35 +104,40 @@ __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
   for (int j0 = 0; j0 < n; j0 += 8) {
     const int bs = n - j0 < 8 ? n - j0 : 8;
     if (threadIdx.x < 32) {
+      // The panel lives in REGISTERS while it is factored: lane r holds the 8 panel entries of rows j0 + r and
+      // j0 + r + 32; the pivot row of column jj is lane jj's, broadcast entry by entry with shuffles -- no shared-memory
+      // round trip and no __syncwarp inside the panel.
       const int lane = threadIdx.x;
       const int r0 = j0 + lane, r1 = r0 + 32;
-      T* L0 = L + (r0 < n ? r0 : j0) * ld + j0;  // rows outside the matrix alias the panel's first row and are discarded
-      T* L1 = L + (r1 < n ? r1 : j0) * ld + j0;
-      for (int jj = 0; jj < bs; ++jj) {
-        const T* Lj = L + (j0 + jj) * ld + j0;
-        T s = Lj[jj], a = L0[jj], b = L1[jj];
-        T s1 = T(0), a1 = T(0), b1 = T(0);
-        int q = 0;
-        for (; q + 1 < jj; q += 2) {
-          const T p0 = Lj[q], p1 = Lj[q + 1];
-          const T x0 = L0[q], x1 = L0[q + 1], y0 = L1[q], y1 = L1[q + 1];
-          s -= p0 * p0; s1 -= p1 * p1;
-          a -= x0 * p0; a1 -= x1 * p1;
-          b -= y0 * p0; b1 -= y1 * p1;
+      const bool v0 = r0 < n, v1 = r1 < n;
+      T x[8], y[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        x[q] = (v0 && q < bs) ? L[r0 * ld + j0 + q] : T(0);
+        y[q] = (v1 && q < bs) ? L[r1 * ld + j0 + q] : T(0);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (jj < bs) {
+          T a = x[jj], b = y[jj];
+#pragma unroll
+          for (int q = 0; q < jj; ++q) {
+            const T pq = __shfl_sync(0xffffffffu, x[q], jj);  // L[j0 + jj][j0 + q]
+            a -= x[q] * pq;
+            b -= y[q] * pq;
+          }
+          const T sjj = __shfl_sync(0xffffffffu, a, jj);  // the pivot row's own dot product
+          const T rinv = rsqrt(sjj);
+          x[jj] = lane == jj ? sjj * rinv : (lane > jj ? a * rinv : T(0));
+          y[jj] = b * rinv;
         }
-        if (q < jj) {
-          const T p0 = Lj[q];
-          s -= p0 * p0;
-          a -= L0[q] * p0;
-          b -= L1[q] * p0;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        if (q < bs) {
+          if (v0) L[r0 * ld + j0 + q] = x[q];
+          if (v1) L[r1 * ld + j0 + q] = y[q];
         }
-        const T sjj = s + s1;
-        const T rinv = rsqrt(sjj);
-        __syncwarp();  // every lane has read column jj of the working copy before it is overwritten
-        if (lane == jj) L[(j0 + jj) * ld + j0 + jj] = sjj * rinv;
-        if (r0 > j0 + jj && r0 < n) L0[jj] = (a + a1) * rinv;
-        if (r1 > j0 + jj && r1 < n) L1[jj] = (b + b1) * rinv;
-        __syncwarp();
       }
     }
     __syncthreads();
