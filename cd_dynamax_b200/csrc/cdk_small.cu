@@ -4,22 +4,11 @@
 // _predict (:46-148, moment ODE dm = f(m), dP = F P + P F^T + L Qc L^T) and _condition_on (:153-199) for the
 // registry drifts whose whole filter state fits in registers.
 //
-// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_v5`:
-//  * One thread integrates one trajectory-gap at a time, all arithmetic in registers (FP64 FMA pipe bound).
-//  * Irregular gaps give every trajectory its own substep count q_k in {3..6}.  A warp that keeps a fixed set of 32
-//    trajectories runs every gap to the warp-wide maximum (what jax.vmap does to diffrax's while_loop: 4.5/6 = 75 %
-//    lane efficiency).  Instead the CANONICAL per-trajectory state lives in shared memory (SoA by slot) and, every
-//    observation step, the CTA re-assigns trajectories to threads with a counting sort on ceil(gap / dt0), so that the
-//    32 lanes of a warp integrate gaps with (nearly) the same number of substeps.  The sort key only depends on the
-//    time stamps, so it is computed one step ahead, off the critical path; it costs one extra barrier per step.
-//    Which thread integrates a trajectory never changes its arithmetic, so results are bit-reproducible.
-//  * Observations and time stamps stream HBM -> shared memory through a 4-deep cp.async ring (issued three steps ahead).
-//  * Warp specialisation: 7 worker warps (224 trajectory slots) + 1 I/O warp per CTA.  While the workers integrate step
-//    k, the I/O warp (a) issues the cp.async loads of step k+3, (b) computes the assignment of step k+1, and (c) flushes
-//    the outputs of step k-1 -- which sit in the same shared-memory slots that hold the canonical state (double-buffered
-//    by step parity) -- with coalesced stores, instead of 24 lane-scattered 8-byte stores per step (32 L1 wavefronts
-//    each).  The worker critical path is update + substeps + ONE barrier per step.
-//  * 256-thread CTAs, 2 per SM: 148 * 2 * 224 = 66,304 >= 65,536 trajectories in ONE wave (128 registers/thread).
+// B200 mapping (BASELINE config 3: N = 65,536, K = 1,000, n = 3, m = 1) -- kernel `ekf_small_lw` below: one warp keeps 32
+// trajectories for the whole kernel, all arithmetic in registers (FP64 FMA pipe bound), warps never synchronise with each
+// other.  `eks_small_lw` is the matching backward (smoothing) pass.  Earlier variants -- thread per trajectory with a
+// flattened substep stream, CTA-wide per-step regrouping by substep count with a helper I/O warp, a trajectory pool per
+// warp -- were measured slower and removed; DESIGN.md section 4.1 and profiles/ keep their numbers.
 #include <type_traits>
 
 #include "cdk_common.cuh"
@@ -329,40 +318,11 @@ __device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-#ifndef CDK_EKF_DEFAULT_MODE
-#define CDK_EKF_DEFAULT_MODE 2
-#endif
-constexpr int V5_W = 224;         // worker threads (7 warps) = trajectory slots per CTA
-constexpr int V5_TPB = 256;       // + 1 helper warp; 2 CTAs / SM (128 registers / thread)
-constexpr int V5_LD = V5_W + 1;   // SoA row stride of the input rings (odd: conflict-free)
-constexpr int V5_TRING = 6;       // time-stamp ring depth (steps k .. k+3 are read, k+5 is in flight)
-constexpr int V5_TAHEAD = 5;
-constexpr int V5_YRING = 4;       // emission ring depth (step k is read, k+2 is in flight)
-constexpr int V5_YAHEAD = 2;
-constexpr int V5_NB = 32;         // counting-sort buckets (substep count clamped to 1..31; 0 = dead slot)
-constexpr int V5_SPL = V5_W / 32; // slots per helper-warp lane
-
-// TMA descriptors of the four per-step output arrays viewed as 2-D tensors [N][K*len] (len = NX or NX*NX): one box is
-// {2 steps x len elements, 224 trajectories}, so ONE cp.async.bulk.tensor store per array writes a whole CTA's two steps.
+// TMA descriptors of the per-step output arrays viewed as 2-D tensors [N][K*len] (len = NX or NX*NX): one box is
+// {2 steps x len elements, 32 trajectories}, so ONE cp.async.bulk.tensor store per array writes a warp's two steps.
 struct alignas(64) V5Maps {
   CUtensorMap m[4];  // FM, FP, PM, PP
   int use_tma;
-};
-
-template <typename T, int NX, int NY>
-struct alignas(128) V5Smem {
-  // Output staging = canonical state, in the exact global row layout [slot][2 steps][len] (dense: it is a TMA box).
-  T fm[V5_W][2][NX];
-  alignas(128) T fp[V5_W][2][NX * NX];
-  alignas(128) T pm[V5_W][2][NX];
-  alignas(128) T pp[V5_W][2][NX * NX];
-  T inY[V5_YRING][NY][V5_LD];
-  T inT[V5_TRING][V5_LD];
-  T ll[V5_LD];
-  int status[V5_W];
-  int perm[2][V5_W];   // thread -> slot assignment, by step parity
-  int hist[3][V5_NB];  // counting-sort histograms, by step mod 3 (counted 2 steps ahead, scanned 1 step ahead)
-  // followed by the model constants: NPAR values (shared) or V5_W * NPAR (one block per slot when batched)
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -372,292 +332,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 
-// Fallback flush (fp32, odd K, unaligned outputs): all threads copy rows [k0, k0 + nrow) of every live slot.
-template <typename T, int NX, int NY>
-__device__ __forceinline__ void v5_flush_generic(const V5Smem<T, NX, NY>& sm, void* const* out, int k0, int nrow, int K,
-                                                 long long traj0, int nlive) {
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    T* __restrict__ G = static_cast<T*>(out[a == 0 ? CDK_OUT_FM : a == 1 ? CDK_OUT_FP : a == 2 ? CDK_OUT_PM : CDK_OUT_PP]);
-    if (!G) continue;
-    const int len = (a & 1) ? NX * NX : NX;
-    const T* src = a == 0 ? &sm.fm[0][0][0] : a == 1 ? &sm.fp[0][0][0] : a == 2 ? &sm.pm[0][0][0] : &sm.pp[0][0][0];
-    const int per = nrow * len;
-    const int total = nlive * per;
-    const int r0 = k0 & 1;
-    for (int u = threadIdx.x; u < total; u += V5_TPB) {
-      const int slot = u / per;
-      const int e = u - slot * per;
-      G[((traj0 + slot) * (long long)K + k0) * len + e] = src[slot * 2 * len + r0 * len + e];
-    }
-  }
-}
-
-template <typename T, class Drift, int NY, int SOLVER, bool REGROUP>
-__global__ void __launch_bounds__(V5_TPB, 2) ekf_small_v5(const KArgs<T> a, const __grid_constant__ V5Maps maps) {
-  constexpr int NX = Drift::NX;
-  constexpr int NP = St<T, NX>::NP;
-  constexpr int NTH = Drift::NTHETA;
-  constexpr int NPAR = NTH + NP + NY * NX + NY + NY * NY;  // theta | lql (packed) | H | d | R
-  using S = V5Smem<T, NX, NY>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  S& sm = *reinterpret_cast<S*>(smem_raw);
-  T* parbase = reinterpret_cast<T*>(smem_raw + sizeof(S));
-
-  const long long N = a.d.N;
-  const int K = a.d.K;
-  const int tid = threadIdx.x;
-  const int lane = tid & 31;
-  const bool helper = tid >= V5_W;
-  const long long traj0 = (long long)blockIdx.x * V5_W;
-  const int nlive = (int)((N - traj0) < V5_W ? (N - traj0) : V5_W);
-  const bool home_live = tid < nlive;  // worker thread whose home slot holds a trajectory
-  const long long traj = traj0 + tid;
-  const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
-                            (1u << CDK_IN_D) | (1u << CDK_IN_R);
-  const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0;
-  const T* __restrict__ Ybase = a.in[CDK_IN_Y] + traj0 * a.in_stride[CDK_IN_Y];
-  const T* __restrict__ Tbase = a.in[CDK_IN_T] + traj0 * a.in_stride[CDK_IN_T];
-  const long long ystride = a.in_stride[CDK_IN_Y], tstride = a.in_stride[CDK_IN_T];
-  const T dt0 = T(a.d.dt0);
-  const T dtf = T(a.d.dt_final);
-  const T inv_dt0 = T(1) / dt0;
-
-  // ---- prologue: model constants, initial moments, first input steps ----
-  if ((par_batched && home_live) || (!par_batched && tid == 0)) {
-    T* par = par_batched ? parbase + tid * NPAR : parbase;
-    const long long tj = par_batched ? traj : 0;
-    const T* th = a.in[CDK_IN_F] + tj * a.in_stride[CDK_IN_F];
-    const T* Lm = a.in[CDK_IN_L] + tj * a.in_stride[CDK_IN_L];
-    const T* Qc = a.in[CDK_IN_QC] + tj * a.in_stride[CDK_IN_QC];
-    const T* H = a.in[CDK_IN_H] + tj * a.in_stride[CDK_IN_H];
-    const T* dv = a.in[CDK_IN_D] + tj * a.in_stride[CDK_IN_D];
-    const T* R = a.in[CDK_IN_R] + tj * a.in_stride[CDK_IN_R];
-    for (int i = 0; i < NTH; ++i) par[i] = th[i];
-    // L Qc L^T (inference_ekf.py:86-87,105; loop-invariant, hoisted)
-    for (int i = 0; i < NX; ++i)
-      for (int j = i; j < NX; ++j) {
-        T acc = T(0);
-        for (int p = 0; p < NX; ++p) {
-          T lq = T(0);
-          for (int q = 0; q < NX; ++q) lq += Lm[i * NX + q] * Qc[q * NX + p];
-          acc += lq * Lm[j * NX + p];
-        }
-        par[NTH + pidx<NX>(i, j)] = acc;
-      }
-    for (int i = 0; i < NY * NX; ++i) par[NTH + NP + i] = H[i];
-    for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
-    for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
-  }
-  if (!helper) {
-    sm.status[tid] = 0;
-    sm.ll[tid] = T(0);
-    sm.perm[0][tid] = tid;
-    sm.perm[1][tid] = tid;
-  } else {
-    for (int i = lane; i < 3 * V5_NB; i += 32) (&sm.hist[0][0])[i] = 0;
-  }
-  if (home_live) {
-    const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
-    const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
-    // the prior is the prediction for t_0 (inference_ekf.py:320): it sits where step -1 (row 1) would have left it
-#pragma unroll
-    for (int i = 0; i < NX; ++i) sm.pm[tid][1][i] = m0[i];
-#pragma unroll
-    for (int i = 0; i < NX * NX; ++i) sm.pp[tid][1][i] = P0[i];
-    for (int kk = 0; kk < V5_TAHEAD && kk < K; ++kk) {
-      if (kk < V5_YAHEAD) {
-#pragma unroll
-        for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk][c][tid], Ybase + tid * ystride + (long long)kk * NY + c);
-      }
-      cp_async_elem(&sm.inT[kk][tid], Tbase + tid * tstride + kk);
-    }
-    cp_async_commit();
-    cp_async_wait_all();
-  }
-  __syncthreads();
-
-  // ---- per-step regrouping (worker threads): counting sort of the home slots by the substep count of the gap after
-  //      observation kk.  count(kk) runs during step kk-2, scatter(kk) during step kk-1 -> perm[kk & 1] for step kk.
-  int my_bucket = 0, my_rank = 0;
-  auto sort_count = [&](int kk) {
-    int b = 0;
-    if (home_live) {
-      const T t0 = sm.inT[kk % V5_TRING][tid];
-      const T t1 = kk + 1 < K ? sm.inT[(kk + 1) % V5_TRING][tid] : t0 + dtf;
-      const T q = ceil((t1 - t0) * inv_dt0);
-      b = q > T(1) ? (q < T(V5_NB - 1) ? (int)q : V5_NB - 1) : 1;
-    }
-    const unsigned grp = __match_any_sync(0xffffffffu, b);
-    const int leader = __ffs(grp) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&sm.hist[kk % 3][b], __popc(grp));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    my_bucket = b;
-    my_rank = base + __popc(grp & ((1u << lane) - 1u));
-  };
-  auto sort_scatter = [&](int kk) {
-    const int cnt = sm.hist[kk % 3][lane];
-    int incl = cnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const int off = __shfl_sync(0xffffffffu, incl - cnt, my_bucket);
-    sm.perm[kk & 1][off + my_rank] = tid;
-  };
-  if (REGROUP) {
-    if (!helper) sort_count(0);
-    __syncthreads();
-    if (!helper) {
-      sort_scatter(0);
-      if (K > 1) sort_count(1);
-    }
-    __syncthreads();
-  }
-
-  const T tol = clip_tol<T>();
-  const int max_steps = a.d.max_steps;
-  const int num_iter = a.d.num_iter;
-  T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
-
-  for (int k = 0; k < K; ++k) {
-    const int row = k & 1;
-    if (!helper) {
-      if (REGROUP && k + 1 < K) sort_scatter(k + 1);
-      // ---- worker: update at t_k, then integrate the gap t_k -> t_{k+1}, for the slot assigned to this thread ----
-      // Sorted chunk c (32 consecutive ranks, c = 6 has the longest gaps) -> warp: the heavy and light chunks are paired on
-      // the warps that share an SM sub-partition (warp w issues on sub-partition w % 4), the heaviest chunk goes to the
-      // sub-partition that only hosts one worker warp (+ the helper warp), so the four FP64 pipes carry equal work.
-      const int chunk = (0x2106345 >> (4 * (tid >> 5))) & 7;  // warps 0..6 -> chunks 5,4,3,6,0,1,2
-      const int p = REGROUP ? sm.perm[k & 1][chunk * 32 + lane] : tid;
-      const bool live = p < nlive;
-      const T* par = par_batched ? parbase + (live ? p : 0) * NPAR : parbase;
-      const T* th = par;
-      const T* lql = par + NTH;
-      St<T, NX> s;
-      T tprev = T(0), t1 = T(0), ll = T(0);
-      if (live) {
-        const T* Hs = par + NTH + NP;
-        const T* ds = Hs + NY * NX;
-        const T* Rs = ds + NY;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) s.m[i] = sm.pm[p][row ^ 1][i];
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-          for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = sm.pp[p][row ^ 1][i * NX + j];
-        T y[NY];
-#pragma unroll
-        for (int c = 0; c < NY; ++c) y[c] = sm.inY[k % V5_YRING][c][p];
-        tprev = sm.inT[k % V5_TRING][p];
-        t1 = k + 1 < K ? sm.inT[(k + 1) % V5_TRING][p] : tprev + dtf;
-        ll = sm.ll[p] + ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
-      }
-      // the TMA store of the previous 2-step block must have finished READING the staging rows before row 0 is rewritten
-      if (use_tma && row == 0) asm volatile("bar.sync 1, %0;" ::"n"(V5_TPB) : "memory");
-      if (live) {
-        sm.ll[p] = ll;
-        if (LLC) LLC[(traj0 + p) * (long long)K + k] = ll;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) sm.fm[p][row][i] = s.m[i];
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-          for (int j = 0; j < NX; ++j) sm.fp[p][row][i * NX + j] = s.P[pidx<NX>(i, j)];
-        // diffrax ConstantStepSize stepping (diffrax_utils.py:150-163)
-        T tnext = fmin(tprev + dt0, t1);
-        int nsteps = 0;
-        while (tprev < t1) {
-          if (nsteps >= max_steps) {  // diffrax max_steps exceeded: poison this trajectory, abandon the gap
-            sm.status[p] = 2;
-#pragma unroll
-            for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
-#pragma unroll
-            for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
-            break;
-          }
-          rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
-          ++nsteps;
-          tprev = tnext;
-          const T cand = tprev + dt0;
-          tnext = cand > t1 - tol ? t1 : cand;
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) sm.pm[p][row][i] = s.m[i];
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-#pragma unroll
-          for (int j = 0; j < NX; ++j) sm.pp[p][row][i * NX + j] = s.P[pidx<NX>(i, j)];
-      }
-      if (REGROUP && k + 2 < K) sort_count(k + 2);
-    } else {
-      // ---- helper warp: output store of the previous block, input loads, sort housekeeping ----
-      if (use_tma && row == 0) {
-        if (k > 0 && lane == 0) {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          const int c1 = (int)traj0;
-          if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], (k - 2) * NX, c1);
-          if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], (k - 2) * NX * NX, c1);
-          if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], (k - 2) * NX, c1);
-          if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], (k - 2) * NX * NX, c1);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        }
-        __syncwarp();
-        asm volatile("bar.sync 1, %0;" ::"n"(V5_TPB) : "memory");
-      }
-      const int kt = k + V5_TAHEAD, ky = k + V5_YAHEAD;
-#pragma unroll
-      for (int r = 0; r < V5_SPL; ++r) {
-        const int slot = lane + 32 * r;
-        if (slot < nlive) {
-          if (ky < K) {
-#pragma unroll
-            for (int c = 0; c < NY; ++c)
-              cp_async_elem(&sm.inY[ky % V5_YRING][c][slot], Ybase + slot * ystride + (long long)ky * NY + c);
-          }
-          if (kt < K) cp_async_elem(&sm.inT[kt % V5_TRING][slot], Tbase + slot * tstride + kt);
-        }
-      }
-      cp_async_commit();
-      sm.hist[k % 3][lane] = 0;  // scanned during step k-1, counted again during step k+1
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // the loads issued during step k-1 have landed
-    }
-    __syncthreads();
-    if (!use_tma && (row == 1 || k == K - 1)) {
-      v5_flush_generic<T, NX, NY>(sm, a.out, k - row, row + 1, K, traj0, nlive);
-      __syncthreads();
-    }
-  }
-  if (use_tma && helper && lane == 0) {  // K is even on this path: the last block is rows K-2, K-1
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    const int c1 = (int)traj0;
-    if (a.out[CDK_OUT_FM]) tma_store_2d(&maps.m[0], &sm.fm[0][0][0], (K - 2) * NX, c1);
-    if (a.out[CDK_OUT_FP]) tma_store_2d(&maps.m[1], &sm.fp[0][0][0], (K - 2) * NX * NX, c1);
-    if (a.out[CDK_OUT_PM]) tma_store_2d(&maps.m[2], &sm.pm[0][0][0], (K - 2) * NX, c1);
-    if (a.out[CDK_OUT_PP]) tma_store_2d(&maps.m[3], &sm.pp[0][0][0], (K - 2) * NX * NX, c1);
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-  }
-  if (home_live) {
-    const T ll = sm.ll[tid];
-    int status = sm.status[tid];
-    if (status == 0 && !isfinite(ll)) status = 1;
-    if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
-    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
-  }
-}
-
 // ======================================================================================================================
-// Variant B: INDEPENDENT WARPS.  One warp = 32 trajectories kept for the whole kernel (7 such warps share a CTA only to
-// get an even 2-CTAs-per-SM placement; they never synchronise with each other); the filter state never
-// leaves registers, every gap runs to the warp-wide maximum substep count (predicated lanes, 4.5/6 = 75 % lane efficiency
-// on the benchmark grid) -- but there is no CTA-wide barrier at all, so the ~15 resident warps of an SM drift out of phase
-// and the latency-bound measurement update of one warp hides behind the FP64-bound substeps of the others.  Inputs come
-// through a private 4-deep cp.async ring; each warp stores its own 2-step output block with four TMA tensor stores.
+// INDEPENDENT WARPS.  One warp = 32 trajectories kept for the whole kernel (the 14 warps of a CTA share it only for
+// placement: they never synchronise with each other); the filter state never leaves registers, every gap runs to the
+// warp-wide maximum substep count (predicated lanes, 4.5/6 = 75 % lane efficiency on the benchmark grid), and the
+// latency-bound measurement update of one warp hides behind the FP64-bound substeps of the others.  Inputs come through a
+// private 4-deep cp.async ring; each warp stores its own 2-step output block with four TMA tensor stores.
 // ======================================================================================================================
 constexpr int LW_RING = 4;
 
@@ -701,12 +381,10 @@ __device__ __forceinline__ void stage_row(T* lane_block, const T (&v)[LEN]) {
 
 // Warps per CTA: 7 (two CTAs per SM, <= 128 registers) or 14 (ONE CTA per SM, <= 144 registers: the drift parameters and
 // L Qc L^T then live in registers instead of being re-read from shared memory every substep).  Either way 65,536
-// trajectories are one wave of 2,048 warps over 148 SMs.  CDK_LW_WPC selects; CDK_LW_SYNC=p adds a CTA-wide barrier every p
-// steps (keeps the warps of an SM sub-partition progressing together instead of two of them finishing early).
+// trajectories are one wave of 2,048 warps over 148 SMs.  CDK_LW_WPC selects.
 template <typename T, class Drift, int NY, int SOLVER, int WPC>
 __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
-    ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps, const int warp_bytes, const int sync_period,
-                 const int use_token) {
+    ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps, const int warp_bytes, const int use_token) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
@@ -731,12 +409,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   __shared__ unsigned lw_token[4][2];  // [sub-partition][next ticket, tenures completed]
   if (threadIdx.x < 8) (&lw_token[0][0])[threadIdx.x] = 0u;
   __syncthreads();
-  if (traj0 >= N) return;  // whole warp out of range (warps never wait for it: see live_threads)
+  if (traj0 >= N) return;  // whole warp out of range (nobody ever waits for it)
   unsigned hw_warp;
   asm volatile("mov.u32 %0, %warpid;" : "=r"(hw_warp));
   volatile unsigned* const tok = &lw_token[hw_warp & 3][0];
-  const long long rem_cta = N - cta0;
-  const int live_threads = 32 * (int)(rem_cta >= 32 * WPC ? WPC : (rem_cta + 31) / 32);
   const long long traj = traj0 + lane;
   const bool live = traj < N;
   const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
@@ -953,8 +629,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   for (int k = 0; k < K; k += 2) {
     step(std::integral_constant<int, 0>{}, k);
     if (k + 1 < K) step(std::integral_constant<int, 1>{}, k + 1);
-    if (sync_period > 0 && ((k >> 1) + 1) % sync_period == 0)
-      asm volatile("bar.sync 1, %0;" ::"r"(live_threads) : "memory");
   }
   if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (trace && lane == 0) {
@@ -973,317 +647,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     if (status == 0 && !isfinite(ll)) status = 1;
     if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
     if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
-  }
-}
-
-// ======================================================================================================================
-// Variant C: TRAJECTORY POOL PER WARP.  The two structural losses of variant B are (i) lock-step gaps -- every gap of a
-// warp's 32 trajectories runs to the warp-wide maximum substep count (6 on the benchmark grid against a mean of 4.5) --
-// and (ii) 2,048 warps over 592 sub-partitions: 272 of them hold four warps, the rest three, and the kernel ends with
-// the slowest.  Here a CTA is 12 warps (three per sub-partition, one CTA per SM) and a warp owns a POOL of up to 40
-// trajectories (37 on the benchmark: 148 x 12 x 37 >= 65,536) whose canonical state lives in its private shared memory.
-// The warp is a tiny scheduler: a lane holds one trajectory for the length of one gap, integrates it one RK substep per
-// loop iteration and hands it back; trajectories whose gap is complete queue up (FIFO, so nobody falls behind) and are
-// processed -- `thresh` or more at a time -- by an UPDATE PASS in which lane i takes the i-th waiting trajectory at
-// whatever observation index it has reached (measurement update, log-likelihood, output rows), after which free lanes
-// pick them up again.  Lanes never idle through somebody else's longer gap, nothing ever synchronises across warps, and
-// the per-trajectory arithmetic is exactly that of variant B (bit-identical results).
-// Outputs go straight from registers to HBM in the update pass: a lane writes the prediction row of step k-1 and the
-// filtered row of step k of ITS trajectory with 128-bit stores (rows are 24 / 72 bytes, so at most one 8-byte store per
-// row); the 126 MB L2 merges the rows of consecutive steps into full lines before they reach DRAM.
-// Observations: y_{k+1} and t_{k+2} are prefetched with cp.async into a two-deep per-trajectory ring during pass k.
-// ======================================================================================================================
-constexpr int PL_WPC = 12;  // warps per CTA
-constexpr int PL_PP = 40;   // largest pool per warp
-
-template <int NX, int NY>
-struct alignas(16) PoolSmem {
-  double cm[NX][PL_PP];                                   // canonical mean, structure-of-arrays
-  double cP[NX * (NX + 1) / 2][PL_PP];                    // canonical covariance (packed upper triangle)
-  double ct0[PL_PP], ct1[PL_PP], cll[PL_PP], csp[PL_PP];  // gap start / end, log-likelihood, running product of S
-  double py[2][NY][PL_PP], pt[2][PL_PP];                  // prefetched y_k and t_{k+1}, ring slot k & 1
-  int ck[PL_PP];                                          // next observation index
-  int cflag[PL_PP];                                       // bits 0..1 status, bit 2 "S was not positive"
-  unsigned char rq[64], nq[64];                           // FIFO rings: ready for a lane / waiting for an update pass
-};
-
-// One output row (LEN doubles at row index `row` of a [rows][LEN] array whose base is 16-byte aligned): 128-bit stores
-// wherever the address allows (row * LEN * 8 is 16-byte aligned iff row is even for odd LEN).
-template <int LEN>
-__device__ __forceinline__ void store_row_f64(double* __restrict__ base, long long row, const double (&v)[LEN]) {
-  double* p = base + row * LEN;
-  if ((LEN & 1) == 0 || (row & 1) == 0) {
-#pragma unroll
-    for (int e = 0; e + 1 < LEN; e += 2) *reinterpret_cast<double2*>(p + e) = make_double2(v[e], v[e + 1]);
-    if (LEN & 1) p[LEN - 1] = v[LEN - 1];
-  } else {
-    p[0] = v[0];
-#pragma unroll
-    for (int e = 1; e + 1 < LEN; e += 2) *reinterpret_cast<double2*>(p + e) = make_double2(v[e], v[e + 1]);
-  }
-}
-
-template <class Drift, int NY, int SOLVER>
-__global__ void __launch_bounds__(32 * PL_WPC, 1)
-    ekf_small_pool(const KArgs<double> a, const int pool, const int thresh, const int vec_out) {
-  using T = double;
-  constexpr int NX = Drift::NX;
-  constexpr int NP = St<T, NX>::NP;
-  constexpr int NTH = Drift::NTHETA;
-  using S = PoolSmem<NX, NY>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  S& sm = *reinterpret_cast<S*>(smem_raw + (size_t)warp * sizeof(S));
-  const long long N = a.d.N;
-  const int K = a.d.K;
-  const long long gw = (long long)blockIdx.x * PL_WPC + warp;
-  const long long traj0 = gw * pool;
-  if (traj0 >= N) return;
-  const int np = (int)((N - traj0) < pool ? (N - traj0) : pool);  // trajectories in this warp's pool
-  unsigned long long* const trace = g_lw_trace;
-  const unsigned long long t_entry = trace ? globaltimer() : 0ull;
-
-  // model constants: shared by all trajectories (per-trajectory parameter blocks take variant B), kept in registers
-  T th[NTH], lql[NP], Hs[NY * NX], ds[NY], Rs[NY * NY];
-  {
-    const T* thg = a.in[CDK_IN_F];
-    const T* Lm = a.in[CDK_IN_L];
-    const T* Qc = a.in[CDK_IN_QC];
-#pragma unroll
-    for (int i = 0; i < NTH; ++i) th[i] = thg[i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i)
-#pragma unroll
-      for (int j = i; j < NX; ++j) {
-        T acc = T(0);
-        for (int p = 0; p < NX; ++p) {
-          T lq = T(0);
-          for (int q = 0; q < NX; ++q) lq += Lm[i * NX + q] * Qc[q * NX + p];
-          acc += lq * Lm[j * NX + p];
-        }
-        lql[pidx<NX>(i, j)] = acc;
-      }
-#pragma unroll
-    for (int i = 0; i < NY * NX; ++i) Hs[i] = a.in[CDK_IN_H][i];
-#pragma unroll
-    for (int i = 0; i < NY; ++i) ds[i] = a.in[CDK_IN_D][i];
-#pragma unroll
-    for (int i = 0; i < NY * NY; ++i) Rs[i] = a.in[CDK_IN_R][i];
-  }
-  const T* __restrict__ Yg = a.in[CDK_IN_Y] + traj0 * a.in_stride[CDK_IN_Y];
-  const T* __restrict__ Tg = a.in[CDK_IN_T] + traj0 * a.in_stride[CDK_IN_T];
-  const long long ystride = a.in_stride[CDK_IN_Y], tstride = a.in_stride[CDK_IN_T];
-  // canonical state of every pool member = the prior; all of them queue for their first update
-  for (int u = lane; u < np; u += 32) {
-    const long long tj = traj0 + u;
-    const T* m0 = a.in[CDK_IN_M0] + tj * a.in_stride[CDK_IN_M0];
-    const T* P0 = a.in[CDK_IN_P0] + tj * a.in_stride[CDK_IN_P0];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) sm.cm[i][u] = m0[i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i)
-#pragma unroll
-      for (int j = i; j < NX; ++j) sm.cP[pidx<NX>(i, j)][u] = P0[i * NX + j];
-    sm.ct0[u] = T(0);
-    sm.ct1[u] = Tg[u * tstride];  // "end of the previous gap" of step 0 = t_0
-    sm.cll[u] = T(0);
-    sm.csp[u] = T(1);
-#pragma unroll
-    for (int c = 0; c < NY; ++c) sm.py[0][c][u] = Yg[u * ystride + c];
-    sm.pt[0][u] = K > 1 ? Tg[u * tstride + 1] : T(0);
-    sm.ck[u] = 0;
-    sm.cflag[u] = 0;
-    sm.nq[u] = (unsigned char)u;
-  }
-  __syncwarp();
-  T* const FM = static_cast<T*>(a.out[CDK_OUT_FM]);
-  T* const FP = static_cast<T*>(a.out[CDK_OUT_FP]);
-  T* const PM = static_cast<T*>(a.out[CDK_OUT_PM]);
-  T* const PP = static_cast<T*>(a.out[CDK_OUT_PP]);
-  T* const LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
-  const T dt0 = T(a.d.dt0), dtf = T(a.d.dt_final), tol = clip_tol<T>();
-  const int max_steps = a.d.max_steps, num_iter = a.d.num_iter;
-
-  // FIFO rings (indices are warp-uniform registers, entries live in shared memory)
-  unsigned nq_head = 0, nq_cnt = (unsigned)np;  // waiting for an update pass
-  unsigned rq_head = 0, rq_cnt = 0;             // updated, waiting for a lane
-  int slot = -1;                                // pool member this lane integrates, or -1
-  int nsteps = 0;
-  St<T, NX> s;
-  T tprev = T(0), tnext = T(0), t1 = T(0);
-#pragma unroll
-  for (int i = 0; i < NX; ++i) s.m[i] = T(0);
-#pragma unroll
-  for (int i = 0; i < NP; ++i) s.P[i] = T(0);
-  const unsigned lt_mask = (1u << lane) - 1u;
-
-  for (;;) {
-    // ---- (A) free lanes pick up ready trajectories, oldest first ----
-    if (rq_cnt != 0u) {
-      const unsigned free_m = __ballot_sync(0xffffffffu, slot < 0);
-      if (free_m != 0u) {
-        const unsigned nfree = __popc(free_m);
-        const unsigned ntake = nfree < rq_cnt ? nfree : rq_cnt;
-        const unsigned myrank = __popc(free_m & lt_mask);
-        if (slot < 0 && myrank < ntake) {
-          const int mine = sm.rq[(rq_head + myrank) & 63u];
-          slot = mine;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) s.m[i] = sm.cm[i][mine];
-#pragma unroll
-          for (int i = 0; i < NP; ++i) s.P[i] = sm.cP[i][mine];
-          tprev = sm.ct0[mine];
-          t1 = sm.ct1[mine];
-          tnext = fmin(tprev + dt0, t1);
-          nsteps = 0;
-        }
-        rq_head += ntake;
-        rq_cnt -= ntake;
-      }
-    }
-    const unsigned act_m = __ballot_sync(0xffffffffu, slot >= 0);
-    if (nq_cnt >= (unsigned)thresh || (act_m == 0u && nq_cnt != 0u)) {
-      // ---- (C) update pass: lane i takes the i-th waiting trajectory ----
-      const unsigned ntake = nq_cnt < 32u ? nq_cnt : 32u;
-      asm volatile("cp.async.wait_group 0;" ::: "memory");  // observation prefetches issued by earlier passes have landed
-      __syncwarp();
-      const bool has = (unsigned)lane < ntake;
-      bool again = false;  // the trajectory goes back to the ready ring (it has observations left)
-      int us = -1;
-      if (has) {
-        us = sm.nq[(nq_head + lane) & 63u];
-        const long long tj = traj0 + us;
-        const int k = sm.ck[us];
-        St<T, NX> u;
-#pragma unroll
-        for (int i = 0; i < NX; ++i) u.m[i] = sm.cm[i][us];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) u.P[i] = sm.cP[i][us];
-        const long long row = tj * (long long)K + k;
-        if (vec_out && k > 0) {  // the state before the update is the prediction made at step k - 1
-          T full[NX * NX];
-#pragma unroll
-          for (int i = 0; i < NX; ++i)
-#pragma unroll
-            for (int j = 0; j < NX; ++j) full[i * NX + j] = u.P[pidx<NX>(i, j)];
-          if (PM) store_row_f64<NX>(PM, row - 1, u.m);
-          if (PP) store_row_f64<NX * NX>(PP, row - 1, full);
-        }
-        T ll = sm.cll[us];
-        int flag = sm.cflag[us];
-        if (k < K) {
-          T y[NY];
-#pragma unroll
-          for (int c = 0; c < NY; ++c) y[c] = sm.py[k & 1][c][us];
-          const T tk = sm.ct1[us];  // t_k is the end of the previous gap, bit for bit
-          const T tk1 = k + 1 < K ? sm.pt[k & 1][us] : tk + dtf;
-          if (k + 1 < K) {  // prefetch y_{k+1}, t_{k+2} into the other ring slot
-#pragma unroll
-            for (int c = 0; c < NY; ++c)
-              cp_async_elem(&sm.py[(k + 1) & 1][c][us], Yg + us * ystride + (long long)(k + 1) * NY + c);
-            if (k + 2 < K) cp_async_elem(&sm.pt[(k + 1) & 1][us], Tg + us * tstride + k + 2);
-          }
-          T sprod = sm.csp[us];
-          if (NY == 1 && !LLC) {
-            T Sk;
-            ll += ekf_update<T, NX, NY>(Hs, ds, Rs, u, y, num_iter, &Sk);
-            if (!(Sk > T(0))) flag |= 4;
-            if (Sk > T(1e-8) && Sk < T(1e8)) {
-              sprod *= Sk;
-            } else {
-              ll -= T(0.5) * log(Sk);
-            }
-            if ((k & 7) == 7) {
-              ll -= T(0.5) * log(sprod);
-              sprod = T(1);
-            }
-          } else {
-            ll += ekf_update<T, NX, NY>(Hs, ds, Rs, u, y, num_iter);
-            if (LLC) LLC[row] = ll;
-          }
-          if (vec_out) {
-            T full[NX * NX];
-#pragma unroll
-            for (int i = 0; i < NX; ++i)
-#pragma unroll
-              for (int j = 0; j < NX; ++j) full[i * NX + j] = u.P[pidx<NX>(i, j)];
-            if (FM) store_row_f64<NX>(FM, row, u.m);
-            if (FP) store_row_f64<NX * NX>(FP, row, full);
-          }
-#pragma unroll
-          for (int i = 0; i < NX; ++i) sm.cm[i][us] = u.m[i];
-#pragma unroll
-          for (int i = 0; i < NP; ++i) sm.cP[i][us] = u.P[i];
-          sm.ct0[us] = tk;
-          sm.ct1[us] = tk1;
-          sm.cll[us] = ll;
-          sm.csp[us] = sprod;
-          sm.ck[us] = k + 1;
-          sm.cflag[us] = flag;
-        } else {
-          // k == K: the last prediction has been written above; finish the trajectory
-          ll -= T(0.5) * log(sm.csp[us]);
-          if (flag & 4) ll = T(NAN);
-          int status = flag & 3;
-          if (status == 0 && !isfinite(ll)) status = 1;
-          if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[tj] = ll;
-          if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[tj] = status;
-        }
-        again = k < K;
-      }
-      cp_async_commit();
-      const unsigned again_m = __ballot_sync(0xffffffffu, again);  // push onto the ready ring in pass order
-      if (again) sm.rq[(rq_head + rq_cnt + __popc(again_m & lt_mask)) & 63u] = (unsigned char)us;
-      rq_cnt += __popc(again_m);
-      nq_head += ntake;
-      nq_cnt -= ntake;
-      __syncwarp();
-      continue;
-    }
-    if (act_m == 0u) break;  // nothing integrating, nothing waiting: the pool is finished
-    // ---- (B) one RK substep for every lane that holds a trajectory ----
-    bool fin = false;
-    if (slot >= 0) {
-      if (tprev < t1 && nsteps < max_steps) {
-        rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
-        ++nsteps;
-        tprev = tnext;
-        const T cand = tprev + dt0;
-        tnext = cand > t1 - tol ? t1 : cand;
-      }
-      fin = !(tprev < t1) || nsteps >= max_steps;
-    }
-    const unsigned fin_m = __ballot_sync(0xffffffffu, fin);
-    if (fin_m != 0u) {
-      if (fin) {
-        if (tprev < t1) {  // diffrax max_steps exceeded: the reference result is NaN
-          sm.cflag[slot] = (sm.cflag[slot] & ~3) | 2;
-#pragma unroll
-          for (int i = 0; i < NX; ++i) s.m[i] = T(NAN);
-#pragma unroll
-          for (int i = 0; i < NP; ++i) s.P[i] = T(NAN);
-        }
-#pragma unroll
-        for (int i = 0; i < NX; ++i) sm.cm[i][slot] = s.m[i];
-#pragma unroll
-        for (int i = 0; i < NP; ++i) sm.cP[i][slot] = s.P[i];
-        sm.nq[(nq_head + nq_cnt + __popc(fin_m & lt_mask)) & 63u] = (unsigned char)slot;
-        slot = -1;
-      }
-      nq_cnt += __popc(fin_m);
-      __syncwarp();
-    }
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  if (trace && lane == 0) {
-    unsigned smid, wid;
-    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
-    asm volatile("mov.u32 %0, %warpid;" : "=r"(wid));
-    unsigned long long* r = trace + 4 * gw;
-    r[0] = t_entry;
-    r[1] = globaltimer();
-    r[2] = smid;
-    r[3] = wid;
   }
 }
 
@@ -1663,95 +1026,37 @@ template <typename T, class Drift, int NY, int SOLVER>
 int launch_one(const KArgs<T>& a, cudaStream_t s) {
   constexpr int NX = Drift::NX;
   constexpr int NPAR = Drift::NTHETA + NX * (NX + 1) / 2 + NY * NX + NY + NY * NY;
-  using S = V5Smem<T, NX, NY>;
+  using SW = LWSmem<T, NX, NY>;
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
-  const size_t smem = sizeof(S) + sizeof(T) * NPAR * (par_batched ? V5_W : 1);
-  const long long blocks = (a.d.N + V5_W - 1) / V5_W;
-  if (blocks == 0) return CDK_OK;
-  if (blocks > 2147483647LL) return CDK_E_SIZE;
-  // CDK_EKF_MODE=regroup : CTA-wide per-step regrouping (ekf_small_v5);  lockstep : same kernel, fixed assignment;
-  //              warp    : independent warps (ekf_small_lw);  pool : trajectory pool per warp (ekf_small_pool).
-  static const int mode = []() {
-    const char* e = getenv("CDK_EKF_MODE");
-    if (e && e[0] == 'r') return 0;
-    if (e && e[0] == 'l') return 1;
-    if (e && e[0] == 'w') return 2;
-    if (e && e[0] == 'p') return 3;
-    return CDK_EKF_DEFAULT_MODE;
+  if (a.d.N == 0) return CDK_OK;
+  // 14 warps in ONE CTA per SM (drift parameters in registers), or -- CDK_LW_WPC=7, and always when every lane carries
+  // its own parameter block in shared memory -- two CTAs of 7 warps
+  static const int wpc_env = []() {
+    const char* e = getenv("CDK_LW_WPC");
+    return e && atoi(e) == 7 ? 7 : 14;
   }();
+  const int warp_bytes = (int)((sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1) + 127) & ~size_t(127));
+  const int wpc = (size_t)warp_bytes * wpc_env > 227 * 1024 ? 7 : wpc_env;
+  const size_t smw = (size_t)warp_bytes * wpc;
+  const long long wblocks = (a.d.N + 32 * wpc - 1) / (32 * wpc);
+  if (wblocks > 2147483647LL) return CDK_E_SIZE;
   V5Maps maps;
-  if constexpr (sizeof(T) == 8) {
-    // Variant C (trajectory pool per warp): fp64, parameters shared by all trajectories, 16-byte aligned output bases
-    // (128-bit row stores).
-    const bool any_out = a.out[CDK_OUT_FM] || a.out[CDK_OUT_FP] || a.out[CDK_OUT_PM] || a.out[CDK_OUT_PP];
-    bool aligned = true;
-    for (int sl : {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP})
-      if (a.out[sl] && (reinterpret_cast<uintptr_t>(a.out[sl]) & 15)) aligned = false;
-    if (mode == 3 && !par_batched && aligned) {
-      using SP = PoolSmem<NX, NY>;
-      static const int thresh = []() {
-        const char* e = getenv("CDK_POOL_T");
-        const int v = e ? atoi(e) : 16;
-        return v < 1 ? 1 : (v > 32 ? 32 : v);
-      }();
-      int dev = 0, nsm = 148;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-      long long pool = (a.d.N + (long long)nsm * PL_WPC - 1) / ((long long)nsm * PL_WPC);  // one wave when it fits
-      pool = pool < 32 ? 32 : (pool > PL_PP ? PL_PP : pool);
-      const long long pblocks = (a.d.N + pool * PL_WPC - 1) / (pool * PL_WPC);
-      if (pblocks > 2147483647LL) return CDK_E_SIZE;
-      const size_t smp = sizeof(SP) * PL_WPC;
-      auto kp = ekf_small_pool<Drift, NY, SOLVER>;
-      if (smp > 48 * 1024 &&
-          cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smp) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(ekf_small_pool)");
-      kp<<<(unsigned)pblocks, 32 * PL_WPC, smp, s>>>(a, (int)pool, thresh, any_out ? 1 : 0);
-      note_launch();
-      return check_launch("ekf_small_pool");
-    }
+  make_maps<T>(a, NX, 32, maps);
+  auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7> : ekf_small_lw<T, Drift, NY, SOLVER, 14>;
+  if (smw > 48 * 1024) {
+    if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw) != cudaSuccess)
+      return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
   }
-  if (mode == 2 || mode == 3) {
-    using SW = LWSmem<T, NX, NY>;
-    static const int wpc_env = []() {
-      const char* e = getenv("CDK_LW_WPC");
-      return e && atoi(e) == 7 ? 7 : 14;
-    }();
-    static const int sync_period = []() {
-      const char* e = getenv("CDK_LW_SYNC");
-      return e ? atoi(e) : 0;
-    }();
-    const int warp_bytes = (int)((sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1) + 127) & ~size_t(127));
-    const int wpc = (size_t)warp_bytes * wpc_env > 227 * 1024 ? 7 : wpc_env;  // per-lane parameter blocks: 2 CTAs of 7 warps
-    const size_t smw = (size_t)warp_bytes * wpc;
-    const long long wblocks = (a.d.N + 32 * wpc - 1) / (32 * wpc);
-    if (wblocks > 2147483647LL) return CDK_E_SIZE;
-    make_maps<T>(a, NX, 32, maps);
-    auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7> : ekf_small_lw<T, Drift, NY, SOLVER, 14>;
-    if (smw > 48 * 1024) {
-      if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw) != cudaSuccess)
-        return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
-    }
-    static const int token_env = []() {
-      const char* e = getenv("CDK_LW_TOKEN");
-      return e ? atoi(e) : 0;
-    }();
-    const int use_token = wpc == 14 ? token_env : 0;  // with two CTAs per SM the lock would have to span CTAs
-    kw<<<(unsigned)wblocks, 32 * wpc, smw, s>>>(a, maps, warp_bytes, sync_period, use_token);
-    note_launch();
-    return check_launch("ekf_small_lw");
-  }
-  make_maps<T>(a, NX, V5_W, maps);
-  auto kern = mode == 0 ? ekf_small_v5<T, Drift, NY, SOLVER, true> : ekf_small_v5<T, Drift, NY, SOLVER, false>;
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(ekf_small_v5)");
-  }
-  kern<<<(unsigned)blocks, V5_TPB, smem, s>>>(a, maps);
+  static const int token_env = []() {  // experiment, default off (see the kernel)
+    const char* e = getenv("CDK_LW_TOKEN");
+    return e ? atoi(e) : 0;
+  }();
+  const int use_token = wpc == 14 ? token_env : 0;  // with two CTAs per SM the lock would have to span CTAs
+  kw<<<(unsigned)wblocks, 32 * wpc, smw, s>>>(a, maps, warp_bytes, use_token);
   note_launch();
-  return check_launch("ekf_small_v5");
+  return check_launch("ekf_small_lw");
 }
 
 template <typename T, class Drift, int NY>
