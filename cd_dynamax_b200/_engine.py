@@ -141,7 +141,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     d.batched_mask = mask
     nchunks = STREAM_CHUNKS if (stream_bytes >= STREAM_MIN_BYTES and N >= 2 * STREAM_CHUNKS) else 1
     if host_out and N >= 2 * STREAM_CHUNKS:
-        out_bytes = sum(int(np.prod(_out_shape(s, N, K, n, scross_rows), dtype=np.int64)) * esz for s in want)
+        out_bytes = sum(int(np.prod(_out_shape(s, N, K, n, scross_rows, int(desc_fields.get("n_theta", 0))),
+                                    dtype=np.int64)) * esz for s in want)
         if out_bytes >= STREAM_MIN_BYTES:
             nchunks = STREAM_CHUNKS
     h2d, d2h, comp = _streams(dev) if (nchunks > 1 or host_out) else (None, None, None)
@@ -163,7 +164,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     # ---- outputs ----
     out = {}
     for slot in want:
-        out[slot] = torch.empty(_out_shape(slot, N, K, n, scross_rows), dtype=tdt, device=dev)
+        out[slot] = torch.empty(_out_shape(slot, N, K, n, scross_rows, int(desc_fields.get("n_theta", 0))), dtype=tdt,
+                                device=dev)
     if status is None:
         status = torch.zeros((N,), dtype=torch.int32, device=dev)
     out[L.OUT_STATUS] = status
@@ -242,8 +244,9 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     return out
 
 
-def _out_shape(slot, N, K, n, scross_rows=None):
+def _out_shape(slot, N, K, n, scross_rows=None, n_theta=0):
     return {
+        L.OUT_GRAD: (N, n_theta),
         L.OUT_LL: (N,), L.OUT_FM: (N, K, n), L.OUT_FP: (N, K, n, n), L.OUT_PM: (N, K, n), L.OUT_PP: (N, K, n, n),
         L.OUT_LLCUM: (N, K), L.OUT_SM: (N, K, n), L.OUT_SP: (N, K, n, n),
         L.OUT_SCROSS: (N, max(K - 1, 0) if scross_rows is None else scross_rows, n, n), L.OUT_STATUS: (N,),

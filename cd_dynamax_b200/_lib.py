@@ -5,15 +5,17 @@ import os
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "lib", "libcdk.so")
 
-NUM_IN, NUM_OUT = 16, 11
+NUM_IN, NUM_OUT = 16, 12
 (IN_Y, IN_T, IN_U, IN_M0, IN_P0, IN_F, IN_B, IN_BU, IN_L, IN_QC, IN_H, IN_D, IN_DU, IN_R, IN_FM, IN_FP) = range(16)
-(OUT_LL, OUT_FM, OUT_FP, OUT_PM, OUT_PP, OUT_LLCUM, OUT_SM, OUT_SP, OUT_SCROSS, OUT_STATUS, OUT_SCRATCH) = range(11)
+(OUT_LL, OUT_FM, OUT_FP, OUT_PM, OUT_PP, OUT_LLCUM, OUT_SM, OUT_SP, OUT_SCROSS, OUT_STATUS, OUT_SCRATCH,
+ OUT_GRAD) = range(12)
 SOLVERS = {"euler": 0, "heun": 1, "midpoint": 2, "ralston": 3, "bosh3": 4, "rk4": 5, "dopri5": 6}
 DRIFT_LINEAR, DRIFT_LORENZ63, DRIFT_LORENZ96, DRIFT_QUADRATIC = 0, 1, 2, 3
 ORDERS = {"zeroth": 0, "first": 1, "second": 2}
 FLAG_KEEP_PUSHFORWARD = 1  # CDK_FLAG_KEEP_PUSHFORWARD (desc.reserved[2])
 ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
+ENTRY_POINTS.append("cdk_ekf_grad_f64")
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
                  "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
                  "cdk_last_error"]

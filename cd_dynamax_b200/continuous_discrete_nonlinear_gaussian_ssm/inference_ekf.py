@@ -69,3 +69,38 @@ def iterated_extended_kalman_smoother(params, emissions, hyperparams: EKFHyperPa
                                       t_emissions=None, num_iter: int = 2, inputs=None) -> PosteriorGSSMSmoothed:
     """Upstream silently runs a single smoothing pass (:577-586); so does this."""
     return extended_kalman_smoother(params, emissions, hyperparams, t_emissions, None, inputs)
+
+
+def ekf_marginal_log_prob_and_grad(params, emissions, t_emissions=None, hyperparams: EKFHyperParams = EKFHyperParams(),
+                                   inputs=None):
+    """Marginal log-likelihood of the CD-EKF and its gradient with respect to the drift parameters:
+    -> (marginal_loglik, {"sigma": .., "rho": .., "beta": ..}), batched like the filter ([N] each for [N,K,m] emissions).
+
+    This is what `jax.value_and_grad(lambda p: model.marginal_log_prob(p, ...))` yields upstream for the drift leaves
+    (src/utils/optimize_utils.py:102, src/ssm_temissions.py:550-568) -- here as a forward-mode derivative of exactly the
+    discrete filter `cdnlgssm_filter` runs (cdk_ekf_grad_f64), so that a `jax.custom_vjp` around the filter can be fed
+    (INTEGRATION.md).  First step of SURVEY section 8f rank 1: LearnableLorenz63 drift, scalar emission, num_iter = 1;
+    anything else raises NotImplementedError."""
+    from .cdnlgssm_utils import drift_to_theta
+    from ._common import nonlinear_inputs, _val
+    from ..continuous_discrete_linear_gaussian_ssm.inference import _shape, prepare_data
+    if type(params.dynamics.drift).__name__ != "LearnableLorenz63":
+        raise NotImplementedError("gradients are implemented for the LearnableLorenz63 drift only (SURVEY 8f rank 1)")
+    kind = E.kind_of(emissions)
+    Y, T, U, batched = prepare_data(emissions, t_emissions, None)
+    N, K, m = _shape(Y)
+    if m != 1:
+        raise NotImplementedError("gradients are implemented for scalar emissions only")
+    n = 3
+    dt = E.pick_dtype(emissions)
+    if dt != "f64":
+        raise NotImplementedError("gradients are fp64 only")
+    ins, drift_fields = nonlinear_inputs(params, Y, T, n, m)
+    fields = dict(E.parse_settings(hyperparams.diffeqsolve_settings), **drift_fields, **_ekf_fields(hyperparams, 1))
+    try:
+        out = E.run("cdk_ekf_grad", dt, N, K, n, m, ins, (L.OUT_LL, L.OUT_GRAD), fields, host_out=(kind != "cuda"))
+    except L.CdkError as e:
+        raise NotImplementedError(str(e)) from e
+    g = lambda t: E.from_dev(_sq(t, batched), kind)
+    grad = out[L.OUT_GRAD]
+    return g(out[L.OUT_LL]), {"sigma": g(grad[:, 0]), "rho": g(grad[:, 1]), "beta": g(grad[:, 2])}

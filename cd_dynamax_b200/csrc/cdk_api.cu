@@ -279,6 +279,18 @@ CDK_DEF(cdk_ukf_filter_f32, float, ALGO_UKF_FILTER)
 CDK_DEF(cdk_enkf_filter_f64, double, ALGO_ENKF_FILTER)
 CDK_DEF(cdk_enkf_filter_f32, float, ALGO_ENKF_FILTER)
 
+int cdk_ekf_grad_f64(const cdk_desc* d, const void* const* in, void* const* out, cdk_stream_t stream) {
+  int rc = validate(d, in, out, ALGO_EKF_FILTER);
+  if (rc != CDK_OK) return rc;
+  if (d->N == 0) return CDK_OK;
+  if (!out[CDK_OUT_GRAD]) return fail(CDK_E_NULL, "cdk_ekf_grad_f64 needs out[CDK_OUT_GRAD]");
+  KArgs<double> a = make_args<double>(d, in, out, ALGO_EKF_FILTER);
+  rc = launch_ekf_l63_grad(a, static_cast<double*>(out[CDK_OUT_GRAD]), reinterpret_cast<cudaStream_t>(stream));
+  if (rc == CDK_E_UNSUPPORTED)
+    return fail(rc, "cdk_ekf_grad_f64: only the Lorenz-63 drift with a scalar emission, num_iter = 1, order first/second");
+  return rc;
+}
+
 size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point) {
   if (!d || !entry_point) return 0;
   // the EnKF keeps its ensemble in (distributed) shared memory; the only device scratch is the optional pushforward

@@ -974,6 +974,195 @@ __global__ void __launch_bounds__(32 * 14, 1) eks_small_lw(const KArgs<T> a, con
   }
 }
 
+// ======================================================================================================================
+// d log-likelihood / d theta for the register CD-EKF (what jax.value_and_grad of
+// marginal_log_prob gives the reference's fit_sgd, src/utils/optimize_utils.py:102) -- FORWARD mode, drift parameters.
+// Tangent of the moment ODE (inference_ekf.py:76-123) w.r.t. theta_p:  m' and P' obey
+//   dm'/dt = J m' + df/dtheta_p,   dP'/dt = J' P + J P' + (J' P + J P')^T,   J' = (dJ/dm)[m'] + dJ/dtheta_p,
+// and an explicit RK step of the augmented system (m, P, m', P') IS the derivative of the RK step of (m, P) (the step
+// sizes do not depend on theta), so the result is the exact derivative of the discrete filter the forward kernels run.
+// Tangent of the scalar-emission update (:153-199, :285-289) with S = H P H^T + R, r = y - H m - d, K = P H^T / (S + 1e-9):
+//   l' = -r r'/S + (r^2/S^2 - 1/S) S'/2,   K' = (P' H^T) / (S + eps) - K S' / (S + eps),
+//   m+' = m' + K' r + K r',   P+' = P' - (K' S K^T + K S' K^T + K S K'^T).
+// One lane per trajectory, one launch per parameter (the base filter is recomputed: 18 doubles of state instead of 36).
+// ======================================================================================================================
+template <typename T, int NE, int SOLVER, class RHS>
+__device__ __forceinline__ void rk_step_flat(T (&y)[NE], T dt, RHS rhs) {
+  using TB = Tab<SOLVER>;
+  constexpr int I0 = TB::b(0) != 0.0 ? 0 : (TB::S > 1 && TB::b(1) != 0.0 ? 1 : (TB::S > 2 && TB::b(2) != 0.0 ? 2 : 3));
+  T k[TB::S][NE], ksum[NE];
+#pragma unroll
+  for (int i = 0; i < TB::S; ++i) {
+    T yi[NE];
+#pragma unroll
+    for (int e = 0; e < NE; ++e) yi[e] = y[e];
+#pragma unroll
+    for (int j = 0; j < i; ++j) {
+      if (TB::a(i, j) != 0.0) {
+        const T c = T(TB::a(i, j)) * dt;
+#pragma unroll
+        for (int e = 0; e < NE; ++e) yi[e] = fma(c, k[j][e], yi[e]);
+      }
+    }
+    rhs(yi, k[i]);
+    if (i == I0) {
+#pragma unroll
+      for (int e = 0; e < NE; ++e) ksum[e] = k[i][e];
+    } else if (TB::b(i) != 0.0) {
+      const T c = T(TB::b(i) / TB::b(I0));
+#pragma unroll
+      for (int e = 0; e < NE; ++e) ksum[e] = fma(c, k[i][e], ksum[e]);
+    }
+  }
+  const T w = T(TB::b(I0)) * dt;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) y[e] = fma(w, ksum[e], y[e]);
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a, const int p, double* __restrict__ grad,
+                                                             const int grad_stride) {
+  using T = double;
+  constexpr int NX = 3, NP = 6, NE = 2 * (NX + NP);
+  const long long N = a.d.N;
+  const int K = a.d.K;
+  const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (traj >= N) return;
+  T th[3], lql[NP], H[NX];
+  {
+    const T* thg = a.in[CDK_IN_F] + traj * a.in_stride[CDK_IN_F];
+    const T* Lm = a.in[CDK_IN_L] + traj * a.in_stride[CDK_IN_L];
+    const T* Qc = a.in[CDK_IN_QC] + traj * a.in_stride[CDK_IN_QC];
+    const T* Hg = a.in[CDK_IN_H] + traj * a.in_stride[CDK_IN_H];
+    for (int i = 0; i < 3; ++i) th[i] = thg[i];
+    for (int i = 0; i < NX; ++i) H[i] = Hg[i];
+    for (int i = 0; i < NX; ++i)
+      for (int j = i; j < NX; ++j) {
+        T acc = T(0);
+        for (int q = 0; q < NX; ++q) {
+          T lq = T(0);
+          for (int r = 0; r < NX; ++r) lq += Lm[i * NX + r] * Qc[r * NX + q];
+          acc += lq * Lm[j * NX + q];
+        }
+        lql[pidx<NX>(i, j)] = acc;
+      }
+  }
+  const T dv = (a.in[CDK_IN_D] + traj * a.in_stride[CDK_IN_D])[0];
+  const T R = (a.in[CDK_IN_R] + traj * a.in_stride[CDK_IN_R])[0];
+  const T* __restrict__ Y = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  // y = [m (3) | P (6) | m' (3) | P' (6)]
+  T y[NE];
+  {
+    const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
+    const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
+    for (int i = 0; i < NX; ++i) y[i] = m0[i];
+    for (int i = 0; i < NX; ++i)
+      for (int j = i; j < NX; ++j) y[NX + pidx<NX>(i, j)] = P0[i * NX + j];
+    for (int e = NX + NP; e < NE; ++e) y[e] = T(0);
+  }
+  const T ds = p == 0 ? T(1) : T(0), dr = p == 1 ? T(1) : T(0), db = p == 2 ? T(1) : T(0);
+  auto rhs = [&](const T (&u)[NE], T (&k)[NE]) {
+    T m[NX] = {u[0], u[1], u[2]}, mt[NX] = {u[9], u[10], u[11]};
+    T P[NP], Pt[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      P[i] = u[NX + i];
+      Pt[i] = u[NX + NP + NX + i];
+    }
+    T f[NX], G[NX][NX], G2[NX][NX];
+    DriftL63::f(th, m, f);
+    DriftL63::jp(th, m, P, G);    // J P
+    DriftL63::jp(th, m, Pt, G2);  // J P'
+    // f' = J m' + df/dtheta_p
+    const T ft0 = th[0] * (mt[1] - mt[0]) + ds * (m[1] - m[0]);
+    const T ft1 = (th[1] - m[2]) * mt[0] - mt[1] - m[0] * mt[2] + dr * m[0];
+    const T ft2 = m[1] * mt[0] + m[0] * mt[1] - th[2] * mt[2] - db * m[2];
+    // J' P,  J' = [[-ds, ds, 0], [dr - z', 0, -x'], [y', x', -db]]
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      const T p0 = P[pidx<NX>(0, j)], p1 = P[pidx<NX>(1, j)], p2 = P[pidx<NX>(2, j)];
+      G2[0][j] += ds * (p1 - p0);
+      G2[1][j] += (dr - mt[2]) * p0 - mt[0] * p2;
+      G2[2][j] += mt[1] * p0 + mt[0] * p1 - db * p2;
+    }
+    k[0] = f[0]; k[1] = f[1]; k[2] = f[2];
+    k[9] = ft0; k[10] = ft1; k[11] = ft2;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        k[NX + pidx<NX>(i, j)] = (G[i][j] + G[j][i]) + lql[pidx<NX>(i, j)];
+        k[NX + NP + NX + pidx<NX>(i, j)] = G2[i][j] + G2[j][i];
+      }
+  };
+  const T dt0 = T(a.d.dt0), dtf = T(a.d.dt_final), tol = clip_tol<T>();
+  const int max_steps = a.d.max_steps;
+  T ll = T(0), llt = T(0);
+  T tprev = Tm[0];
+  for (int k = 0; k < K; ++k) {
+    // ---- measurement update and its tangent ----
+    T HP[NX], HPt[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      T acc = T(0), acct = T(0);
+#pragma unroll
+      for (int q = 0; q < NX; ++q) {
+        acc += H[q] * y[NX + pidx<NX>(q, j)];
+        acct += H[q] * y[NX + NP + NX + pidx<NX>(q, j)];
+      }
+      HP[j] = acc;
+      HPt[j] = acct;
+    }
+    T S = R, St = T(0), hm = dv, hmt = T(0);
+#pragma unroll
+    for (int q = 0; q < NX; ++q) {
+      S += HP[q] * H[q];
+      St += HPt[q] * H[q];
+      hm += H[q] * y[q];
+      hmt += H[q] * y[NX + NP + q];
+    }
+    const T r = Y[k] - hm, rt = -hmt;
+    const T iS = T(1) / S;
+    ll += T(-0.5) * (r * r * iS) - T(0.5) * log(S) - half_log_2pi<T>();
+    llt += -(r * rt * iS) + T(0.5) * (r * r * iS * iS - iS) * St;
+    const T rb = T(1) / (S + T(1e-9));
+    T Kg[NX], Kt[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      Kg[j] = HP[j] * rb;
+      Kt[j] = HPt[j] * rb - Kg[j] * St * rb;
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+      for (int j = i; j < NX; ++j) {
+        y[NX + NP + NX + pidx<NX>(i, j)] -= Kt[i] * S * Kg[j] + Kg[i] * St * Kg[j] + Kg[i] * S * Kt[j];
+        y[NX + pidx<NX>(i, j)] -= Kg[i] * S * Kg[j];
+      }
+      y[NX + NP + i] += Kt[i] * r + Kg[i] * rt;
+      y[i] += Kg[i] * r;
+    }
+    // ---- predict across the gap (diffrax stepping rule) ----
+    const T t1 = k + 1 < K ? Tm[k + 1] : tprev + dtf;
+    T tnext = fmin(tprev + dt0, t1);
+    int nsteps = 0;
+    while (tprev < t1 && nsteps < max_steps) {
+      rk_step_flat<T, NE, SOLVER>(y, tnext - tprev, rhs);
+      ++nsteps;
+      tprev = tnext;
+      const T cand = tprev + dt0;
+      tnext = cand > t1 - tol ? t1 : cand;
+    }
+    if (tprev < t1) {
+      for (int e = 0; e < NE; ++e) y[e] = T(NAN);
+    }
+    tprev = t1;
+  }
+  if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
+  grad[traj * grad_stride + p] = llt;
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1113,6 +1302,27 @@ int launch_ekf_small(const KArgs<T>& a, cudaStream_t s) {
 int set_lw_trace(void* devbuf) {
   unsigned long long* p = static_cast<unsigned long long*>(devbuf);
   return cudaMemcpyToSymbol(g_lw_trace, &p, sizeof(p)) == cudaSuccess ? CDK_OK : CDK_E_CUDA;
+}
+
+// d ll / d theta of the Lorenz-63 CD-EKF (scalar emission, num_iter 1, state_order first / second): grad [N, 3]
+int launch_ekf_l63_grad(const KArgs<double>& a, double* grad, cudaStream_t s) {
+  const cdk_desc& d = a.d;
+  if (d.drift_id != CDK_DRIFT_LORENZ63 || d.n != 3 || d.m != 1 || d.num_iter != 1 || d.state_order == CDK_ORDER_ZEROTH)
+    return CDK_E_UNSUPPORTED;
+  if (d.N == 0) return CDK_OK;
+  const long long blocks = (d.N + 127) / 128;
+  if (blocks > 2147483647LL) return CDK_E_SIZE;
+  for (int p = 0; p < 3; ++p) {
+    switch (d.solver) {
+      case CDK_RK4: ekf_l63_grad_kernel<CDK_RK4><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
+      case CDK_DOPRI5: ekf_l63_grad_kernel<CDK_DOPRI5><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
+      case CDK_EULER: ekf_l63_grad_kernel<CDK_EULER><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
+      case CDK_HEUN: ekf_l63_grad_kernel<CDK_HEUN><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
+      default: return CDK_E_UNSUPPORTED;
+    }
+    note_launch();
+  }
+  return check_launch("ekf_l63_grad_kernel");
 }
 
 // EKS backward pass fast path: Lorenz-63, solvers rk4 / dopri5 / euler / heun (anything else: generic_smooth_kernel).

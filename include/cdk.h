@@ -97,7 +97,8 @@ enum {
   CDK_OUT_SP,     /* smoothed covariances  [N,K,n,n]                                                */
   CDK_OUT_SCROSS, /* smoothed cross terms  [N,K-1,n,n] (type 1; NaN for type 2)                    */
   CDK_OUT_STATUS, /* int32 [N]: 0 ok, 1 non-finite result (non-PD / NaN), 2 max_steps exceeded      */
-  CDK_OUT_SCRATCH,/* device scratch of cdk_scratch_bytes() bytes (EnKF with large ensembles), else NULL */
+  CDK_OUT_SCRATCH,/* device scratch of cdk_scratch_bytes() bytes (CD-KF pushforward cache), else NULL */
+  CDK_OUT_GRAD,   /* cdk_ekf_grad_f64: d marginal log-likelihood / d theta  [N, n_theta]                */
   CDK_NUM_OUT
 };
 
@@ -155,6 +156,11 @@ CDK_DECL(cdk_ukf_filter_f64);
 CDK_DECL(cdk_ukf_filter_f32);
 CDK_DECL(cdk_enkf_filter_f64);
 CDK_DECL(cdk_enkf_filter_f32);
+/* Log-likelihood (out[CDK_OUT_LL]) and its gradient with respect to the drift parameters (out[CDK_OUT_GRAD], [N, n_theta])
+ * of the CD-EKF: what jax.value_and_grad(marginal_log_prob) hands the reference's fit_sgd (src/utils/optimize_utils.py:102,
+ * src/ssm_temissions.py:550-568).  Forward-mode derivative of exactly the discrete filter cdk_ekf_filter_f64 runs.  Today:
+ * Lorenz-63 drift, scalar emission, num_iter = 1, state_order first / second; anything else returns CDK_E_UNSUPPORTED. */
+CDK_DECL(cdk_ekf_grad_f64);
 
 /* Bytes of device scratch the given entry point needs in out[CDK_OUT_SCRATCH] (0 for most). algo: "kf_filter", ... */
 size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point);

@@ -456,3 +456,40 @@ def test_eks_fast_path_matches_generic_kernel(monkeypatch):
         r = o.extended_kalman_smoother(po, y[n:n + 1], t[n:n + 1], settings=o.SolverSettings("rk4", 0.0025))
         assert scaled_err(s.smoothed_means[n], r["smoothed_means"][0]) < 1e-8
         assert scaled_err(s.smoothed_covariances[n], r["smoothed_covariances"][0]) < 1e-8
+
+
+# ---- d log-likelihood / d drift parameters (first step): forward-mode kernel vs central differences of
+# ---- the oracle's log-likelihood ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("solver,dt0", [("rk4", 0.0025), ("dopri5", 0.01), ("heun", 0.002)])
+def test_ekf_loglik_gradient_vs_oracle_finite_differences(solver, dt0):
+    cd = api()
+    N, K = 6, 40
+    t, y = c3_problem(N, K, seed=21)
+    theta = np.array([10.0, 28.0, 8.0 / 3.0])
+    g = dict(m0=np.array([1.0, 1.0, 20.0]), P0=2 * np.eye(3), drift="lorenz63", theta=theta,
+             L=np.eye(3) + 0.1 * np.arange(9).reshape(3, 3) / 9, Qc=np.eye(3) + 0.05, H=np.array([[1.0, 0.3, -0.2]]),
+             R=0.7 * np.eye(1), d=np.array([0.1]))
+    hp = cd.EKFHyperParams(dt_final=0.004, diffeqsolve_settings={"solver": solver, "dt0": dt0})
+    ll, grad = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp)
+    f = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], hp, output_fields=[])
+    assert max_rel_err(ll, f.marginal_loglik) < 1e-12  # the value is the filter's own
+
+    def oracle_ll(th):
+        po = o.NonlinearParams(m0=g["m0"], P0=g["P0"], drift=make_drift("lorenz63", th, 3), L=g["L"], Qc=g["Qc"],
+                               H=g["H"], R=g["R"], d=g["d"])
+        return o.extended_kalman_filter(po, y, t, dt_final=0.004, settings=o.SolverSettings(solver, dt0))["marginal_loglik"]
+
+    for p, name in enumerate(("sigma", "rho", "beta")):
+        h = 1e-5 * theta[p]
+        tp, tm = theta.copy(), theta.copy()
+        tp[p] += h
+        tm[p] -= h
+        fd = (oracle_ll(tp) - oracle_ll(tm)) / (2 * h)
+        # central differences at h = 1e-5 |theta|: truncation ~1e-10 relative, round-off ~1e-9 absolute
+        np.testing.assert_allclose(grad[name], fd, rtol=2e-6, atol=2e-7, err_msg=name)
+    # unbatched call keeps scalar shapes; unsupported requests fail loudly
+    ll1, g1 = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y[0], t[0][:, None], hp)
+    assert np.ndim(ll1) == 0 and np.ndim(g1["rho"]) == 0 and g1["rho"] == grad["rho"][0]
+    with pytest.raises(NotImplementedError):
+        cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(dict(g, H=np.eye(3)[:2], R=np.eye(2), d=np.zeros(2))),
+                                          np.zeros((K, 2)), t[0][:, None], hp)
