@@ -111,6 +111,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     for k, v in desc_fields.items():
         if k == "flags":
             d.reserved[2] = int(v)
+        elif k == "grad_groups":
+            d.reserved[3] = int(v)
         else:
             setattr(d, k, v)
     tdt = _TORCH_DT[dt]
@@ -246,7 +248,7 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
 
 def _out_shape(slot, N, K, n, scross_rows=None, n_theta=0):
     return {
-        L.OUT_GRAD: (N, n_theta),
+        L.OUT_GRAD: (N, L.GRAD_COLS_L63),
         L.OUT_LL: (N,), L.OUT_FM: (N, K, n), L.OUT_FP: (N, K, n, n), L.OUT_PM: (N, K, n), L.OUT_PP: (N, K, n, n),
         L.OUT_LLCUM: (N, K), L.OUT_SM: (N, K, n), L.OUT_SP: (N, K, n, n),
         L.OUT_SCROSS: (N, max(K - 1, 0) if scross_rows is None else scross_rows, n, n), L.OUT_STATUS: (N,),

@@ -71,21 +71,37 @@ def iterated_extended_kalman_smoother(params, emissions, hyperparams: EKFHyperPa
     return extended_kalman_smoother(params, emissions, hyperparams, t_emissions, None, inputs)
 
 
-def ekf_marginal_log_prob_and_grad(params, emissions, t_emissions=None, hyperparams: EKFHyperParams = EKFHyperParams(),
-                                   inputs=None):
-    """Marginal log-likelihood of the CD-EKF and its gradient with respect to the drift parameters:
-    -> (marginal_loglik, {"sigma": .., "rho": .., "beta": ..}), batched like the filter ([N] each for [N,K,m] emissions).
+_GRAD_GROUPS = {"drift": 1, "diffusion_coefficient": 2, "diffusion_cov": 2, "emission_cov": 4, "emission_bias": 8,
+                "emission_weights": 16, "initial_mean": 32, "initial_cov": 64}
 
-    This is what `jax.value_and_grad(lambda p: model.marginal_log_prob(p, ...))` yields upstream for the drift leaves
+
+def ekf_marginal_log_prob_and_grad(params, emissions, t_emissions=None, hyperparams: EKFHyperParams = EKFHyperParams(),
+                                   inputs=None, wrt=("drift",)):
+    """Marginal log-likelihood of the CD-EKF and its gradient with respect to the model parameters.
+
+    -> (marginal_loglik, grads): `grads` maps "sigma", "rho", "beta" (wrt "drift"), "diffusion_coefficient" [3,3],
+    "diffusion_cov" [3,3], "emission_cov" [1,1], "emission_bias" [1], "emission_weights" [1,3], "initial_mean" [3],
+    "initial_cov" [3,3] to arrays, with a leading N for batched emissions.  `wrt` = any of those group names, or "all".
+
+    This is what `jax.value_and_grad(lambda p: model.marginal_log_prob(p, ...))` yields upstream
     (src/utils/optimize_utils.py:102, src/ssm_temissions.py:550-568) -- here as a forward-mode derivative of exactly the
-    discrete filter `cdnlgssm_filter` runs (cdk_ekf_grad_f64), so that a `jax.custom_vjp` around the filter can be fed
-    (INTEGRATION.md).  First step of SURVEY section 8f rank 1: LearnableLorenz63 drift, scalar emission, num_iter = 1;
-    anything else raises NotImplementedError."""
-    from .cdnlgssm_utils import drift_to_theta
+    discrete filter `cdnlgssm_filter` runs (cdk_ekf_grad_f64, one launch per direction), so that a `jax.custom_vjp`
+    around the filter can be fed.  Symmetric matrices (diffusion_cov, initial_cov) are differentiated
+    along symmetric directions: the result is the symmetric part (G + G^T)/2 of the entry-wise gradient G, which is what
+    any PSD parameterisation consumes; diffusion_coefficient's gradient is exact.  First step of SURVEY section 8f rank 1:
+    LearnableLorenz63 drift, scalar emission, num_iter = 1, fp64; anything else raises NotImplementedError."""
+    import torch
     from ._common import nonlinear_inputs, _val
     from ..continuous_discrete_linear_gaussian_ssm.inference import _shape, prepare_data
     if type(params.dynamics.drift).__name__ != "LearnableLorenz63":
         raise NotImplementedError("gradients are implemented for the LearnableLorenz63 drift only (SURVEY 8f rank 1)")
+    wrt = tuple(_GRAD_GROUPS) if wrt == "all" else ((wrt,) if isinstance(wrt, str) else tuple(wrt))
+    unknown = [w for w in wrt if w not in _GRAD_GROUPS]
+    if unknown:
+        raise ValueError(f"unknown gradient groups {unknown}; choose from {sorted(_GRAD_GROUPS)}")
+    groups = 0
+    for w in wrt:
+        groups |= _GRAD_GROUPS[w]
     kind = E.kind_of(emissions)
     Y, T, U, batched = prepare_data(emissions, t_emissions, None)
     N, K, m = _shape(Y)
@@ -97,10 +113,44 @@ def ekf_marginal_log_prob_and_grad(params, emissions, t_emissions=None, hyperpar
         raise NotImplementedError("gradients are fp64 only")
     ins, drift_fields = nonlinear_inputs(params, Y, T, n, m)
     fields = dict(E.parse_settings(hyperparams.diffeqsolve_settings), **drift_fields, **_ekf_fields(hyperparams, 1))
+    fields["grad_groups"] = groups
+    dev_ins = {}
     try:
-        out = E.run("cdk_ekf_grad", dt, N, K, n, m, ins, (L.OUT_LL, L.OUT_GRAD), fields, host_out=(kind != "cuda"))
+        out = E.run("cdk_ekf_grad", dt, N, K, n, m, ins, (L.OUT_LL, L.OUT_GRAD), fields, dev_inputs=dev_ins)
     except L.CdkError as e:
         raise NotImplementedError(str(e)) from e
+    G = out[L.OUT_GRAD]  # [N, 23] on the device: theta 3 | LQL 6 | R | d | H 3 | m0 3 | P0 6
     g = lambda t: E.from_dev(_sq(t, batched), kind)
-    grad = out[L.OUT_GRAD]
-    return g(out[L.OUT_LL]), {"sigma": g(grad[:, 0]), "rho": g(grad[:, 1]), "beta": g(grad[:, 2])}
+
+    def sym(cols):  # packed symmetric-direction derivatives -> symmetric gradient matrix Gs (off-diagonals halved)
+        M = torch.zeros((N, 3, 3), dtype=G.dtype, device=G.device)
+        iu = [(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]
+        for c, (i, j) in enumerate(iu):
+            v = cols[:, c] if i == j else 0.5 * cols[:, c]
+            M[:, i, j] = v
+            M[:, j, i] = v
+        return M
+
+    grads = {}
+    if groups & 1:
+        grads.update(sigma=g(G[:, 0]), rho=g(G[:, 1]), beta=g(G[:, 2]))
+    if groups & 2:
+        Gs = sym(G[:, 3:9])
+        Lm, Qc = dev_ins[L.IN_L].to(G.dtype), dev_ins[L.IN_QC].to(G.dtype)
+        Lm = Lm.expand(N, 3, 3) if Lm.dim() == 2 else Lm
+        Qc = Qc.expand(N, 3, 3) if Qc.dim() == 2 else Qc
+        if "diffusion_cov" in wrt:
+            grads["diffusion_cov"] = g(Lm.transpose(1, 2) @ Gs @ Lm)  # d(L Qc L^T) = L dQc L^T
+        if "diffusion_coefficient" in wrt:
+            grads["diffusion_coefficient"] = g(2.0 * Gs @ Lm @ Qc)  # d(L Qc L^T) = dL Qc L^T + L Qc dL^T
+    if groups & 4:
+        grads["emission_cov"] = g(G[:, 9].reshape(N, 1, 1))
+    if groups & 8:
+        grads["emission_bias"] = g(G[:, 10].reshape(N, 1))
+    if groups & 16:
+        grads["emission_weights"] = g(G[:, 11:14].reshape(N, 1, 3))
+    if groups & 32:
+        grads["initial_mean"] = g(G[:, 14:17])
+    if groups & 64:
+        grads["initial_cov"] = g(sym(G[:, 17:23]))
+    return g(out[L.OUT_LL]), grads

@@ -1019,9 +1019,14 @@ __device__ __forceinline__ void rk_step_flat(T (&y)[NE], T dt, RHS rhs) {
   for (int e = 0; e < NE; ++e) y[e] = fma(w, ksum[e], y[e]);
 }
 
+// Direction of differentiation = (kind, idx): CDK_GRAD_THETA idx 0..2 (sigma, rho, beta); CDK_GRAD_LQL / CDK_GRAD_P0
+// idx = packed upper-triangle index of the SYMMETRIC matrix L Qc L^T / P0 (an off-diagonal direction moves both mirror
+// entries); CDK_GRAD_R, CDK_GRAD_D (scalar emission); CDK_GRAD_H, CDK_GRAD_M0 idx 0..2.  Column `col` of grad.
+enum { CDK_GRAD_THETA = 0, CDK_GRAD_LQL, CDK_GRAD_R, CDK_GRAD_D, CDK_GRAD_H, CDK_GRAD_M0, CDK_GRAD_P0 };
+
 template <int SOLVER>
-__global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a, const int p, double* __restrict__ grad,
-                                                             const int grad_stride) {
+__global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a, const int kind, const int idx,
+                                                             double* __restrict__ grad, const int grad_stride, const int col) {
   using T = double;
   constexpr int NX = 3, NP = 6, NE = 2 * (NX + NP);
   const long long N = a.d.N;
@@ -1034,13 +1039,19 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
     const T* Lm = a.in[CDK_IN_L] + traj * a.in_stride[CDK_IN_L];
     const T* Qc = a.in[CDK_IN_QC] + traj * a.in_stride[CDK_IN_QC];
     const T* Hg = a.in[CDK_IN_H] + traj * a.in_stride[CDK_IN_H];
+#pragma unroll
     for (int i = 0; i < 3; ++i) th[i] = thg[i];
+#pragma unroll
     for (int i = 0; i < NX; ++i) H[i] = Hg[i];
+#pragma unroll
     for (int i = 0; i < NX; ++i)
+#pragma unroll
       for (int j = i; j < NX; ++j) {
         T acc = T(0);
+#pragma unroll
         for (int q = 0; q < NX; ++q) {
           T lq = T(0);
+#pragma unroll
           for (int r = 0; r < NX; ++r) lq += Lm[i * NX + r] * Qc[r * NX + q];
           acc += lq * Lm[j * NX + q];
         }
@@ -1056,12 +1067,30 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
   {
     const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
     const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
+#pragma unroll
     for (int i = 0; i < NX; ++i) y[i] = m0[i];
+#pragma unroll
     for (int i = 0; i < NX; ++i)
+#pragma unroll
       for (int j = i; j < NX; ++j) y[NX + pidx<NX>(i, j)] = P0[i * NX + j];
+#pragma unroll
     for (int e = NX + NP; e < NE; ++e) y[e] = T(0);
+#pragma unroll
+    for (int e = 0; e < NX; ++e)
+      if (kind == CDK_GRAD_M0 && idx == e) y[NX + NP + e] = T(1);
+#pragma unroll
+    for (int e = 0; e < NP; ++e)
+      if (kind == CDK_GRAD_P0 && idx == e) y[NX + NP + NX + e] = T(1);
   }
-  const T ds = p == 0 ? T(1) : T(0), dr = p == 1 ? T(1) : T(0), db = p == 2 ? T(1) : T(0);
+  const bool wrt_theta = kind == CDK_GRAD_THETA;
+  const T ds = wrt_theta && idx == 0 ? T(1) : T(0), dr = wrt_theta && idx == 1 ? T(1) : T(0),
+          db = wrt_theta && idx == 2 ? T(1) : T(0);
+  const T dR = kind == CDK_GRAD_R ? T(1) : T(0), dd = kind == CDK_GRAD_D ? T(1) : T(0);
+  T dH[NX], dlql[NP];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) dH[i] = (kind == CDK_GRAD_H && idx == i) ? T(1) : T(0);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) dlql[i] = (kind == CDK_GRAD_LQL && idx == i) ? T(1) : T(0);
   auto rhs = [&](const T (&u)[NE], T (&k)[NE]) {
     T m[NX] = {u[0], u[1], u[2]}, mt[NX] = {u[9], u[10], u[11]};
     T P[NP], Pt[NP];
@@ -1093,7 +1122,7 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
 #pragma unroll
       for (int j = i; j < NX; ++j) {
         k[NX + pidx<NX>(i, j)] = (G[i][j] + G[j][i]) + lql[pidx<NX>(i, j)];
-        k[NX + NP + NX + pidx<NX>(i, j)] = G2[i][j] + G2[j][i];
+        k[NX + NP + NX + pidx<NX>(i, j)] = (G2[i][j] + G2[j][i]) + dlql[pidx<NX>(i, j)];
       }
   };
   const T dt0 = T(a.d.dt0), dtf = T(a.d.dt_final), tol = clip_tol<T>();
@@ -1101,7 +1130,7 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
   T ll = T(0), llt = T(0);
   T tprev = Tm[0];
   for (int k = 0; k < K; ++k) {
-    // ---- measurement update and its tangent ----
+    // ---- measurement update and its tangent (H' = dH, R' = dR, d' = dd are the parameter seeds) ----
     T HP[NX], HPt[NX];
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
@@ -1109,18 +1138,18 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
 #pragma unroll
       for (int q = 0; q < NX; ++q) {
         acc += H[q] * y[NX + pidx<NX>(q, j)];
-        acct += H[q] * y[NX + NP + NX + pidx<NX>(q, j)];
+        acct += H[q] * y[NX + NP + NX + pidx<NX>(q, j)] + dH[q] * y[NX + pidx<NX>(q, j)];
       }
       HP[j] = acc;
-      HPt[j] = acct;
+      HPt[j] = acct;  // (H P)' = H P' + H' P
     }
-    T S = R, St = T(0), hm = dv, hmt = T(0);
+    T S = R, St = dR, hm = dv, hmt = dd;
 #pragma unroll
     for (int q = 0; q < NX; ++q) {
       S += HP[q] * H[q];
-      St += HPt[q] * H[q];
+      St += HPt[q] * H[q] + HP[q] * dH[q];  // S' = (H P)' H^T + H P H'^T + R'
       hm += H[q] * y[q];
-      hmt += H[q] * y[NX + NP + q];
+      hmt += H[q] * y[NX + NP + q] + dH[q] * y[q];
     }
     const T r = Y[k] - hm, rt = -hmt;
     const T iS = T(1) / S;
@@ -1155,12 +1184,13 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
       tnext = cand > t1 - tol ? t1 : cand;
     }
     if (tprev < t1) {
+#pragma unroll
       for (int e = 0; e < NE; ++e) y[e] = T(NAN);
     }
     tprev = t1;
   }
   if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
-  grad[traj * grad_stride + p] = llt;
+  grad[traj * grad_stride + col] = llt;
 }
 
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -1304,7 +1334,9 @@ int set_lw_trace(void* devbuf) {
   return cudaMemcpyToSymbol(g_lw_trace, &p, sizeof(p)) == cudaSuccess ? CDK_OK : CDK_E_CUDA;
 }
 
-// d ll / d theta of the Lorenz-63 CD-EKF (scalar emission, num_iter 1, state_order first / second): grad [N, 3]
+// Gradient of the Lorenz-63 CD-EKF log-likelihood (scalar emission, num_iter 1, state_order first / second):
+// grad [N, 23], columns = theta (3) | L Qc L^T packed (6) | R | d | H (3) | m0 (3) | P0 packed (6); `groups` (bit g = group g
+// in that order, 0 = theta only) selects which columns are computed (the others are left untouched).
 int launch_ekf_l63_grad(const KArgs<double>& a, double* grad, cudaStream_t s) {
   const cdk_desc& d = a.d;
   if (d.drift_id != CDK_DRIFT_LORENZ63 || d.n != 3 || d.m != 1 || d.num_iter != 1 || d.state_order == CDK_ORDER_ZEROTH)
@@ -1312,15 +1344,22 @@ int launch_ekf_l63_grad(const KArgs<double>& a, double* grad, cudaStream_t s) {
   if (d.N == 0) return CDK_OK;
   const long long blocks = (d.N + 127) / 128;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
-  for (int p = 0; p < 3; ++p) {
-    switch (d.solver) {
-      case CDK_RK4: ekf_l63_grad_kernel<CDK_RK4><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
-      case CDK_DOPRI5: ekf_l63_grad_kernel<CDK_DOPRI5><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
-      case CDK_EULER: ekf_l63_grad_kernel<CDK_EULER><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
-      case CDK_HEUN: ekf_l63_grad_kernel<CDK_HEUN><<<(unsigned)blocks, 128, 0, s>>>(a, p, grad, 3); break;
-      default: return CDK_E_UNSUPPORTED;
+  const int groups = d.reserved[3] ? d.reserved[3] : 1;
+  static const int kinds[7] = {CDK_GRAD_THETA, CDK_GRAD_LQL, CDK_GRAD_R, CDK_GRAD_D, CDK_GRAD_H, CDK_GRAD_M0, CDK_GRAD_P0};
+  static const int count[7] = {3, 6, 1, 1, 3, 3, 6};
+  int col = 0;
+  for (int g = 0; g < 7; ++g) {
+    for (int idx = 0; idx < count[g]; ++idx, ++col) {
+      if (!((groups >> g) & 1)) continue;
+      switch (d.solver) {
+        case CDK_RK4: ekf_l63_grad_kernel<CDK_RK4><<<(unsigned)blocks, 128, 0, s>>>(a, kinds[g], idx, grad, CDK_GRAD_COLS_L63, col); break;
+        case CDK_DOPRI5: ekf_l63_grad_kernel<CDK_DOPRI5><<<(unsigned)blocks, 128, 0, s>>>(a, kinds[g], idx, grad, CDK_GRAD_COLS_L63, col); break;
+        case CDK_EULER: ekf_l63_grad_kernel<CDK_EULER><<<(unsigned)blocks, 128, 0, s>>>(a, kinds[g], idx, grad, CDK_GRAD_COLS_L63, col); break;
+        case CDK_HEUN: ekf_l63_grad_kernel<CDK_HEUN><<<(unsigned)blocks, 128, 0, s>>>(a, kinds[g], idx, grad, CDK_GRAD_COLS_L63, col); break;
+        default: return CDK_E_UNSUPPORTED;
+      }
+      note_launch();
     }
-    note_launch();
   }
   return check_launch("ekf_l63_grad_kernel");
 }

@@ -98,7 +98,7 @@ enum {
   CDK_OUT_SCROSS, /* smoothed cross terms  [N,K-1,n,n] (type 1; NaN for type 2)                    */
   CDK_OUT_STATUS, /* int32 [N]: 0 ok, 1 non-finite result (non-PD / NaN), 2 max_steps exceeded      */
   CDK_OUT_SCRATCH,/* device scratch of cdk_scratch_bytes() bytes (CD-KF pushforward cache), else NULL */
-  CDK_OUT_GRAD,   /* cdk_ekf_grad_f64: d marginal log-likelihood / d theta  [N, n_theta]                */
+  CDK_OUT_GRAD,   /* cdk_ekf_grad_f64: d marginal log-likelihood / d parameters  [N, CDK_GRAD_COLS_L63]    */
   CDK_NUM_OUT
 };
 
@@ -126,7 +126,7 @@ typedef struct cdk_desc {
   double alpha, beta, kappa;    /* ukf (inference_ukf.py:31-33) */
   uint64_t rng_seed;      /* enkf: Philox4x32-10 key */
   uint64_t rng_offset;    /* enkf: added to the trajectory index in the counter (sharding across GPUs) */
-  int32_t reserved[4];    /* [0], [1]: absent-slot masks of the XLA adaptor; [2]: CDK_FLAG_* bits; [3]: 0 */
+  int32_t reserved[4];    /* [0], [1]: absent-slot masks of the XLA adaptor; [2]: CDK_FLAG_* bits; [3]: cdk_ekf_grad groups */
 } cdk_desc;
 
 /* reserved[2] bit 0: keep the pushforward.  cdk_kf_filter_f64 then also writes (A_k, Q_k) of every gap k < K-1 into
@@ -156,10 +156,15 @@ CDK_DECL(cdk_ukf_filter_f64);
 CDK_DECL(cdk_ukf_filter_f32);
 CDK_DECL(cdk_enkf_filter_f64);
 CDK_DECL(cdk_enkf_filter_f32);
-/* Log-likelihood (out[CDK_OUT_LL]) and its gradient with respect to the drift parameters (out[CDK_OUT_GRAD], [N, n_theta])
- * of the CD-EKF: what jax.value_and_grad(marginal_log_prob) hands the reference's fit_sgd (src/utils/optimize_utils.py:102,
- * src/ssm_temissions.py:550-568).  Forward-mode derivative of exactly the discrete filter cdk_ekf_filter_f64 runs.  Today:
+/* Log-likelihood (out[CDK_OUT_LL]) and its gradient with respect to the model parameters (out[CDK_OUT_GRAD],
+ * [N, CDK_GRAD_COLS_L63]) of the CD-EKF: what jax.value_and_grad(marginal_log_prob) hands the reference's fit_sgd
+ * (src/utils/optimize_utils.py:102, src/ssm_temissions.py:550-568).  Forward-mode derivative of exactly the discrete filter
+ * cdk_ekf_filter_f64 runs, one launch per direction.  Columns: theta = sigma, rho, beta (3) | L Qc L^T, packed upper
+ * triangle 00 01 02 11 12 22 (6) | R | d | H (3) | m0 (3) | P0, packed upper triangle (6).  Symmetric matrices are
+ * differentiated along SYMMETRIC directions (an off-diagonal column moves both mirror entries).  desc.reserved[3] is a
+ * bit mask of the column groups to compute, in that order (0 = theta only); other columns are left untouched.  Today:
  * Lorenz-63 drift, scalar emission, num_iter = 1, state_order first / second; anything else returns CDK_E_UNSUPPORTED. */
+#define CDK_GRAD_COLS_L63 23
 CDK_DECL(cdk_ekf_grad_f64);
 
 /* Bytes of device scratch the given entry point needs in out[CDK_OUT_SCRATCH] (0 for most). algo: "kf_filter", ... */

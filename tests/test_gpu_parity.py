@@ -493,3 +493,49 @@ def test_ekf_loglik_gradient_vs_oracle_finite_differences(solver, dt0):
     with pytest.raises(NotImplementedError):
         cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(dict(g, H=np.eye(3)[:2], R=np.eye(2), d=np.zeros(2))),
                                           np.zeros((K, 2)), t[0][:, None], hp)
+
+
+def test_ekf_loglik_gradient_all_parameter_groups():
+    """Every leaf of the Lorenz-63 CD-EKF model: directional derivatives of the oracle's log-likelihood (central
+    differences) against <gradient, direction>.  Symmetric matrices are probed along symmetric directions."""
+    cd = api()
+    N, K = 4, 30
+    t, y = c3_problem(N, K, seed=33)
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((3, 3))
+    g = dict(m0=np.array([1.0, 1.0, 20.0]), P0=2 * np.eye(3) + 0.1 * (A + A.T), drift="lorenz63",
+             theta=np.array([10.0, 28.0, 8.0 / 3.0]), L=np.eye(3) + 0.2 * rng.standard_normal((3, 3)),
+             Qc=np.eye(3) + 0.05 * (A @ A.T), H=np.array([[1.0, 0.3, -0.2]]), R=0.7 * np.eye(1), d=np.array([0.1]))
+    hp = cd.EKFHyperParams(dt_final=0.004, diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    ll, grads = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp, wrt="all")
+    assert set(grads) == {"sigma", "rho", "beta", "diffusion_coefficient", "diffusion_cov", "emission_cov", "emission_bias",
+                          "emission_weights", "initial_mean", "initial_cov"}
+
+    def oracle_ll(**over):
+        q = dict(g, **over)
+        po = o.NonlinearParams(m0=q["m0"], P0=q["P0"], drift=make_drift("lorenz63", q["theta"], 3), L=q["L"], Qc=q["Qc"],
+                               H=q["H"], R=q["R"], d=q["d"])
+        return o.extended_kalman_filter(po, y, t, dt_final=0.004, settings=o.SolverSettings("rk4", 0.0025))["marginal_loglik"]
+
+    def check(key, name, direction, h=1e-6):
+        base = g[key]
+        fd = (oracle_ll(**{key: base + h * direction}) - oracle_ll(**{key: base - h * direction})) / (2 * h)
+        got = np.sum(grads[name].reshape(N, -1) * direction.reshape(1, -1), axis=1)
+        np.testing.assert_allclose(got, fd, rtol=5e-6, atol=5e-7, err_msg=f"{name} along {direction.ravel()}")
+
+    E = lambda i, j: np.eye(3)[:, [i]] @ np.eye(3)[[j], :]
+    for i in range(3):
+        check("m0", "initial_mean", np.eye(3)[i])
+        check("H", "emission_weights", np.eye(3)[[i]])
+        for j in range(3):
+            check("L", "diffusion_coefficient", E(i, j))  # exact entry-wise gradient
+        for j in range(i, 3):
+            D = E(i, j) + E(j, i) if i != j else E(i, i)  # symmetric directions
+            check("Qc", "diffusion_cov", D)
+            check("P0", "initial_cov", D)
+    check("R", "emission_cov", np.ones((1, 1)))
+    check("d", "emission_bias", np.ones(1))
+    # the gradient matrices of symmetric parameters are symmetric; the default group is the drift alone
+    assert np.allclose(grads["diffusion_cov"], np.swapaxes(grads["diffusion_cov"], 1, 2))
+    ll2, g2 = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp)
+    assert set(g2) == {"sigma", "rho", "beta"} and np.array_equal(g2["rho"], grads["rho"]) and np.array_equal(ll2, ll)
