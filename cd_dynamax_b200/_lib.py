@@ -18,7 +18,7 @@ ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
 ENTRY_POINTS.append("cdk_ekf_grad_f64")
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
-                 "cdk_xla_custom_call", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
+                 "cdk_xla_custom_call", "cdk_xla_custom_call_status", "cdk_xla_last_rc", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
                  "cdk_last_error"]
 
 
@@ -75,6 +75,11 @@ def lib():
         fn.restype = ctypes.c_int
     L.cdk_fma3_probe_f64.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.cdk_fma3_probe_f64.restype = ctypes.c_int
+    L.cdk_xla_custom_call.argtypes = [ctypes.c_void_p, pp, ctypes.c_char_p, ctypes.c_size_t]
+    L.cdk_xla_custom_call.restype = None
+    L.cdk_xla_custom_call_status.argtypes = [ctypes.c_void_p, pp, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_void_p]
+    L.cdk_xla_custom_call_status.restype = None
+    L.cdk_xla_last_rc.restype = ctypes.c_int
     L.cdk_debug_set_trace.argtypes = [ctypes.c_void_p]
     L.cdk_debug_set_trace.restype = ctypes.c_int
     L.cdk_launch_count.restype = ctypes.c_int64

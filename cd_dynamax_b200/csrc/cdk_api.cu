@@ -327,11 +327,9 @@ int cdk_ll_allreduce(void* nccl_comm, double* ll_sum, cdk_stream_t stream) {
   return CDK_OK;
 }
 
-void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len) {
-  if (!buffers || !opaque || opaque_len < sizeof(cdk_xla_opaque)) {
-    fail(CDK_E_SIZE, "xla custom call: bad opaque");
-    return;
-  }
+// Shared body of the two XLA adaptors: unpack the opaque blob, rebuild the in[] / out[] slot arrays, dispatch by name.
+static int xla_dispatch(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len) {
+  if (!buffers || !opaque || opaque_len < sizeof(cdk_xla_opaque)) return fail(CDK_E_SIZE, "xla custom call: bad opaque");
   cdk_xla_opaque op;
   memcpy(&op, opaque, sizeof(op));
   op.entry_point[sizeof(op.entry_point) - 1] = 0;
@@ -346,14 +344,35 @@ void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque
       {"cdk_ekf_filter_f64", cdk_ekf_filter_f64}, {"cdk_ekf_filter_f32", cdk_ekf_filter_f32},
       {"cdk_ekf_smooth_f64", cdk_ekf_smooth_f64}, {"cdk_ekf_smooth_f32", cdk_ekf_smooth_f32},
       {"cdk_ukf_filter_f64", cdk_ukf_filter_f64}, {"cdk_ukf_filter_f32", cdk_ukf_filter_f32},
-      {"cdk_enkf_filter_f64", cdk_enkf_filter_f64}, {"cdk_enkf_filter_f32", cdk_enkf_filter_f32}};
+      {"cdk_enkf_filter_f64", cdk_enkf_filter_f64}, {"cdk_enkf_filter_f32", cdk_enkf_filter_f32},
+      {"cdk_ekf_grad_f64", cdk_ekf_grad_f64}};
   for (auto& e : table)
-    if (strcmp(e.name, op.entry_point) == 0) {
-      e.fn(&op.desc, in, out, stream);
-      return;
-    }
-  fail(CDK_E_ENUM, "xla custom call: unknown entry point");
+    if (strcmp(e.name, op.entry_point) == 0) return e.fn(&op.desc, in, out, stream);
+  return fail(CDK_E_ENUM, "xla custom call: unknown entry point");
 }
+
+static thread_local int g_xla_rc = 0;
+
+void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len) {
+  g_xla_rc = xla_dispatch(stream, buffers, opaque, opaque_len);
+}
+
+void cdk_xla_custom_call_status(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status) {
+  g_xla_rc = xla_dispatch(stream, buffers, opaque, opaque_len);
+  if (g_xla_rc == CDK_OK || !status) return;
+  // XlaCustomCallStatusSetFailure(XlaCustomCallStatus*, const char* message, size_t message_len) lives in the XLA
+  // runtime (jaxlib) that called us; resolved at run time so libcdk.so has no link-time dependency on it.
+  typedef void (*set_failure_fn)(void*, const char*, size_t);
+  static set_failure_fn set_failure = reinterpret_cast<set_failure_fn>(dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure"));
+  if (!set_failure) set_failure = reinterpret_cast<set_failure_fn>(dlsym(RTLD_DEFAULT, "XlaCustomCallStatusSetFailure"));
+  if (set_failure) {
+    char msg[320];
+    const int len = snprintf(msg, sizeof(msg), "cdk (%d): %s", g_xla_rc, g_err);
+    set_failure(status, msg, (size_t)(len < (int)sizeof(msg) ? len : (int)sizeof(msg) - 1));
+  }
+}
+
+int cdk_xla_last_rc(void) { return g_xla_rc; }
 
 int cdk_fma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream) { return fma_probe<double>(blocks, iters, sink, stream); }
 int cdk_fma_probe_f32(int blocks, int iters, float* sink, cdk_stream_t stream) { return fma_probe<float>(blocks, iters, sink, stream); }

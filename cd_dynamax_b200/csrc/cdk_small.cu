@@ -398,7 +398,9 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   const long long N = a.d.N;
   const int K = a.d.K;
   const int lane = threadIdx.x & 31;
-  const long long cta0 = (long long)blockIdx.x * WPC * 32;
+  // the CTA may be launched with FEWER warps than WPC (launch_one picks the count from N so that a small batch still
+  // spreads over every SM and sub-partition): the trajectory map only depends on the run-time block size
+  const long long cta0 = (long long)blockIdx.x * blockDim.x;
   const long long traj0 = cta0 + warp * 32;
   // Optional FP64-pipe semaphore (CDK_LW_TOKEN = permits, default off): at most `permits` warps of an SM sub-partition are
   // inside the RK substep loop at a time (FIFO tickets), the others update / stage / store.  Built to break the convoy
@@ -723,14 +725,13 @@ __global__ void __launch_bounds__(32 * 14, 1) eks_small_lw(const KArgs<T> a, con
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
-  constexpr int WPC = 14;
   using S = EKSmem<T, NX>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   S& sm = *reinterpret_cast<S*>(smem_raw + (size_t)warp * sizeof(S));
   const long long N = a.d.N;
   const int K = a.d.K;
-  const long long traj0 = ((long long)blockIdx.x * WPC + warp) * 32;
+  const long long traj0 = (long long)blockIdx.x * blockDim.x + warp * 32;  // 1..14 warps per CTA (launch_eks_one)
   if (traj0 >= N) return;
   const long long traj = traj0 + lane;
   const bool live = traj < N;
@@ -1209,6 +1210,26 @@ encode_tiled_fn get_encode_tiled() {
   return fn;
 }
 
+// Warps per CTA for a batch of N trajectories: the smallest count that still fits the batch into one wave of
+// `ctas_per_sm` CTAs per SM (so the warps spread over every SM and sub-partition), at most `max_warps`.
+// CDK_LW_WARPS=k forces k (experiments).
+int lw_warps_per_cta(long long N, int max_warps, int ctas_per_sm) {
+  static const int forced = []() {
+    const char* e = getenv("CDK_LW_WARPS");
+    return e ? atoi(e) : 0;
+  }();
+  static const int num_sms = []() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+      n = 148;
+    return n;
+  }();
+  if (forced >= 1) return forced < max_warps ? forced : max_warps;
+  const long long nwarps = (N + 31) / 32, slots = (long long)num_sms * ctas_per_sm;
+  const long long w = (nwarps + slots - 1) / slots;
+  return (int)(w < 1 ? 1 : (w > max_warps ? max_warps : w));
+}
+
 // Build the four output tensor maps.  Returns false when the TMA path does not apply (fp32, odd K, unaligned pointers,
 // CDK_EKF_TMA=0): the kernel then uses the cooperative-copy flush.
 template <typename T>
@@ -1250,22 +1271,27 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
   if (a.d.N == 0) return CDK_OK;
-  // 14 warps in ONE CTA per SM (drift parameters in registers), or -- CDK_LW_WPC=7, and always when every lane carries
-  // its own parameter block in shared memory -- two CTAs of 7 warps
+  // Kernel variant: 14 = ONE CTA per SM of up to 14 warps (drift parameters in registers), or -- CDK_LW_WPC=7, and always
+  // when every lane carries its own parameter block in shared memory -- two CTAs per SM of up to 7 warps.
   static const int wpc_env = []() {
     const char* e = getenv("CDK_LW_WPC");
     return e && atoi(e) == 7 ? 7 : 14;
   }();
   const int warp_bytes = (int)((sizeof(SW) + sizeof(T) * NPAR * (par_batched ? 32 : 1) + 127) & ~size_t(127));
   const int wpc = (size_t)warp_bytes * wpc_env > 227 * 1024 ? 7 : wpc_env;
-  const size_t smw = (size_t)warp_bytes * wpc;
-  const long long wblocks = (a.d.N + 32 * wpc - 1) / (32 * wpc);
+  // Occupancy-aware geometry: a trajectory is a serial chain of K steps, so what matters for a batch smaller than one
+  // full wave (148 SMs x 14 warps x 32 = 66,304 trajectories) is that its ceil(N / 32) warps spread over ALL SMs and all
+  // four sub-partitions of each -- N / 8 = 8,192 trajectories (the 8-GPU shard of BASELINE config 3) are 256 warps, i.e.
+  // 128 CTAs of 2 warps instead of 19 CTAs of 14.  Warps never synchronise with each other, so the kernel is the same.
+  const int warps = lw_warps_per_cta(a.d.N, wpc, wpc == 7 ? 2 : 1);
+  const size_t smw = (size_t)warp_bytes * warps;
+  const long long wblocks = (a.d.N + 32 * warps - 1) / (32 * warps);
   if (wblocks > 2147483647LL) return CDK_E_SIZE;
   V5Maps maps;
   make_maps<T>(a, NX, 32, maps);
   auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7> : ekf_small_lw<T, Drift, NY, SOLVER, 14>;
-  if (smw > 48 * 1024) {
-    if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw) != cudaSuccess)
+  if ((size_t)warp_bytes * wpc > 48 * 1024) {
+    if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)warp_bytes * wpc)) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
   }
   static const int token_env = []() {  // experiment, default off (see the kernel)
@@ -1273,7 +1299,7 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
     return e ? atoi(e) : 0;
   }();
   const int use_token = wpc == 14 ? token_env : 0;  // with two CTAs per SM the lock would have to span CTAs
-  kw<<<(unsigned)wblocks, 32 * wpc, smw, s>>>(a, maps, warp_bytes, use_token);
+  kw<<<(unsigned)wblocks, 32 * warps, smw, s>>>(a, maps, warp_bytes, use_token);
   note_launch();
   return check_launch("ekf_small_lw");
 }
@@ -1303,17 +1329,19 @@ template <typename T, class Drift, int SOLVER>
 int launch_eks_one(const KArgs<T>& a, cudaStream_t s) {
   constexpr int NX = Drift::NX;
   using S = EKSmem<T, NX>;
-  const long long blocks = (a.d.N + 32 * 14 - 1) / (32 * 14);
-  if (blocks == 0) return CDK_OK;
+  if (a.d.N == 0) return CDK_OK;
+  const int warps = lw_warps_per_cta(a.d.N, 14, 1);  // same occupancy-aware geometry as the filter
+  const long long blocks = (a.d.N + 32 * warps - 1) / (32 * warps);
   if (blocks > 2147483647LL) return CDK_E_SIZE;
   V5Maps maps;
   const int slots[4] = {CDK_OUT_SM, CDK_OUT_SP, -1, -1};
   make_maps<T>(a, NX, 32, maps, slots);
-  const size_t smem = sizeof(S) * 14;
+  const size_t smem = sizeof(S) * warps;
   auto kern = eks_small_lw<T, Drift, SOLVER>;
-  if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  if (sizeof(S) * 14 > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(S) * 14)) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(eks_small_lw)");
-  kern<<<(unsigned)blocks, 32 * 14, smem, s>>>(a, maps);
+  kern<<<(unsigned)blocks, 32 * warps, smem, s>>>(a, maps);
   note_launch();
   return check_launch("eks_small_lw");
 }

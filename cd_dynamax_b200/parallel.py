@@ -60,3 +60,67 @@ def sharded_marginal_log_prob(filter_fn: Callable, emissions, t_emissions, input
     else:
         total = ll.to(torch.float64).sum().reshape(1)
     return allreduce_loglik(total, group)[0]
+
+
+# ---- cdk_ll_allreduce with a raw ncclComm_t (hosts that do not use torch.distributed: the JAX process of INTEGRATION.md) --
+class RawNcclComm:
+    """An `ncclComm_t` created directly on libnccl (the copy torch bundles is already in the process), i.e. the kind of
+    communicator a non-torch host hands to `cdk_ll_allreduce` (include/cdk.h).  The 128-byte ncclUniqueId of rank 0 has to
+    reach the other ranks out of band: pass `unique_id` (bytes), or leave it None to have it broadcast through an
+    initialised torch.distributed group.  One communicator per process / GPU."""
+
+    def __init__(self, rank: int, world_size: int, device=None, unique_id: Optional[bytes] = None, group=None):
+        import ctypes
+
+        class _UniqueId(ctypes.Structure):
+            _fields_ = [("internal", ctypes.c_char * 128)]
+
+        self._nccl = ctypes.CDLL("libnccl.so.2")
+        if device is not None:
+            torch.cuda.set_device(device)
+        uid = _UniqueId()
+        if unique_id is None:
+            if rank == 0:
+                rc = self._nccl.ncclGetUniqueId(ctypes.byref(uid))
+                if rc != 0:
+                    raise RuntimeError(f"ncclGetUniqueId failed ({rc})")
+            if world_size > 1:
+                if not (dist.is_available() and dist.is_initialized()):
+                    raise ValueError("world_size > 1 needs unique_id bytes or an initialised torch.distributed group")
+                box = [bytes(uid) if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0, group=group)
+                ctypes.memmove(ctypes.byref(uid), box[0], 128)
+        else:
+            ctypes.memmove(ctypes.byref(uid), unique_id, 128)
+        self.unique_id = bytes(uid)
+        self._comm = ctypes.c_void_p()
+        self._nccl.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _UniqueId, ctypes.c_int]
+        rc = self._nccl.ncclCommInitRank(ctypes.byref(self._comm), int(world_size), uid, int(rank))
+        if rc != 0:
+            raise RuntimeError(f"ncclCommInitRank failed ({rc})")
+        self.rank, self.world_size = rank, world_size
+
+    @property
+    def handle(self) -> int:
+        if self._comm is None:
+            raise RuntimeError("communicator already destroyed")
+        return self._comm.value
+
+    def destroy(self):
+        if self._comm is not None and self._comm.value:
+            self._nccl.ncclCommDestroy(self._comm)
+        self._comm = None
+
+
+def allreduce_loglik_nccl(local_sum: torch.Tensor, comm: RawNcclComm) -> torch.Tensor:
+    """In-place sum of one float64 device value over the ranks of a raw NCCL communicator through the C ABI's
+    `cdk_ll_allreduce` (enqueued on the current stream; no host synchronisation)."""
+    import ctypes
+
+    from . import _lib as L
+    if local_sum.dtype != torch.float64 or local_sum.numel() != 1 or not local_sum.is_cuda:
+        raise ValueError("allreduce_loglik_nccl expects one float64 value on the GPU")
+    stream = torch.cuda.current_stream(local_sum.device).cuda_stream
+    L.check(L.lib().cdk_ll_allreduce(ctypes.c_void_p(comm.handle), ctypes.c_void_p(local_sum.data_ptr()),
+                                     ctypes.c_void_p(stream)), "cdk_ll_allreduce")
+    return local_sum

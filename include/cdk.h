@@ -188,6 +188,13 @@ typedef struct cdk_xla_opaque {
   cdk_desc desc;
 } cdk_xla_opaque;
 void cdk_xla_custom_call(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len);
+/* The same target with XLA's status-returning signature (CustomCallApiVersion API_VERSION_STATUS_RETURNING; register with
+ * api_version=1 in jax 0.4.13's xla_client).  A non-zero CDK_E_* code from descriptor validation or the launch is
+ * reported with XlaCustomCallStatusSetFailure(status, "cdk (<code>): <cdk_last_error()>"), resolved from the calling XLA
+ * runtime at run time, so a rejected request fails the XLA executable instead of passing silently.  `status` may be NULL. */
+void cdk_xla_custom_call_status(cdk_stream_t stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+/* Return code of the last cdk_xla_custom_call* on this thread (the legacy signature has no way to report it). */
+int cdk_xla_last_rc(void);
 
 /* FP64/FP32 FMA-pipe probe used by bench.py for the roofline denominator: runs `iters` dependent-chain-free FMAs per
  * thread on `blocks` x 256 threads and writes one value per thread to sink (so the work is not eliminated).

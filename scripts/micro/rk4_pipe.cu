@@ -8,7 +8,7 @@
 #include "../../cd_dynamax_b200/csrc/cdk_small.cu"
 
 namespace cdk {
-__global__ void rk4_probe(double* sink, long long* cyc, int iters, double dt) {
+__global__ void rk4_probe(double* sink, long long* cyc, int iters, double dt, unsigned lane_mask = 0xffffffffu) {
   St<double, 3> s;
   s.m[0] = 1.0 + 1e-3 * threadIdx.x; s.m[1] = 1.0; s.m[2] = 20.0;
   for (int i = 0; i < 6; ++i) s.P[i] = (i == 0 || i == 3 || i == 5) ? 1.0 : 0.0;
@@ -16,8 +16,13 @@ __global__ void rk4_probe(double* sink, long long* cyc, int iters, double dt) {
   double lql[6] = {1, 0, 0, 1, 0, 1};
   __syncthreads();
   long long t0 = clock64();
+  // lane_mask: does the FP64 pipe spend less time on a warp instruction when only half (a quarter) of the lanes are
+  // active?  (It does not -- profiles/r02_micro_rk4_lanes.jsonl -- so spreading a small batch over more, emptier warps
+  // buys nothing: the cost of this arithmetic is per WARP instruction.)
+  if ((lane_mask >> (threadIdx.x & 31)) & 1u) {
 #pragma unroll 1
-  for (int it = 0; it < iters; ++it) rk_step<double, DriftL63, CDK_RK4>(th, lql, s, dt);
+    for (int it = 0; it < iters; ++it) rk_step<double, DriftL63, CDK_RK4>(th, lql, s, dt);
+  }
   long long t1 = clock64();
   double acc = 0;
   for (int i = 0; i < 3; ++i) acc += s.m[i];
@@ -44,6 +49,17 @@ int main() {
     const double per_smsp = w < 4 ? 1 : (w + 3) / 4;  // warps on the fullest sub-partition
     printf("{\"warps_per_sm\": %d, \"cycles_per_substep_per_warp\": %.1f, \"cycles_per_substep_fullest_smsp\": %.1f}\n", w,
            m / iters, m / iters / per_smsp);
+  }
+  struct { const char* name; unsigned mask; } masks[] = {{"32 lanes", 0xffffffffu}, {"lanes 0-15", 0x0000ffffu},
+                                                         {"even lanes", 0x55555555u}, {"lanes 0-7", 0x000000ffu}};
+  for (auto& mk : masks) {
+    for (int rep = 0; rep < 2; ++rep) cdk::rk4_probe<<<148, 32 * 4>>>(sink, cyc, iters, 1e-4, mk.mask);
+    cudaDeviceSynchronize();
+    long long h[148];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    double m = 0;
+    for (int i = 0; i < 148; ++i) m += h[i];
+    printf("{\"active\": \"%s\", \"warps_per_sm\": 4, \"cycles_per_substep_per_warp\": %.1f}\n", mk.name, m / 148 / iters);
   }
   return 0;
 }

@@ -25,3 +25,17 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity errors of this run (tests.helpers.record) -> gpurun_out/parity_errors.json (merged back from the box)."""
+    try:
+        import json
+        from tests import helpers
+        if helpers._RECORD:
+            out = os.path.join(ROOT, "gpurun_out")
+            os.makedirs(out, exist_ok=True)
+            with open(os.path.join(out, "parity_errors.json"), "w") as f:
+                json.dump(dict(sorted(helpers._RECORD.items())), f, indent=1)
+    except Exception:
+        pass

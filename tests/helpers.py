@@ -84,6 +84,50 @@ def max_rel_err(a, b, floor=1e-12):
     return float(np.max(np.where(np.isnan(err), np.inf, err)))
 
 
+def elem_err(a, b, core_ndim=1, floor=1e-6):
+    """The parity gate for filtered / predicted moments: ELEMENT-WISE relative error |a - b| / max(|b|, floor * s), where
+    s is the max-norm of the entry's own moment (the last `core_ndim` axes: one mean vector, one covariance matrix), so
+    a small entry is compared at its own magnitude and not at the scale of the whole [N, K, ...] array.
+
+    Why the floor is 1e-6 of the moment's own norm and not SURVEY 8(d)'s 1e-12 of the array scale: means and off-diagonal
+    covariances of a chaotic system cross zero, and an entry that happens to be 1e-7 of its vector's norm carries the
+    rounding error of the O(1) terms it is the difference of.  Two CPU restatements of the SAME algorithm (NumPy oracle
+    vs C oracle, operations in a different order) differ by 1.2e-9 under the 1e-12 floor on BASELINE config 3 while
+    agreeing to 1.6e-14 of the scale and 1.3e-10 under this gate (tests/test_oracle_golden.py::
+    test_c_oracle_matches_numpy_oracle keeps those numbers), so the 1e-12 floor measures zero crossings, not parity."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    if a.size == 0:
+        return 0.0
+    ax = tuple(range(a.ndim - core_ndim, a.ndim))
+    with np.errstate(invalid="ignore"):
+        s = np.nanmax(np.abs(b), axis=ax, keepdims=True) if not np.isnan(b).all() else np.ones_like(b)
+    s = np.where(np.isfinite(s) & (s > 0), s, 1.0)
+    both_nan = np.isnan(a) & np.isnan(b)
+    err = np.abs(a - b) / np.maximum(np.abs(b), floor * s)
+    err = np.where(both_nan, 0.0, err)
+    return float(np.max(np.where(np.isnan(err), np.inf, err)))
+
+
+FIELD_CORE = {"filtered_means": 1, "predicted_means": 1, "smoothed_means": 1, "filtered_covariances": 2,
+              "predicted_covariances": 2, "smoothed_covariances": 2, "smoothed_cross_covariances": 2}
+
+
+def moment_err(post, ref, fld, prefix=""):
+    """elem_err of one result field (`post`: result tuple, `ref`: dict of oracle / golden arrays)."""
+    a = getattr(post, fld)
+    a = a.cpu().numpy() if hasattr(a, "cpu") else a
+    return elem_err(a, ref[prefix + fld], core_ndim=FIELD_CORE[fld])
+
+
+_RECORD = {}
+
+
+def record(name, value):
+    """Keep the measured parity errors of a GPU run (written to gpurun_out/parity_errors_*.json at session end)."""
+    _RECORD[name] = float(value)
+
+
 def scaled_err(a, b):
     """max |a-b| / max|b| -- error relative to the array's scale."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)

@@ -132,3 +132,53 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stderr)
+
+
+def test_xla_status_returning_adaptor_reports_failures(lib, tmp_path):
+    """cdk_xla_custom_call_status maps a non-zero CDK_E_* code to XlaCustomCallStatusSetFailure (SURVEY 8b "Errors").
+    The XLA runtime that owns that symbol is absent here, so a 10-line stand-in is compiled and loaded RTLD_GLOBAL; the
+    requests below are rejected by host-side validation before any CUDA call."""
+    import subprocess
+    from cd_dynamax_b200 import _lib
+    src = tmp_path / "xla_stub.c"
+    src.write_text(
+        "#include <string.h>\n#include <stddef.h>\n"
+        "typedef struct { int failed; char message[320]; } XlaCustomCallStatus;\n"
+        "void XlaCustomCallStatusSetFailure(XlaCustomCallStatus* s, const char* m, size_t n) {\n"
+        "  s->failed = 1; if (n > 319) n = 319; memcpy(s->message, m, n); s->message[n] = 0; }\n")
+    so = tmp_path / "libxla_stub.so"
+    subprocess.run(["gcc", "-shared", "-fPIC", "-o", str(so), str(src)], check=True)
+    ctypes.CDLL(str(so), mode=ctypes.RTLD_GLOBAL)
+
+    class Status(ctypes.Structure):
+        _fields_ = [("failed", ctypes.c_int), ("message", ctypes.c_char * 320)]
+
+    class Opaque(ctypes.Structure):
+        _fields_ = [("entry_point", ctypes.c_char * 32), ("desc", _lib.CdkDesc)]
+
+    bufs = (ctypes.c_void_p * (_lib.NUM_IN + _lib.NUM_OUT))()
+    op = Opaque()
+    op.entry_point = b"cdk_ekf_filter_f64"
+    op.desc = _lib.new_desc()
+    op.desc.N, op.desc.K, op.desc.n, op.desc.m, op.desc.solver = 4, 10, 3, 1, 99  # unknown solver
+    blob = ctypes.string_at(ctypes.byref(op), ctypes.sizeof(op))
+    st = Status()
+    lib.cdk_xla_custom_call_status(None, bufs, blob, len(blob), ctypes.byref(st))
+    assert st.failed == 1 and b"unknown solver" in st.message and b"(-3)" in st.message
+    assert lib.cdk_xla_last_rc() == -3
+    op.entry_point = b"cdk_no_such_entry"
+    blob = ctypes.string_at(ctypes.byref(op), ctypes.sizeof(op))
+    st = Status()
+    lib.cdk_xla_custom_call_status(None, bufs, blob, len(blob), ctypes.byref(st))
+    assert st.failed == 1 and b"unknown entry point" in st.message
+    # the legacy signature cannot report: the code is still retrievable; a too-short opaque is rejected, not read
+    lib.cdk_xla_custom_call(None, bufs, blob[:8], 8)
+    assert lib.cdk_xla_last_rc() == -2
+    # N = 0 is a valid no-op request
+    op.entry_point = b"cdk_ekf_filter_f64"
+    op.desc = _lib.new_desc()
+    op.desc.N, op.desc.K, op.desc.n, op.desc.m, op.desc.drift_id, op.desc.n_theta = 0, 10, 3, 1, 1, 3
+    blob = ctypes.string_at(ctypes.byref(op), ctypes.sizeof(op))
+    st = Status()
+    lib.cdk_xla_custom_call_status(None, bufs, blob, len(blob), ctypes.byref(st))
+    assert st.failed == 0 and lib.cdk_xla_last_rc() == 0

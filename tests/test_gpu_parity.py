@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import cd_oracle as o
-from tests.helpers import golden_cases, load_golden, make_drift, max_rel_err, scaled_err
+from tests.helpers import golden_cases, load_golden, make_drift, max_rel_err, moment_err, record, scaled_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-9
@@ -17,6 +17,15 @@ FIELDS = ["filtered_means", "filtered_covariances", "predicted_means", "predicte
 def api():
     import cd_dynamax_b200 as cd
     return cd
+
+
+def check_moments(post, ref, tag, prefix="", tol=TOL, fields=FIELDS):
+    """Filtered / predicted moments against the oracle or a golden case: the element-wise gate of tests/helpers.elem_err
+    (relative error of every entry, denominators floored at 1e-6 of the entry's own vector / matrix norm)."""
+    for fld in fields:
+        e = moment_err(post, ref, fld, prefix)
+        record(f"{tag}:{fld}", e)
+        assert e < tol, (tag, fld, e)
 
 
 def linear_params_api(g):
@@ -68,8 +77,7 @@ def test_kf_filter_and_smoothers_vs_reference_golden(name):
     u = g.get("u")
     f = cd.cdlgssm_filter(p, g["y"], g["t"][..., None], hp, u)
     assert max_rel_err(f.marginal_loglik, g["filt_marginal_loglik"]) < TOL
-    for fld in FIELDS:
-        assert scaled_err(getattr(f, fld), g["filt_" + fld]) < TOL, fld
+    check_moments(f, g, name, prefix="filt_")
     s1 = cd.cdlgssm_smoother(p, g["y"], g["t"][..., None], hp, u, smoother_type="cd_smoother_1")
     for fld in ("smoothed_means", "smoothed_covariances", "smoothed_cross_covariances"):
         assert scaled_err(getattr(s1, fld), g["s1_" + fld]) < 1e-8, fld
@@ -94,8 +102,7 @@ def test_ekf_and_eks_vs_reference_golden(name):
                            cov_rescaling=float(g["cov_rescaling"]), diffeqsolve_settings=settings_api(g))
     f = cd.cdnlgssm_filter(p, g["y"], g["t"][..., None], hp, num_iter=int(g["num_iter"]))
     assert max_rel_err(f.marginal_loglik, g["filt_marginal_loglik"]) < TOL
-    for fld in FIELDS:
-        assert scaled_err(getattr(f, fld), g["filt_" + fld]) < TOL, fld
+    check_moments(f, g, name, prefix="filt_")
     c = cd.cdnlgssm_filter(p, g["y"], g["t"][..., None], hp, num_iter=int(g["num_iter"]),
                            output_fields=["marginal_loglik"])
     assert c.filtered_means is None
@@ -114,8 +121,12 @@ def test_ukf_vs_reference_golden(name):
     hp = cd.UKFHyperParams(dt_final=float(g["dt_final"]), diffeqsolve_settings=settings_api(g))
     f = cd.cdnlgssm_filter(p, g["y"], g["t"][..., None], hp)
     assert max_rel_err(f.marginal_loglik, g["filt_marginal_loglik"]) < TOL
-    for fld in FIELDS:
-        assert scaled_err(getattr(f, fld), g["filt_" + fld]) < TOL, fld
+    check_moments(f, g, name, prefix="filt_")
+
+
+def _tag():
+    import os
+    return os.environ.get("PYTEST_CURRENT_TEST", "?").split("::")[-1].split(" ")[0]
 
 
 def c3_problem(N, K, seed=1237, dtype=np.float64):
@@ -142,8 +153,7 @@ def test_ekf_l63_fast_path_vs_oracle(solver, dt0):
                            H=g["H"], R=g["R"], d=g["d"])
     r = o.extended_kalman_filter(po, y, t, settings=o.SolverSettings(solver, dt0))
     assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < TOL
-    for fld in FIELDS:
-        assert scaled_err(getattr(f, fld), r[fld]) < TOL, fld
+    check_moments(f, r, _tag())
 
 
 @pytest.mark.parametrize("N,K", [(1, 1), (3, 7), (225, 33), (500, 64)])
@@ -161,8 +171,7 @@ def test_ekf_l63_fast_path_ragged_shapes(N, K):
                            H=g["H"], R=g["R"], d=g["d"])
     r = o.extended_kalman_filter(po, y, t, settings=o.SolverSettings("rk4", 0.0025))
     assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < TOL
-    for fld in FIELDS:
-        assert scaled_err(getattr(f, fld), r[fld]) < TOL, fld
+    check_moments(f, r, _tag())
     # a subset of outputs (NULL output pointers) must not change the others
     f2 = cd.cdnlgssm_filter(p, y, t[..., None], hp, output_fields=["predicted_covariances"])
     assert f2.filtered_means is None and np.array_equal(f2.predicted_covariances, f.predicted_covariances)
@@ -402,10 +411,10 @@ def test_kf_warp_filter_and_smoother_vs_oracle(N, K, n, m, solver, batched_model
     po = o.LinearParams(m0=g["m0"], P0=g["P0"], F=F, L=Lm, Qc=g["Qc"], H=g["H"], R=g["R"], b=g["b"], d=g["d"])
     r = o.cdlgssm_smoother(po, y, t, dt_final=0.03, settings=o.SolverSettings(solver, 0.01))
     assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < TOL
-    for fld in FIELDS:
-        assert scaled_err(getattr(f, fld), r[fld]) < TOL, fld
+    check_moments(f, r, _tag())
     for fld in ("smoothed_means", "smoothed_covariances", "smoothed_cross_covariances"):
         if r[fld].size:
+            record(f"{_tag()}:{fld}", moment_err(s, r, fld))
             assert scaled_err(getattr(s, fld), r[fld]) < 1e-8, fld
     assert s.smoothed_cross_covariances.shape == (N, K - 1, n, n)
 
@@ -426,9 +435,9 @@ def test_eks_l63_fast_path_vs_oracle(N, K, solver, dt0):
                            H=g["H"], R=g["R"], d=g["d"])
     r = o.extended_kalman_smoother(po, y, t, dt_final=0.004, settings=o.SolverSettings(solver, dt0))
     assert max_rel_err(s.marginal_loglik, r["marginal_loglik"]) < TOL
-    for fld in ("filtered_means", "filtered_covariances"):
-        assert scaled_err(getattr(s, fld), r[fld]) < TOL, fld
+    check_moments(s, r, _tag(), fields=("filtered_means", "filtered_covariances"))
     for fld in ("smoothed_means", "smoothed_covariances"):
+        record(f"{_tag()}:{fld}", moment_err(s, r, fld))
         assert scaled_err(getattr(s, fld), r[fld]) < 1e-8, fld
     # the last smoothed step is the filtered one, verbatim
     assert np.array_equal(s.smoothed_means[:, -1], s.filtered_means[:, -1])

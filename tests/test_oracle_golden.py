@@ -91,3 +91,43 @@ def test_enkf_oracle_matches_kalman_filter_in_distribution():
         en = o.ensemble_kalman_filter(nl, y, t, E=E, seed=5, settings=o.SolverSettings("euler", 0.0025))
         errs.append(np.max(np.abs(en["filtered_means"] - kf["filtered_means"])))
     assert errs[1] < 0.08 and errs[1] < errs[0]
+
+
+def test_c_oracle_matches_numpy_oracle():
+    """The C restatement (oracle/cd_oracle_c.c: the CPU baseline of bench.py and the checker of the K = 1,000 GPU parity
+    tests) against the NumPy oracle that the golden vectors pin: same algorithm, operations in a different order.
+    Also the evidence for the element-wise gate's floor (tests/helpers.elem_err): under SURVEY 8(d)'s 1e-12-of-scale floor
+    two CPU restatements of one algorithm already disagree at ~1e-9 on zero-crossing entries while agreeing to ~1e-14
+    of the scale."""
+    from oracle import cpu_baseline as cb
+    from tests.helpers import elem_err, scaled_err
+    rng = np.random.default_rng(1237)
+    N, K = 48, 400
+    gaps = 0.01 * rng.uniform(0.5, 1.5, size=(N, K))
+    gaps[:, 0] = 0.0
+    t = np.cumsum(gaps, axis=1)
+    y = 8.0 * rng.standard_normal((N, K, 1))
+    po = o.NonlinearParams(m0=np.zeros(3), P0=5 * np.eye(3), drift=o.Lorenz63Drift(10.0, 28.0, 8.0 / 3.0), L=np.eye(3),
+                           Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))
+    r = o.extended_kalman_filter(po, y, t, settings=o.SolverSettings("rk4", 0.0025))
+    c = cb.filter_c("ekf", y, t, po.m0, po.P0, np.array([10.0, 28.0, 8.0 / 3.0]), po.L, po.Qc, po.H, po.d, po.R,
+                    drift_id=1, solver="rk4", dt0=0.0025)
+    assert max_rel_err(c["marginal_loglik"], r["marginal_loglik"]) < 1e-12
+    for fld, core in (("filtered_means", 1), ("filtered_covariances", 2), ("predicted_means", 1), ("predicted_covariances", 2)):
+        assert elem_err(c[fld], r[fld], core) < 1e-9, fld
+        assert scaled_err(c[fld], r[fld]) < 1e-12, fld
+    # linear CD-KF, n = 16, m = 4 (BASELINE config 2 model), RK4 and the reference-default Dopri5
+    n, m, N, K = 16, 4, 6, 60
+    F = -0.5 * np.eye(n) + 0.3 * rng.standard_normal((n, n)) / np.sqrt(n)
+    lp = o.LinearParams(m0=np.zeros(n), P0=np.eye(n), F=F, L=np.eye(n), Qc=0.1 * np.eye(n), H=np.eye(n)[:m],
+                        R=0.1 * np.eye(m), b=0.05 * rng.standard_normal(n), d=np.zeros(m))
+    gaps = 0.04 * rng.uniform(0.5, 1.5, size=(N, K))
+    gaps[:, 0] = 0.0
+    t = np.cumsum(gaps, axis=1)
+    y = rng.standard_normal((N, K, m))
+    for solver in ("rk4", "dopri5"):
+        r = o.cdlgssm_filter(lp, y, t, settings=o.SolverSettings(solver, 0.01))
+        c = cb.filter_c("kf", y, t, lp.m0, lp.P0, F, lp.L, lp.Qc, lp.H, lp.d, lp.R, bias=lp.b, solver=solver, dt0=0.01)
+        assert max_rel_err(c["marginal_loglik"], r["marginal_loglik"]) < 1e-12
+        for fld, core in (("filtered_means", 1), ("filtered_covariances", 2), ("predicted_means", 1), ("predicted_covariances", 2)):
+            assert elem_err(c[fld], r[fld], core) < 1e-9, (solver, fld)
