@@ -6,11 +6,15 @@
         bench.py --gpus N --steps K --warmup W
 
 Workload (BASELINE.json configs[2], the configuration the metric is quoted on): CD-EKF on stochastic Lorenz-63,
-d_x = 3, d_y = 1 (observe x), N = 65,536 trajectories PER GPU (weak scaling: trajectories are independent and shard
-with no data-path collective), K = 1,000 irregular observation times, classical RK4 moment ODE with dt0 = mean gap / 4.
-One "step" = one filter pass over the whole batch (update + predict for all N x K observation-steps, writing the four
-moment arrays the reference returns by default) followed by the sum of the per-trajectory log-likelihoods and, at
-N > 1 GPUs, one all-reduce of that scalar.
+d_x = 3, d_y = 1 (observe x), N = 65,536 trajectories, K = 1,000 irregular observation times, classical RK4 moment ODE
+with dt0 = mean gap / 4.  One "step" = one filter pass over the whole batch (update + predict for all N x K
+observation-steps, writing the four moment arrays the reference returns by default) followed by the sum of the
+per-trajectory log-likelihoods and, at N > 1 GPUs, one all-reduce of that scalar (cdk_ll_allreduce on a raw NCCL
+communicator).  Trajectories are independent and shard with no data-path collective.
+
+`--scaling strong` (default): the north star's FIXED N = 65,536 is split over the ranks (parallel.shard_bounds), so the
+            value at 8 GPUs is the 8-GPU time of the SAME job; `--scaling weak`: 65,536 trajectories PER GPU.  At N > 1 the
+            other mode is measured too and reported beside the headline (`weak_scaling` / `strong_scaling` object).
 
 `value`   : inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`     : the same metric through the public drop-in API with HOST (pinned) buffers: every step copies emissions and
@@ -54,7 +58,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-traj", type=int, default=CFG["N"], help="trajectories per GPU (default = BASELINE config 3)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --n-traj is the TOTAL batch, split over the GPUs (north star); weak: --n-traj per GPU")
+    ap.add_argument("--n-traj", type=int, default=CFG["N"], help="trajectories (default = BASELINE config 3: 65,536)")
+    ap.add_argument("--no-other-mode", action="store_true", help="at N > 1 GPUs skip the second (other scaling mode) measurement")
     ap.add_argument("--k-obs", type=int, default=CFG["K"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     ap.add_argument("--cpu-sample-traj", type=int, default=0, help="trajectories in the CPU sample (0 = auto)")

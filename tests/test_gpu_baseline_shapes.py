@@ -8,8 +8,9 @@
   C2  CD-KF n = 16, m = 4, K = 500 (filter, both smoother types);
 and one stated-bound test for every fp32 entry point of include/cdk.h.
 
-Gates: log-likelihood rel 1e-9; filtered / predicted moments element-wise 1e-9 (tests/helpers.elem_err); smoothed
-moments and the EnKF 1e-8 (see test_gpu_parity.py); fp32 bounds are written in each test."""
+Gates: log-likelihood rel 1e-9; filtered / predicted moments: SURVEY 8(d)'s element-wise gate at 1e-9 and 1e-10 of every
+moment's own norm (tests/helpers.gate_err, moment_norm_err); smoothed moments and the EnKF 1e-8 (see test_gpu_parity.py);
+fp32 bounds are written in each test, about 10x the error measured on B200 (gpurun_out/parity_errors.json)."""
 import ctypes
 
 import numpy as np
@@ -116,7 +117,7 @@ def test_c5_enkf_l96_e1024_cluster4_vs_oracle(solver):
     record(f"c5_enkf_e1024_{solver}:marginal_loglik", e)
     assert e < 1e-8
     for fld in FIELDS:
-        record(f"c5_enkf_e1024_{solver}:{fld}", moment_err(f, r, fld))
+        record(f"c5_enkf_e1024_{solver}:{fld}:own_norm", moment_err(f, r, fld)[1])
         assert scaled_err(getattr(f, fld), r[fld]) < 1e-8, fld
 
 
@@ -154,7 +155,7 @@ def test_c2_kf_n16_k500_vs_oracle(solver, dt0):
         s = cd.cdlgssm_smoother(linear_params_api(g), y[:ns], t[:ns, :, None], hp, smoother_type=stype)
         rs = o.cdlgssm_smoother(po, y[:ns], t[:ns], settings=o.SolverSettings(solver, dt0), smoother_type=int(stype[-1]))
         for fld in ("smoothed_means", "smoothed_covariances"):
-            record(f"c2_kf_k500_{solver}_{stype}:{fld}", moment_err(s, rs, fld))
+            record(f"c2_kf_k500_{solver}_{stype}:{fld}:own_norm", moment_err(s, rs, fld)[1])
             assert scaled_err(getattr(s, fld), rs[fld]) < 1e-8, (stype, fld)
 
 
