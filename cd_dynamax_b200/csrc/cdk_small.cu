@@ -130,6 +130,21 @@ __device__ __forceinline__ void rk_step(const T* th, const T* lql, St<T, Drift::
   for (int e = 0; e < NP; ++e) y.P[e] = fma(w, ksum.P[e], y.P[e]);
 }
 
+// 1 / x for a positive, normal x without the IEEE slow path: MUFU.RCP64H seed (rcp.approx.ftz.f64, ~20 bits) and two
+// Newton steps (error e -> e^2: below 2^-53 after the second).  The compiler's own double division carries two
+// data-dependent branches and a call to a fix-up routine per division; the scalar-emission update needs two reciprocals
+// per observation, of innovation variances that are positive and nowhere near the ends of the exponent range (anything
+// else -- zero, negative, NaN -- gives inf / NaN here and the trajectory is flagged, as in the reference).
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float x) { return 1.0f / x; }
+
 // Measurement update + log-likelihood increment (inference_ekf.py:285-289, :153-199; psd_solve utils.py:202-207).
 // sh: H[NY*NX], d[NY], R[NY*NY] in shared memory.
 template <typename T, int NX, int NY>
@@ -417,6 +432,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   volatile unsigned* const tok = &lw_token[hw_warp & 3][0];
   const long long traj = traj0 + lane;
   const bool live = traj < N;
+  // A lane past the end of the batch (ragged last warp) shadows the last trajectory: it computes, never stores (its
+  // staging rows fall outside the tensor map and TMA clips them; the cooperative flush copies `nlive` rows).  The step
+  // body therefore has no per-lane `live` branch at all.
+  const long long trc = live ? traj : N - 1;
   const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
@@ -426,9 +445,9 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   const bool use_tma = sizeof(T) == 8 && maps.use_tma != 0 && any_out;
   unsigned long long* const trace = g_lw_trace;
   const unsigned long long t_entry = trace ? globaltimer() : 0ull;
-  if ((par_batched && live) || (!par_batched && lane == 0)) {
+  if (par_batched || lane == 0) {
     T* par = par_batched ? parbase + lane * NPAR : parbase;
-    const long long tj = par_batched ? traj : 0;
+    const long long tj = par_batched ? trc : 0;
     const T* th = a.in[CDK_IN_F] + tj * a.in_stride[CDK_IN_F];
     const T* Lm = a.in[CDK_IN_L] + tj * a.in_stride[CDK_IN_L];
     const T* Qc = a.in[CDK_IN_QC] + tj * a.in_stride[CDK_IN_QC];
@@ -450,10 +469,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
     for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
   }
-  const T* __restrict__ Yg = a.in[CDK_IN_Y] + (live ? traj : 0) * a.in_stride[CDK_IN_Y];
-  const T* __restrict__ Tg = a.in[CDK_IN_T] + (live ? traj : 0) * a.in_stride[CDK_IN_T];
+  const T* __restrict__ Yg = a.in[CDK_IN_Y] + trc * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Tg = a.in[CDK_IN_T] + trc * a.in_stride[CDK_IN_T];
   auto prefetch = [&](int kk) {
-    if (live && kk < K) {
+    if (kk < K) {
 #pragma unroll
       for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (LW_RING - 1)][c][lane], Yg + (long long)kk * NY + c);
       cp_async_elem(&sm.inT[kk & (LW_RING - 1)][lane], Tg + kk);
@@ -464,13 +483,9 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   prefetch(1);
   prefetch(2);
   St<T, NX> s;
-#pragma unroll
-  for (int i = 0; i < NX; ++i) s.m[i] = T(0);
-#pragma unroll
-  for (int i = 0; i < NP; ++i) s.P[i] = T(0);
-  if (live) {
-    const T* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
-    const T* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
+  {
+    const T* m0 = a.in[CDK_IN_M0] + trc * a.in_stride[CDK_IN_M0];
+    const T* P0 = a.in[CDK_IN_P0] + trc * a.in_stride[CDK_IN_P0];
 #pragma unroll
     for (int i = 0; i < NX; ++i) s.m[i] = m0[i];
 #pragma unroll
@@ -491,13 +506,28 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   const T* Hs = par + NTH + NP;
   const T* ds = Hs + NY * NX;
   const T* Rs = ds + NY;
+  // scalar emission, WPC == 14: the emission row, bias and variance live in registers too (the step body then reads
+  // shared memory only for the observation and the two time stamps)
+  constexpr bool EM_REGS = NY == 1 && WPC == 14;
+  T Hr[NX], dr = T(0), Rr = T(0);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) Hr[i] = EM_REGS ? Hs[i] : T(0);
+  if (EM_REGS) {
+    dr = ds[0];
+    Rr = Rs[0];
+  }
   const T dt0 = T(a.d.dt0);
   const T dtf = T(a.d.dt_final);
   const T tol = clip_tol<T>();
   const int max_steps = a.d.max_steps;
   const int num_iter = a.d.num_iter;
   T* __restrict__ LLC = static_cast<T*>(a.out[CDK_OUT_LLCUM]);
+  // Scalar emission, one update per observation, no cumulative output: the LEAN update.  sum_k log S_k is kept as
+  // (esum, sprod) with prod_k S_k = sprod * 2^esum, sprod renormalised into [1, 2) by integer operations on its exponent
+  // field every step, so the whole pass takes ONE log per trajectory (at the end); r^2 / S and the gain use fast_rcp.
+  const bool lean = NY == 1 && !LLC && num_iter == 1;
   T ll = T(0), sprod = T(1);
+  int esum = 0;
   bool sbad = false;
   int status = 0;
   auto tma_pair = [&](int first, int k0) {  // lane 0: store arrays {first, first + 1} of the block starting at step k0
@@ -512,7 +542,9 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
   };
-  // one RK step with the diffrax stepping rule (tnext = tprev + dt0, clipped to t1 within tol)
+  // one RK step with the diffrax stepping rule (tnext = tprev + dt0, clipped to t1 within tol).  A lane whose gap is
+  // already complete has tnext == tprev == t1: it takes a step of length 0, which leaves its state bit-identical
+  // (y + 0 * ksum), so the substep loop needs no per-lane predication -- its trip count is warp-uniform (vote).
   auto substep = [&](T& tprev, T& tnext, const T t1) {
     rk_step<T, Drift, SOLVER>(th, lql, s, tnext - tprev);
     tprev = tnext;
@@ -542,39 +574,72 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   auto step = [&](auto rowc, const int k) {
     constexpr int row = decltype(rowc)::value;
     asm volatile("cp.async.wait_group 1;" ::: "memory");  // own loads of steps <= k+1 have landed
-    T tprev = T(0), t1 = T(0);
-    if (live) {
-      T y[NY];
+    T y[NY];
 #pragma unroll
-      for (int c = 0; c < NY; ++c) y[c] = sm.inY[k & (LW_RING - 1)][c][lane];
-      tprev = sm.inT[k & (LW_RING - 1)][lane];
-      t1 = k + 1 < K ? sm.inT[(k + 1) & (LW_RING - 1)][lane] : tprev + dtf;
-      if (NY == 1 && !LLC) {
-        // sum_k log S_k = log prod_k S_k, folded every 8 steps (factors outside [1e-8, 1e8] take the direct log); a
-        // non-positive S (non-PD covariance) must still poison the log-likelihood as log() would.
-        T Sk;
-        ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter, &Sk);
-        if (!(Sk > T(0))) sbad = true;
-        if (Sk > T(1e-8) && Sk < T(1e8)) {
-          sprod *= Sk;  // at most 8 (fp32: 4) factors in [1e-8, 1e8]: no overflow / underflow
-        } else {
-          ll -= T(0.5) * log(Sk);
+    for (int c = 0; c < NY; ++c) y[c] = sm.inY[k & (LW_RING - 1)][c][lane];
+    T tprev = sm.inT[k & (LW_RING - 1)][lane];
+    const T t1 = k + 1 < K ? sm.inT[(k + 1) & (LW_RING - 1)][lane] : tprev + dtf;
+    if constexpr (NY == 1) {
+      if (lean) {
+        // log N(y; H m + d, S) = -r^2 / (2 S) - log(S) / 2 - log(2 pi) / 2,  K = P H^T / (S + 1e-9),  P -= K S K^T
+        // (inference_ekf.py:285-289, :153-199; psd_solve boost utils.py:204); the constant is added after the loop
+        const T* Hp = EM_REGS ? Hr : Hs;
+        const T dd = EM_REGS ? dr : ds[0], RR = EM_REGS ? Rr : Rs[0];
+        T HP[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) {
+          T acc = Hp[0] * s.P[pidx<NX>(0, j)];
+#pragma unroll
+          for (int q = 1; q < NX; ++q) acc = fma(Hp[q], s.P[pidx<NX>(q, j)], acc);
+          HP[j] = acc;
         }
-        if ((k & (sizeof(T) == 8 ? 7 : 3)) == (sizeof(T) == 8 ? 7 : 3)) {
-          ll -= T(0.5) * log(sprod);
-          sprod = T(1);
+        T Sk = RR, hm = dd;
+#pragma unroll
+        for (int q = 0; q < NX; ++q) {
+          Sk = fma(HP[q], Hp[q], Sk);
+          hm = fma(Hp[q], s.m[q], hm);
+        }
+        const T r = y[0] - hm;
+        const T iS = fast_rcp(Sk), rb = fast_rcp(Sk + T(1e-9));
+        const T rr = r * r;
+        T quad = rr * iS;
+        quad = fma(fma(-Sk, quad, rr), iS, quad);  // one residual correction: r^2 / S to the last bit or two
+        ll = fma(T(-0.5), quad, ll);
+        if (!(Sk > T(0)) || !(Sk < T(INFINITY))) sbad = true;  // log() of a non-PD innovation variance is NaN
+        sprod *= Sk;
+        if constexpr (sizeof(T) == 8) {
+          const int hi = __double2hiint(sprod);
+          esum += (hi >> 20) - 1023;
+          sprod = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(sprod));
+        } else {
+          const int bits = __float_as_int(sprod);
+          esum += (bits >> 23) - 127;
+          sprod = __int_as_float((bits & 0x007fffff) | 0x3f800000);
+        }
+        T Kt[NX];
+#pragma unroll
+        for (int j = 0; j < NX; ++j) Kt[j] = HP[j] * rb;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          const T ks = Kt[i] * Sk;
+#pragma unroll
+          for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = fma(-ks, Kt[j], s.P[pidx<NX>(i, j)]);
+          s.m[i] = fma(Kt[i], r, s.m[i]);
         }
       } else {
         ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
-        if (LLC) LLC[traj * (long long)K + k] = ll;
+        if (LLC && live) LLC[traj * (long long)K + k] = ll;
       }
+    } else {
+      ll += ekf_update<T, NX, NY>(Hs, ds, Rs, s, y, num_iter);
+      if (LLC && live) LLC[traj * (long long)K + k] = ll;
     }
     prefetch(k + 3);
     if (use_tma && row == 0 && k > 0) {  // the FM/FP store of the previous block was issued ~6 substeps ago
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
-    if (live && any_out) stage(rowc, &sm.fm[lane][0][0], &sm.fp[lane][0][0]);
+    if (any_out) stage(rowc, &sm.fm[lane][0][0], &sm.fp[lane][0][0]);
     if (use_tma && row == 1) {  // the filtered rows of this block are complete: store them while the gap is integrated
       __syncwarp();
       if (lane == 0) tma_pair(0, k - 1);
@@ -586,10 +651,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
       while ((int)(ticket - tok[1]) >= use_token) {  // use_token = permits: warps inside the substep loop at a time
       }
     }
-    if (live) {
+    {
       T tnext = fmin(tprev + dt0, t1);
       int nsteps = 0;
-      while (tprev < t1 && nsteps < max_steps) {
+      while (__any_sync(0xffffffffu, tprev < t1) && nsteps < max_steps) {
         substep(tprev, tnext, t1);
         ++nsteps;
       }
@@ -603,7 +668,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
-    if (live && any_out) stage(rowc, &sm.pm[lane][0][0], &sm.pp[lane][0][0]);
+    if (any_out) stage(rowc, &sm.pm[lane][0][0], &sm.pp[lane][0][0]);
     if (any_out && (row == 1 || k == K - 1)) {
       __syncwarp();
       if (use_tma) {
@@ -644,8 +709,11 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     r[3] = wid;
   }
   if (live) {
-    ll -= T(0.5) * log(sprod);
-    if (sbad) ll = T(NAN);
+    if (lean) {
+      // sum_k log S_k = esum log 2 + log(sprod); the -log(2 pi)/2 of every step
+      ll -= T(0.5) * (T(esum) * T(0.69314718055994530942) + log(sprod)) + T(K) * half_log_2pi<T>();
+      if (sbad) ll = T(NAN);
+    }
     if (status == 0 && !isfinite(ll)) status = 1;
     if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
     if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;

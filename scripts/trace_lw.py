@@ -28,7 +28,7 @@ ap.add_argument("--no-outputs", action="store_true", help="log-likelihood only (
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 N, K = a.n, a.k
-t_np = bench.make_times(N, K, bench.CFG["seed"])
+t_np = bench.make_times_rows(0, N, K, bench.CFG["seed"])
 if a.regular:
     t_np = np.broadcast_to(0.01 * np.arange(K)[None], (N, K)).copy()
 t = torch.as_tensor(t_np, device=dev)
