@@ -65,6 +65,23 @@ def from_dev(t: Optional[torch.Tensor], kind: str):
 # streams so that they overlap EACH OTHER as well: one trajectory is a serial chain of K steps, so a chunk of N/8
 # trajectories takes almost as long as the whole batch (the GPU is a single wave either way) and back-to-back chunk
 # kernels would serialise that latency.
+# Per-trajectory status of the kernels (include/cdk.h): 0 ok, 1 non-finite result (the reference's silent NaN), 2 the
+# solver hit max_steps -- where diffrax RAISES ("The maximum number of solver steps was reached", diffeqsolve's default
+# throw=True).  Host callers already wait for their results, so the check is free there and status 2 raises as upstream
+# does; device-resident callers stay asynchronous and can inspect `last_status()` (a device tensor) themselves.
+RAISE_ON_MAX_STEPS = True
+_last_status = None
+
+
+def last_status():
+    """int32 [N] status tensor of the most recent kernel call in this process (device or pinned host memory)."""
+    return _last_status
+
+
+class MaxStepsReached(RuntimeError):
+    pass
+
+
 STREAM_MIN_BYTES = 32 << 20
 STREAM_CHUNKS = 8
 COMPUTE_STREAMS = 4
@@ -96,7 +113,8 @@ def _host_tensor(x, dt: str) -> torch.Tensor:
 def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, object], want: Sequence[int],
         desc_fields: dict, theta_core_ndim: int = 1, scross_rows: Optional[int] = None,
         status: Optional[torch.Tensor] = None, host_out: bool = False,
-        dev_inputs: Optional[dict] = None, scratch: Optional[torch.Tensor] = None) -> Dict[int, torch.Tensor]:
+        dev_inputs: Optional[dict] = None, scratch: Optional[torch.Tensor] = None,
+        core_ndim_override: Optional[dict] = None) -> Dict[int, torch.Tensor]:
     """Call one C-ABI entry point. `inputs` maps slot -> array-like (None = absent); a leading N marks it batched.
     Returns slot -> tensor for every slot in `want` (+ OUT_STATUS): device tensors, or -- with `host_out`, which the
     API shims set when the caller handed in host arrays -- pinned host tensors whose copies have completed.
@@ -128,7 +146,13 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
             continue
         shape = tuple(x.shape) if hasattr(x, "shape") else tuple(np.shape(x))
         core = _CORE_NDIM[slot] if _CORE_NDIM[slot] is not None else theta_core_ndim
+        if core_ndim_override and slot in core_ndim_override:
+            core = core_ndim_override[slot]  # e.g. IN_R as the [m] diagonal (CDK_FLAG_DIAG_R)
         batched = len(shape) == core + 1
+        if batched and shape[0] == 1 and N > 1:
+            # a leading axis of length 1 is a shared (broadcast) input: `t_emissions=None` or one [K, 1] time grid for
+            # a whole batch of emissions, shared `inputs` -- what vmap(..., in_axes=None) does in the reference
+            x, shape, batched = x[0], shape[1:], False
         if batched:
             if shape[0] != N:
                 raise ValueError(f"input slot {slot}: leading axis {shape[0]} != N={N}")
@@ -233,11 +257,18 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
         for t in keep + list(out.values()):
             for st in [h2d, d2h] + (comp if nchunks > 1 else []):
                 t.record_stream(st)
+    global _last_status
     if host_out:
         d2h.synchronize()
+        _last_status = hout[L.OUT_STATUS]
+        if RAISE_ON_MAX_STEPS and N > 0 and bool((hout[L.OUT_STATUS] == 2).any()):
+            bad = int((hout[L.OUT_STATUS] == 2).sum())
+            raise MaxStepsReached(f"{entry}: the maximum number of solver steps (max_steps={int(d.max_steps)}) was reached "
+                                  f"in {bad} of {N} trajectories; increase diffeqsolve_settings['max_steps'] or dt0")
         if scratch_row:
             hout[L.OUT_SCRATCH] = scratch
         return hout
+    _last_status = status
     # staged inputs / scratch were allocated on this stream: the caching allocator keeps them valid until the kernel
     # has consumed them (stream-ordered reuse), so dropping `keep` here is safe.
     del keep

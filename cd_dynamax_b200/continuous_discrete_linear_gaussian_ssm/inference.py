@@ -88,6 +88,13 @@ def prepare_data(emissions, t_emissions, inputs):
     return Y, T, U, batched
 
 
+def _diag_r(params) -> bool:
+    """A 1-D `emissions.cov` [m] (or [N, m] when batched over parameter samples together with 3-D weights) is the diagonal
+    of R: the reference's Woodbury update (cd_linear/inference.py:240-254)."""
+    rs, hs = _shape(params.emissions.cov), _shape(params.emissions.weights)
+    return len(rs) == 1 or (len(rs) == 2 and len(hs) == 3 and rs[-1] != rs[-2])
+
+
 def _linear_inputs(params: ParamsCDLGSSM, Y, T, U, n, m, d_u):
     dyn, em = params.dynamics, params.emissions
     for nm, v in (("dynamics.weights", dyn.weights), ("dynamics.diffusion_coefficient", dyn.diffusion_coefficient),
@@ -95,10 +102,6 @@ def _linear_inputs(params: ParamsCDLGSSM, Y, T, U, n, m, d_u):
                   ("emissions.cov", em.cov)):
         assert v is not None, f"params.{nm} is required (cd_linear/inference.py:266-272)"
         _check_constant(v, nm, 2)
-    if len(_shape(em.cov)) == 1 or (len(_shape(em.cov)) == 2 and _shape(em.cov)[-1] != _shape(em.cov)[-2]):
-        raise NotImplementedError(
-            "1-D (diagonal) emissions.cov is not supported: the reference's own log-likelihood broadcasts it "
-            "incorrectly (cd_linear/inference.py:613 adds R[j] to every row); pass the full matrix")
     zeros = lambda *s: np.zeros(s)
     ins = {
         L.IN_Y: Y, L.IN_T: T, L.IN_M0: params.initial.mean, L.IN_P0: params.initial.cov, L.IN_F: dyn.weights,
@@ -122,14 +125,17 @@ def _filter_device(params, emissions, t_emissions, filter_hyperparams, inputs, w
     dt = E.pick_dtype(emissions)
     ins = _linear_inputs(params, Y, T, U, n, m, d_u)
     fields = dict(E.parse_settings(hp.diffeqsolve_settings), dt_final=float(hp.dt_final), d_u=d_u)
-    if flags and dt == "f64" and K > 1:
+    diag = _diag_r(params)
+    if diag:
+        fields["flags"] = L.FLAG_DIAG_R
+    elif flags and dt == "f64" and K > 1:
         # keep (A_k, Q_k) of every gap for the type-1 smoother when the cache is affordable (a quarter of the free HBM)
         free, _ = torch.cuda.mem_get_info()
         if N * (K - 1) * 2 * n * n * 8 <= free // 4:
             fields["flags"] = flags
     dev_ins = {}
     out = E.run("cdk_kf_filter", dt, N, K, n, m, ins, want, fields, theta_core_ndim=2, host_out=host_out,
-                dev_inputs=dev_ins)
+                dev_inputs=dev_ins, core_ndim_override={L.IN_R: 1} if diag else None)
     return out, {**ins, **dev_ins}, fields, (N, K, n, m, dt, batched)
 
 
@@ -165,10 +171,12 @@ def cdlgssm_smoother(params: ParamsCDLGSSM, emissions, t_emissions=None,
     ins = dict(ins)
     ins[L.IN_FM], ins[L.IN_FP] = out[L.OUT_FM], out[L.OUT_FP]
     fields = dict(fields, smoother_type=1 if smoother_type == "cd_smoother_1" else 2)
-    if L.OUT_SCRATCH not in out:
-        fields.pop("flags", None)  # the filter kept nothing (not the warp kernel): the smoother re-integrates
+    if L.OUT_SCRATCH not in out and "flags" in fields:
+        # the filter kept nothing (not the warp kernel): the smoother re-integrates the pushforward
+        fields["flags"] = int(fields["flags"]) & ~L.FLAG_KEEP_PUSHFORWARD
     sm = E.run("cdk_kf_smooth", dt, N, K, n, m, ins, (L.OUT_SM, L.OUT_SP, L.OUT_SCROSS), fields, theta_core_ndim=2,
-               status=out[L.OUT_STATUS], scratch=out.get(L.OUT_SCRATCH))
+               status=out[L.OUT_STATUS], scratch=out.get(L.OUT_SCRATCH),
+               core_ndim_override={L.IN_R: 1} if _diag_r(params) else None)
     g = lambda t: E.from_dev(_sq(t, batched), kind)
     return PosteriorGSSMSmoothed(marginal_loglik=g(out[L.OUT_LL]), filtered_means=g(out[L.OUT_FM]),
                                  filtered_covariances=g(out[L.OUT_FP]), smoothed_means=g(sm[L.OUT_SM]),

@@ -1,4 +1,6 @@
 """Shared marshalling for the nonlinear filters (EKF / UKF / EnKF)."""
+import numpy as np
+
 from .. import _engine as E
 from .. import _lib as L
 from ..continuous_discrete_linear_gaussian_ssm.inference import _shape, _sq, prepare_data
@@ -8,6 +10,10 @@ from .cdnlgssm_utils import drift_to_theta
 DEFAULT_FIELDS = ["filtered_means", "filtered_covariances", "predicted_means", "predicted_covariances"]
 _FIELD_SLOT = {"filtered_means": L.OUT_FM, "filtered_covariances": L.OUT_FP, "predicted_means": L.OUT_PM,
                "predicted_covariances": L.OUT_PP, "marginal_loglik": L.OUT_LLCUM}
+
+
+def _to_host(x):
+    return x.detach().cpu().numpy() if hasattr(x, "detach") else x
 
 
 def _val(x):
@@ -33,7 +39,12 @@ def run_filter(entry, params, emissions, t_emissions, inputs, output_fields, des
                diffeqsolve_settings=None, keep_on_device=False):
     """Common driver: returns (PosteriorGSSMFiltered, device outputs dict, context)."""
     kind = E.kind_of(emissions)
-    Y, T, U, batched = prepare_data(emissions, t_emissions, None)  # registry drifts ignore inputs (as upstream's do)
+    if inputs is not None and _shape(inputs)[-1] > 0 and bool(np.any(np.asarray(_to_host(inputs)) != 0)):
+        # the registry drifts and the linear emission take no inputs (upstream's LearnableLorenz63 / LearnableLinear
+        # ignore `u` as well); silently dropping a non-zero input array would change the model without a word
+        raise NotImplementedError("non-zero `inputs` are not supported on the nonlinear path: the registry drifts and "
+                                  "emissions do not depend on u (cdnlgssm_utils.py:50-83)")
+    Y, T, U, batched = prepare_data(emissions, t_emissions, None)
     N, K, m = _shape(Y)
     n = _shape(_val(params.dynamics.diffusion_cov))[-1]
     dt = E.pick_dtype(emissions)

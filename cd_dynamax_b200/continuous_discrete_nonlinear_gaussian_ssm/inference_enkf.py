@@ -4,8 +4,9 @@ ensemble_kalman_filter :151-276.
 Randomness: the reference draws from jax.random (threefry) and a diffrax VirtualBrownianTree, which cannot be
 reproduced outside JAX; this implementation uses a counter-based Philox4x32-10 stream keyed by `key` (an int seed, or
 a 2-word PRNGKey-like array).  Parity with the reference is therefore distributional, exactly as in its own test
-(src/test_scripts/cdnlgssm_test_filter_linear_TRegular.py:434-470).  The SDE step is Euler-Maruyama by default
-(`diffeqsolve_settings={"solver": "heun"}` selects the reference's default Heun scheme)."""
+(src/test_scripts/cdnlgssm_test_filter_linear_TRegular.py:434-470).  The SDE step defaults to the reference's Heun scheme
+(diffrax_utils.py:121-127: dfx.Heun() whenever a diffusion is present and no solver is given);
+`diffeqsolve_settings={"solver": "euler"}` selects Euler-Maruyama (BASELINE config 5)."""
 from typing import Any, List, NamedTuple, Optional
 
 import numpy as np
@@ -32,8 +33,7 @@ def key_to_seed(key) -> int:
 def ensemble_kalman_filter(params, emissions, t_emissions=None, hyperparams: EnKFHyperParams = EnKFHyperParams(),
                            inputs=None, output_fields: Optional[List[str]] = DEFAULT_FIELDS,
                            rng_offset: int = 0) -> PosteriorGSSMFiltered:
-    settings = dict(hyperparams.diffeqsolve_settings or {})
-    settings.setdefault("solver", "euler")
+    settings = dict(hyperparams.diffeqsolve_settings or {})  # no solver given -> parse_settings(sde=True) -> heun
     fields = dict(dt_final=float(hyperparams.dt_final), E=int(hyperparams.N_particles),
                   perturb_measurements=int(bool(hyperparams.perturb_measurements)),
                   rng_seed=key_to_seed(hyperparams.key), rng_offset=int(rng_offset))

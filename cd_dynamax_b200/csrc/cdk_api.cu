@@ -46,7 +46,7 @@ static long long slot_elems(const cdk_desc& d, int slot, int algo) {
     case CDK_IN_H: return m * n;
     case CDK_IN_D: return m;
     case CDK_IN_DU: return m * du;
-    case CDK_IN_R: return m * m;
+    case CDK_IN_R: return ((algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH) && (d.reserved[2] & CDK_FLAG_DIAG_R)) ? m : m * m;
     case CDK_IN_FM: return K * n;
     case CDK_IN_FP: return K * n * n;
   }
@@ -87,6 +87,7 @@ static int validate(const cdk_desc* d, const void* const* in, void* const* out, 
     if (d->num_iter < 1) return fail(CDK_E_SIZE, "num_iter must be >= 1");
   }
   if (algo == ALGO_KF_SMOOTH && d->smoother_type != 1 && d->smoother_type != 2) return fail(CDK_E_ENUM, "smoother_type must be 1 or 2");
+  if (!linear && (d->reserved[2] & CDK_FLAG_DIAG_R)) return fail(CDK_E_UNSUPPORTED, "CDK_FLAG_DIAG_R applies to the linear model only");
   if (algo == ALGO_ENKF_FILTER) {
     if (d->E < 2 || d->E > 65536) return fail(CDK_E_SIZE, "E out of range");
     if (d->solver != CDK_EULER && d->solver != CDK_HEUN) return fail(CDK_E_UNSUPPORTED, "EnKF supports solver euler (Euler-Maruyama) or heun");

@@ -16,7 +16,12 @@
 namespace cdk {
 namespace {
 
-enum { ODE_PUSH = 0, ODE_EKF = 1, ODE_MEAN = 2, ODE_BACK = 3, ODE_UKF = 4 };
+enum { ODE_PUSH = 0, ODE_EKF = 1, ODE_MEAN = 2, ODE_BACK = 3, ODE_UKF = 4, ODE_UKFC = 5 };
+
+// Drifts whose Jacobian is a fixed sparse stencil evaluated on the fly (no n x n Jacobian buffer, no dense J P product)
+__host__ __device__ inline bool stencil_drift(int id) { return id == CDK_DRIFT_LORENZ63 || id == CDK_DRIFT_LORENZ96; }
+// The UKF runs in closed form (see ode_rhs, ODE_UKFC) unless the caller asks for literal sigma points
+__host__ __device__ inline bool ukf_closed(const cdk_desc& d) { return !(d.reserved[2] & CDK_FLAG_UKF_SIGMA_POINTS); }
 
 template <typename T>
 struct GArgs {
@@ -35,6 +40,7 @@ struct Lay {
     const bool lin = algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH;
     const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
     const bool ukf = algo == ALGO_UKF_FILTER;
+    const bool ukfc = ukf && ukf_closed(d);
     nth = lin ? nn : (ukf ? d.n_theta : (d.n_theta > nn ? d.n_theta : nn));
     const int mx = n > m ? n : m;
     const int wsz = mx * ldp(mx);
@@ -48,10 +54,15 @@ struct Lay {
     MU = take(n); P = take(nn);  // contiguous: [MU | P] is the (m, P) ODE state (n is padded to even by take())
     ODEY = take(lin ? 2 * nn : 0);
     YS = take(S); ACC = take(S); KS = take(nslots * S);
-    if (ukf && nslots == 1 && m <= n) {
-      // UKF with a chain tableau: 110 KB instead of 164 KB for n = 40, m = 20, so that TWO trajectories share an SM.
-      // J (the factor of P inside the update) and W3 (update / model-load scratch) are only live while the ODE stage
-      // buffers are not, so they alias KS and ACC; the RHS needs neither (see ode_rhs).
+    if (ukfc && nslots == 1 && m <= n && stencil_drift(d.drift_id)) {
+      // closed-form UKF, stencil Jacobian, chain tableau: the RHS needs no scratch at all (J P is formed in the output
+      // block and symmetrised in place) and the update's three [m x n] scratch matrices are only live while the ODE stage
+      // buffers are not -- 84 KB for n = 40, m = 20.
+      J = KS; W1 = YS; W2 = KS; W3 = ACC;
+    } else if (ukf && !ukfc && nslots == 1 && m <= n) {
+      // sigma-point UKF with a chain tableau: 110 KB instead of 164 KB for n = 40, m = 20, so that TWO trajectories share
+      // an SM.  J (the factor of P inside the update) and W3 (update / model-load scratch) are only live while the ODE
+      // stage buffers are not, so they alias KS and ACC; the RHS needs neither (see ode_rhs).
       J = KS; W1 = take(wsz); W2 = take(wsz); W3 = ACC;
     } else {
       J = take(nn); W1 = take(wsz); W2 = take(wsz); W3 = take(wsz);
@@ -70,6 +81,42 @@ struct Ctx {
   __device__ Ctx(const GArgs<T>& g_, T* sh_) : g(g_), L(g_.k.d, g_.algo, g_.nslots), sh(sh_) {}
   __device__ T* p(int off) const { return sh + off; }
 };
+
+// 0.5 * trace(Hess f_r(x) P) for the registry drifts (all polynomials of degree <= 2, so the Hessian is constant):
+// the exact second-order term of the unscented mean (NOT the reference EKF's 'second' order, whose trace runs over the
+// wrong axes -- SURVEY F8 -- and which drift_graddiv restates).
+template <typename T>
+__device__ __forceinline__ T drift_half_trhp(int id, const T* th, int n, int r, const T* P, int ld) {
+  auto ps = [&](int i, int j) { return T(0.5) * (P[i * ld + j] + P[j * ld + i]); };
+  switch (id) {
+    case CDK_DRIFT_LINEAR: return T(0);
+    case CDK_DRIFT_LORENZ63: return r == 0 ? T(0) : (r == 1 ? -ps(0, 2) : ps(0, 1));  // f1 = x (rho - z) - y, f2 = x y - b z
+    case CDK_DRIFT_LORENZ96: {  // f_r = (x_{r+1} - x_{r-2}) x_{r-1} - x_r + F
+      const int ip = r + 1 == n ? 0 : r + 1, im1 = r == 0 ? n - 1 : r - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
+      return ps(ip, im1) - ps(im2, im1);
+    }
+    default: {  // f_r = a_r + B_rj x_j + C_rjk x_j x_k
+      const T* C = th + n + n * n;
+      T s = T(0);
+      for (int j = 0; j < n; ++j)
+        for (int k = 0; k < n; ++k) s += C[(r * n + j) * n + k] * ps(j, k);
+      return s;
+    }
+  }
+}
+
+// (J(x) P)[r][c] for the stencil drifts, straight from x and P (4 / 3 terms per entry instead of a length-n dot product)
+template <typename T>
+__device__ __forceinline__ T stencil_jp(int id, const T* th, int n, int r, int c, const T* x, const T* P, int ld) {
+  if (id == CDK_DRIFT_LORENZ96) {
+    const int ip = r + 1 == n ? 0 : r + 1, im1 = r == 0 ? n - 1 : r - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
+    return x[im1] * (P[ip * ld + c] - P[im2 * ld + c]) + (x[ip] - x[im2]) * P[im1 * ld + c] - P[r * ld + c];
+  }
+  const T p0 = P[c], p1 = P[ld + c], p2 = P[2 * ld + c];  // Lorenz-63: J = [[-s, s, 0], [r - z, -1, -x], [y, x, -b]]
+  if (r == 0) return th[0] * (p1 - p0);
+  if (r == 1) return (th[1] - x[2]) * p0 - p1 - x[0] * p2;
+  return x[1] * p0 + x[0] * p1 - th[2] * p2;
+}
 
 // k = dt * rhs(kind, ys).  All arrays in shared memory.  Ends with a barrier.
 template <typename T>
@@ -129,6 +176,48 @@ __device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
     FOR_T(e, n * n) {  // P J^T = (J P)^T for the symmetric P
       const int i = e / n, j = e - i * n;
       kP[i * ld + j] = dt * ((JP[i * ld + j] + JP[j * ld + i]) + lql[i * ld + j]);
+    }
+    __syncthreads();
+    return;
+  }
+  if (kind == ODE_UKFC) {
+    // The sigma-point moment ODE (Sarkka eq. 3.183, inference_ukf.py:130-152) in CLOSED FORM.  Every drift of the registry
+    // is a polynomial of degree <= 2, f(m + d) = f(m) + J d + B(d, d) exactly, and the sigma set is symmetric
+    // (X_i^+- = m +- c L_i, L L^T = P, w = 1 / (2 (n + lambda)), c^2 = n + lambda), so
+    //   sum_k w_m[k] f(X_k)                      = f(m) + sum_i B(L_i, L_i) = f(m) + 0.5 tr(Hess f . P)
+    //   sum_k w_c[k] (f(X_k) - fbar)(X_k - m)^T  = w c sum_i (2 c J L_i) L_i^T = J P
+    // hold in exact arithmetic: the unscented predict of these models is dm = f(m) + 0.5 tr(Hess P),
+    // dP = J P + P J^T + L Qc L^T -- no Cholesky factorisation of P at every RK stage (18 per observation-step of BASELINE
+    // config 4) and no 2n + 1 drift evaluations.  The literal sigma-point evaluation below (ODE_UKF) stays available
+    // (CDK_FLAG_UKF_SIGMA_POINTS) and both are checked against the oracle, which evaluates sigma points as the reference
+    // does; they differ by the rounding of the reference's own f(X^+) - f(X^-) cancellation (~1e-13).
+    const T* th = c.p(L.TH);
+    FOR_T(i, n) {
+      km[i] = dt * (drift_f<T>(d.drift_id, th, n, i, [&](int j) { return mm[j]; }) + drift_half_trhp<T>(d.drift_id, th, n, i, P, ld));
+    }
+    T* JP = kP;  // formed in the output block, symmetrised in place
+    if (stencil_drift(d.drift_id)) {
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        JP[i * ld + j] = stencil_jp<T>(d.drift_id, th, n, i, j, mm, P, ld);
+      }
+    } else {
+      T* J = c.p(L.J);
+      FOR_T(e, n * n) {
+        const int i = e / n, j = e - i * n;
+        J[i * ld + j] = drift_jac<T>(d.drift_id, th, n, i, j, mm);
+      }
+      __syncthreads();
+      mm_dmma<T, false, false>(J, ld, P, ld, n, n, n, [&](int i, int j, double v) { JP[i * ld + j] = (T)v; });
+    }
+    __syncthreads();
+    FOR_T(e, n * n) {
+      const int a = e / n, b = e - a * n;
+      if (a <= b) {  // one thread owns the pair (a, b), (b, a)
+        const T sab = JP[a * ld + b] + JP[b * ld + a];
+        kP[a * ld + b] = dt * (sab + lql[a * ld + b]);
+        if (a != b) kP[b * ld + a] = dt * (sab + lql[b * ld + a]);
+      }
     }
     __syncthreads();
     return;
@@ -279,7 +368,11 @@ __device__ void load_model(const Ctx<T>& c, long long traj, bool linear) {
     FOR_T(i, a.d.n_theta) c.p(L.TH)[i] = src(CDK_IN_F)[i];
   }
   load_mat<T>(c.p(L.H), src(CDK_IN_H), m, n, L.ldn);
-  load_mat<T>(c.p(L.R), src(CDK_IN_R), m, m, L.ldm);
+  if (a.d.reserved[2] & CDK_FLAG_DIAG_R) {
+    FOR_T(i, m) c.p(L.R)[i] = src(CDK_IN_R)[i];  // 1-D emissions.cov: the diagonal (linear model only, validated)
+  } else {
+    load_mat<T>(c.p(L.R), src(CDK_IN_R), m, m, L.ldm);
+  }
   FOR_T(i, m) c.p(L.DV)[i] = src(CDK_IN_D)[i];
   // L Qc L^T via W1 = L, W2 = Qc, W3 = L Qc
   T* Lm = c.p(L.W1);
@@ -304,6 +397,162 @@ __device__ void load_model(const Ctx<T>& c, long long traj, bool linear) {
   __syncthreads();
 }
 
+// Linear-model measurement update for a 1-D (diagonal) emission covariance: the reference's Woodbury branch
+// (cd_linear/inference.py:240-254) and its log-likelihood (:613), restated literally:
+//   U = H chol(sym P),  X = U / R[:, None],  S_inv = diag(1/R) - X psd_solve(I + U^T X, X^T),  K = P H^T S_inv,
+//   S = diag(R) + H P H^T,  P <- sym(P - K S K^T),  m <- m + K (y - D u - d - H m);
+//   ll = log N(y; H m + D u + d, chol(H P H^T + (R_i + R_j) / 2)) -- the reference adds the VECTOR R to H P H^T by
+//   broadcasting (entry (i, j) gets R[j]) and TFP's Cholesky factors the symmetrised matrix; for a constant vector this is
+//   diag(R)-free of error only on the diagonal, and it is reproduced as is (parity is with the reference, not the textbook).
+// Scratch: J, the pushforward buffers ODEY (2 n x n, idle during the update), W1..W3, SM, SL.
+template <typename T>
+__device__ T condition_on_diag_r(const Ctx<T>& c) {
+  const Lay& L = c.L;
+  const int n = L.n, m = L.m, ldn = L.ldn, ldm = L.ldm;
+  T* mu = c.p(L.MU);
+  T* P = c.p(L.P);
+  const T* H = c.p(L.H);
+  const T* R = c.p(L.R);  // [m]
+  const T* dv = c.p(L.DV);
+  const T* yv = c.p(L.YV);
+  T* Lp = c.p(L.J);        // chol(sym P)
+  T* Ma = c.p(L.ODEY);     // sym(P), then M = I + U^T X
+  T* Lm = Ma + L.nn;       // chol(sym(M) + 1e-9 I)
+  T* W1 = c.p(L.W1);       // H P [m x n]; then Z = psd_solve(M, X^T) as [n x ldm]; then (P H^T)^T [m x n]
+  T* U = c.p(L.W2);        // [m x n], later Kt
+  T* X = c.p(L.W3);        // [m x n], later S Kt
+  T* Sm = c.p(L.SM);
+  T* Sl = c.p(L.SL);
+  T* rv = c.p(L.RV);
+  T* zv = rv + m;
+  __shared__ T ll_sh;
+  FOR_T(e, m * n) {
+    const int a = e / n, j = e - a * n;
+    T s = T(0);
+    for (int q = 0; q < n; ++q) s += H[a * ldn + q] * P[q * ldn + j];
+    W1[a * ldn + j] = s;
+  }
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    Ma[i * ldn + j] = T(0.5) * (P[i * ldn + j] + P[j * ldn + i]);
+  }
+  FOR_T(a, m) {
+    T s = dv[a];
+    for (int q = 0; q < n; ++q) s += H[a * ldn + q] * mu[q];
+    rv[a] = yv[a] - s;
+  }
+  __syncthreads();
+  FOR_T(e, m * m) {  // H P H^T (plain) in Sm; the log-likelihood's matrix in X (scratch)
+    const int a = e / m, b = e - a * m;
+    T s = T(0);
+    for (int q = 0; q < n; ++q) s += W1[a * ldn + q] * H[b * ldn + q];
+    Sm[a * ldm + b] = s;
+  }
+  __syncthreads();
+  FOR_T(e, m * m) {
+    const int a = e / m, b = e - a * m;
+    // sym(H P H^T + R[None, :]) = (hph_ab + hph_ba) / 2 + (R_a + R_b) / 2
+    X[a * ldm + b] = T(0.5) * ((Sm[a * ldm + b] + R[b]) + (Sm[b * ldm + a] + R[a]));
+  }
+  __syncthreads();
+  chol<T>(X, Sl, m, ldm, T(0));
+  if (threadIdx.x == 0) {
+    T quad = T(0), logdet = T(0);
+    for (int i = 0; i < m; ++i) {
+      T v = rv[i];
+      for (int q = 0; q < i; ++q) v -= Sl[i * ldm + q] * zv[q];
+      v /= Sl[i * ldm + i];
+      zv[i] = v;
+      quad += v * v;
+      logdet += log(Sl[i * ldm + i]);
+    }
+    ll_sh = T(-0.5) * quad - logdet - T(m) * half_log_2pi<T>();
+  }
+  chol<T>(Ma, Lp, n, ldn, T(0));  // jnp.linalg.cholesky(P) symmetrises its input
+  FOR_T(e, m * n) {  // U = H Lp (Lp lower), X = U / R[:, None]
+    const int a = e / n, j = e - a * n;
+    T s = T(0);
+    for (int q = j; q < n; ++q) s += H[a * ldn + q] * Lp[q * ldn + j];
+    U[a * ldn + j] = s;
+    X[a * ldn + j] = s / R[a];
+  }
+  __syncthreads();
+  FOR_T(e, n * n) {  // M = I + U^T X
+    const int i = e / n, j = e - i * n;
+    T s = i == j ? T(1) : T(0);
+    for (int a = 0; a < m; ++a) s += U[a * ldn + i] * X[a * ldn + j];
+    Ma[i * ldn + j] = s;
+  }
+  __syncthreads();
+  T* Ms = U;  // sym(M) (U is no longer needed; n x ldn fits the max(n, m)-sized scratch)
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    Ms[i * ldn + j] = T(0.5) * (Ma[i * ldn + j] + Ma[j * ldn + i]);
+  }
+  T* Z = W1;  // [n x ldm] <- X^T, then psd_solve(M, X^T)  (H P is no longer needed; max(n, m)-sized scratch)
+  __syncthreads();
+  FOR_T(e, n * m) {
+    const int i = e / m, a = e - i * m;
+    Z[i * ldm + a] = X[a * ldn + i];
+  }
+  chol<T>(Ms, Lm, n, ldn, T(1e-9));
+  chol_solve<T>(Lm, n, ldn, Z, m, ldm);
+  T* Si = Sl;  // S_inv = diag(1 / R) - X Z
+  FOR_T(e, m * m) {
+    const int a = e / m, b = e - a * m;
+    T s = a == b ? T(1) / R[a] : T(0);
+    for (int q = 0; q < n; ++q) s -= X[a * ldn + q] * Z[q * ldm + b];
+    Si[a * ldm + b] = s;
+  }
+  __syncthreads();
+  FOR_T(e, m * n) {  // (P H^T)^T, row a = P H[a, :]^T
+    const int a = e / n, i = e - a * n;
+    T s = T(0);
+    for (int q = 0; q < n; ++q) s += P[i * ldn + q] * H[a * ldn + q];
+    W1[a * ldn + i] = s;
+  }
+  __syncthreads();
+  T* Kt = U;  // Kt[a][i] = K[i][a] = sum_b (P H^T)[i][b] S_inv[b][a]
+  FOR_T(e, m * n) {
+    const int a = e / n, i = e - a * n;
+    T s = T(0);
+    for (int b = 0; b < m; ++b) s += W1[b * ldn + i] * Si[b * ldm + a];
+    Kt[a * ldn + i] = s;
+  }
+  FOR_T(a, m) Sm[a * ldm + a] += R[a];  // S = diag(R) + H P H^T
+  __syncthreads();
+  T* SK = X;
+  FOR_T(e, m * n) {
+    const int a = e / n, j = e - a * n;
+    T s = T(0);
+    for (int b = 0; b < m; ++b) s += Sm[a * ldm + b] * Kt[b * ldn + j];
+    SK[a * ldn + j] = s;
+  }
+  __syncthreads();
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    T s = T(0);
+    for (int a = 0; a < m; ++a) s += Kt[a * ldn + i] * SK[a * ldn + j];
+    P[i * ldn + j] -= s;
+  }
+  FOR_T(i, n) {
+    T s = T(0);
+    for (int a = 0; a < m; ++a) s += Kt[a * ldn + i] * rv[a];
+    mu[i] += s;
+  }
+  __syncthreads();
+  FOR_T(e, n * n) {
+    const int i = e / n, j = e - i * n;
+    if (i < j) {
+      const T v = T(0.5) * (P[i * ldn + j] + P[j * ldn + i]);
+      P[i * ldn + j] = v;
+      P[j * ldn + i] = v;
+    }
+  }
+  __syncthreads();
+  return ll_sh;
+}
+
 // Measurement update shared by KF / EKF / UKF.  On entry MU, P hold the prediction; on exit the filtered moments.
 // Returns the log-likelihood increment (same value in every thread).
 template <typename T>
@@ -325,7 +574,10 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
   T* rv = c.p(L.RV);
   T* zv = rv + m;
   __shared__ T ll_sh;
-  const bool ukf = algo == ALGO_UKF_FILTER;
+  // ukf: literal sigma points through chol(P).  The closed-form UKF (linear emission: S = H P H^T + R and the cross term
+  // P H^T exactly) takes the H P products of the KF / EKF branch, but -- like the reference's UKF -- never symmetrises.
+  const bool ukf = algo == ALGO_UKF_FILTER && !ukf_closed(d);
+  const bool no_sym = algo == ALGO_UKF_FILTER;
   for (int it = 0; it < num_iter; ++it) {
     if (!ukf) {
       FOR_T(e, m * n) {
@@ -426,7 +678,7 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
     }
     __syncthreads();
   }
-  if (!ukf) {
+  if (!no_sym) {
     // symmetrize (cd_linear/inference.py:259, inference_ekf.py:199); the UKF does not (inference_ukf.py:202)
     FOR_T(e, n * n) {
       const int i = e / n, j = e - i * n;
@@ -486,7 +738,11 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
       yv[i] = v;
     }
     __syncthreads();
-    ll += condition_on<T>(c, algo, algo == ALGO_EKF_FILTER ? d.num_iter : 1);
+    if (linear && (d.reserved[2] & CDK_FLAG_DIAG_R)) {
+      ll += condition_on_diag_r<T>(c);
+    } else {
+      ll += condition_on<T>(c, algo, algo == ALGO_EKF_FILTER ? d.num_iter : 1);
+    }
     if (FM) FOR_T(i, n) FM[(row0 + k) * n + i] = mu[i];
     if (FP) store_mat<T>(FP + (row0 + k) * n * n, P, n, n, ldn);
     if (LLC && threadIdx.x == 0) LLC[row0 + k] = ll;
@@ -531,7 +787,8 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
       }
       __syncthreads();
     } else {
-      hit = ode_solve<T>(c, algo == ALGO_UKF_FILTER ? ODE_UKF : ODE_EKF, mu, L.mpoff + L.nn, t0, t1, dt0, d.max_steps);
+      const int kind = algo == ALGO_UKF_FILTER ? (ukf_closed(d) ? ODE_UKFC : ODE_UKF) : ODE_EKF;
+      hit = ode_solve<T>(c, kind, mu, L.mpoff + L.nn, t0, t1, dt0, d.max_steps);
     }
     if (hit) status = 2;
     if (PM) FOR_T(i, n) PM[(row0 + k) * n + i] = mu[i];

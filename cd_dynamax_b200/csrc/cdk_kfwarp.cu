@@ -780,6 +780,7 @@ bool kf_warp_eligible(const cdk_desc& d, bool smooth) {
     return e && e[0] == '0';
   }();
   if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return false;
+  if (!smooth && (d.reserved[2] & CDK_FLAG_DIAG_R)) return false;  // the Woodbury update lives in the generic kernel
   if (smooth && d.smoother_type != 1) return false;  // type 2 (backward ODE) stays on the generic kernel
   RtTab rt;
   if (!fill_rt_tab(d.solver, rt)) return false;

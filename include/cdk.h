@@ -79,7 +79,7 @@ enum {
   CDK_IN_H,       /* emission weights H   [m,n]                                                     */
   CDK_IN_D,       /* emission bias d      [m]                                                       */
   CDK_IN_DU,      /* kf: emission input weights D [m,d_u] or NULL                                   */
-  CDK_IN_R,       /* emission covariance R [m,m]                                                    */
+  CDK_IN_R,       /* emission covariance R [m,m] ([m] with CDK_FLAG_DIAG_R)                         */
   CDK_IN_FM,      /* smooth: filtered means        [N,K,n]                                          */
   CDK_IN_FP,      /* smooth: filtered covariances  [N,K,n,n]                                        */
   CDK_NUM_IN
@@ -134,6 +134,15 @@ typedef struct cdk_desc {
  * the same flag and buffer reads them back instead of re-integrating them (cd_linear/inference.py:753 recomputes; the
  * values are bit-identical).  cdk_scratch_bytes() returns 0 when the request is not served by the warp kernels. */
 #define CDK_FLAG_KEEP_PUSHFORWARD 1
+/* reserved[2] bit 1: cdk_ukf_filter_* evaluates the 2n + 1 sigma points literally (Cholesky factor of P at every RK stage,
+ * inference_ukf.py:45-60, :130-152).  By default the unscented predict runs in closed form -- every registry drift is a
+ * polynomial of degree <= 2 and the emission is linear, for which the sigma-point sums are exactly f(m) + tr(Hess P)/2 and
+ * J P (cdk_generic.cu, ODE_UKFC) -- which gives the same moments up to rounding at a fraction of the cost. */
+#define CDK_FLAG_UKF_SIGMA_POINTS 2
+/* reserved[2] bit 2: cdk_kf_filter_*: in[CDK_IN_R] is the DIAGONAL of the emission covariance, [m] (a 1-D emissions.cov):
+ * the update takes the reference's Woodbury branch (cd_linear/inference.py:240-254) and the log-likelihood its broadcast
+ * of the vector over H P H^T (:613), both restated literally (csrc/cdk_generic.cu: condition_on_diag_r). */
+#define CDK_FLAG_DIAG_R 4
 
 #define CDK_MAX_N 64
 #define CDK_MAX_M 64

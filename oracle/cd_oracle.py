@@ -375,10 +375,23 @@ def compute_pushforward(F, LQL, t0, t1, settings: SolverSettings):
     return A, Q, hit
 
 
+def _diag(v):
+    return v[..., :, None] * np.eye(v.shape[-1], dtype=v.dtype)
+
+
 def _kf_condition_on(m, P, H, d, Du, R, y):
-    """cd_linear/inference.py:209-259 (full-R branch :237-239, :257-259)."""
-    S = R + H @ P @ _mT(H)
-    K = _mT(psd_solve(S, H @ P))
+    """cd_linear/inference.py:209-259: full-R branch :237-239, diagonal-R (R.ndim == 1) Woodbury branch :240-254."""
+    if R.ndim == P.ndim:  # [N, m, m]
+        S = R + H @ P @ _mT(H)
+        K = _mT(psd_solve(S, H @ P))
+    else:  # [N, m]: Woodbury with A = diag(R), U = H chol(P), V = U^T, C = I
+        n = P.shape[-1]
+        I = np.eye(n, dtype=P.dtype)
+        U = H @ cholesky(symmetrize(P))  # jnp.linalg.cholesky symmetrises its input
+        X = U / R[..., :, None]
+        S_inv = _diag(1.0 / R) - X @ psd_solve(I + _mT(U) @ X, _mT(X))
+        K = P @ _mT(H) @ S_inv
+        S = _diag(R) + H @ P @ _mT(H)
     Sigma = P - K @ S @ _mT(K)
     mu = m + _mv(K, y - Du - d - _mv(H, m))
     return mu, symmetrize(Sigma)
@@ -390,7 +403,12 @@ def cdlgssm_filter(p: LinearParams, y, t, dt_final=1e-10, settings=SolverSetting
     t = np.asarray(t, dtype)
     N, K, mdim = y.shape
     c = lambda x, core: _bN(np.asarray(x, dtype), N, core)
-    F, L, Qc, H, R = c(p.F, 2), c(p.L, 2), c(p.Qc, 2), c(p.H, 2), c(p.R, 2)
+    F, L, Qc, H = c(p.F, 2), c(p.L, 2), c(p.Qc, 2), c(p.H, 2)
+    # a 1-D emissions.cov (diagonal R) takes the reference's Woodbury update; its log-likelihood adds the vector to
+    # H P H^T by BROADCASTING (cd_linear/inference.py:613: entry (i, j) gets R[j]) and TFP's Cholesky then factors the
+    # symmetrised matrix, i.e. H P H^T + (R_i + R_j) / 2 -- restated as is (it equals diag(R) only for a constant vector)
+    diag_R = np.asarray(p.R).ndim == 1
+    R = c(p.R, 1) if diag_R else c(p.R, 2)
     n = F.shape[-1]
     b = c(p.b if p.b is not None else np.zeros(n), 1)
     d = c(p.d if p.d is not None else np.zeros(mdim), 1)
@@ -412,7 +430,8 @@ def cdlgssm_filter(p: LinearParams, y, t, dt_final=1e-10, settings=SolverSetting
     for k in range(K):
         Du = _mv(D, u[:, k]) if inputs is not None else np.zeros((N, mdim), dtype)
         Bu = _mv(B, u[:, k]) if inputs is not None else np.zeros((N, n), dtype)
-        ll = ll + mvn_logpdf(y[:, k], _mv(H, m) + Du + d, H @ P @ _mT(H) + R)  # :613
+        S_ll = H @ P @ _mT(H) + (symmetrize(np.broadcast_to(R[:, None, :], (N, mdim, mdim))) if diag_R else R)
+        ll = ll + mvn_logpdf(y[:, k], _mv(H, m) + Du + d, symmetrize(S_ll) if diag_R else S_ll)  # :613
         mf, Pf = _kf_condition_on(m, P, H, d, Du, R, y[:, k])  # :616
         A, Q, hit = compute_pushforward(F, LQL, t0s[:, k], t1s[:, k], settings)  # :619
         m = _mv(A, mf) + Bu + b  # :204

@@ -122,9 +122,22 @@ def c4(scale):
     t = times(N, K, 0.02, 4)
     y = 8 + 2 * torch.randn(N, K, m, **f64)
     hp = cd.UKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.005})
+    os.environ["CDK_UKF_SIGMA_POINTS"] = "0"
     ms = timeit(lambda: cd.cdnlgssm_filter(p, y, t[..., None], hp), reps=2)
+    ms_ll = timeit(lambda: cd.cdnlgssm_filter(p, y, t[..., None], hp, output_fields=[]), reps=2)
+    os.environ["CDK_UKF_SIGMA_POINTS"] = "1"
+    Ns = min(N, 2048)
+    ms_sig = timeit(lambda: cd.cdnlgssm_filter(p, y[:Ns], t[:Ns, :, None], hp), reps=1)
+    os.environ["CDK_UKF_SIGMA_POINTS"] = "0"
+    # executed flops of the closed-form kernel per observation-step: 18 RK stages x (n^2 entries x ~14 flop) + update ~0.2 M
     return dict(config=f"C4 UKF Lorenz-96 n=40 m=20 N={N} (of 8,192) K=500", ms=ms, obs_steps_per_s=N * K / ms * 1e3,
-                tflops_survey=5.98e6 * N * K / ms / 1e9)
+                ll_only_ms=ms_ll, ll_only_obs_steps_per_s=N * K / ms_ll * 1e3,
+                note="closed-form unscented predict (default); tflops_survey counts the sigma-point algorithm's flops and is NOT "
+                     "what this kernel executes",
+                tflops_survey_equivalent=5.98e6 * N * K / ms / 1e9,
+                hbm_gbs_outputs=26240.0 * N * K / ms / 1e6,
+                sigma_point_kernel=dict(N=Ns, ms=ms_sig, obs_steps_per_s=Ns * K / ms_sig * 1e3,
+                                        tflops_survey=5.98e6 * Ns * K / ms_sig / 1e9))
 
 
 def c5(scale):

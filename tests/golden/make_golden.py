@@ -83,7 +83,8 @@ def post_to_dict(post):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-def linear_case(name, seed, n, m, N, K, mean_gap, solver, dt0, dt_final, d_u=0, bias=True, regular=False, tracking=False):
+def linear_case(name, seed, n, m, N, K, mean_gap, solver, dt0, dt_final, d_u=0, bias=True, regular=False, tracking=False,
+                diag_R=False):
     rng = np.random.default_rng(seed)
     if tracking:  # cdlgssm_tracking.ipynb:136-225 parameters (BASELINE config 1)
         F = np.zeros((4, 4)); F[0, 2] = F[1, 3] = 1.0
@@ -103,6 +104,8 @@ def linear_case(name, seed, n, m, N, K, mean_gap, solver, dt0, dt_final, d_u=0, 
         p0 = rng.standard_normal((n, n)); P0 = p0 @ p0.T / n + 0.5 * np.eye(n)
         b = 0.1 * rng.standard_normal(n) if bias else np.zeros(n)
         d = 0.1 * rng.standard_normal(m) if bias else np.zeros(m)
+    if diag_R:  # 1-D emissions.cov: the Woodbury branch of _condition_on (cd_linear/inference.py:240-254)
+        R = 0.1 * (1.0 + rng.uniform(size=m))
     B = rng.standard_normal((n, d_u)) if d_u else np.zeros((n, 0))
     D = rng.standard_normal((m, d_u)) if d_u else np.zeros((m, 0))
     t = np.tile(np.arange(K, dtype=np.float64), (N, 1)) if regular else irregular_times(rng, N, K, mean_gap)
@@ -234,6 +237,9 @@ if __name__ == "__main__":
     linear_case("kf_inputs_heun", 12, 3, 2, N=2, K=25, mean_gap=0.05, solver="heun", dt0=0.01, dt_final=0.3, d_u=2)
     linear_case("kf_regular_dopri5", 13, 2, 6, N=2, K=8, mean_gap=1.0, solver=None, dt0=None, dt_final=1.0, regular=True, bias=False)
     linear_case("kf_n16_rk4", 14, 16, 4, N=2, K=12, mean_gap=0.04, solver="rk4", dt0=0.01, dt_final=1e-10)
+    linear_case("kf_diagR_rk4", 15, 5, 3, N=3, K=25, mean_gap=0.05, solver="rk4", dt0=0.0125, dt_final=0.02, diag_R=True)
+    linear_case("kf_diagR_inputs_dopri5", 16, 4, 2, N=2, K=15, mean_gap=0.05, solver=None, dt0=None, dt_final=1e-10, d_u=1,
+                diag_R=True)
     # --- CD-EKF / EKS
     nonlinear_case("ekf_l63_second_rk4", 21, "lorenz63", 3, 1, N=3, K=60, mean_gap=0.01, solver="rk4", dt0=0.0025, smoother=True)
     nonlinear_case("ekf_l63_first_dopri5", 22, "lorenz63", 3, 2, N=2, K=30, mean_gap=0.03, solver=None, dt0=None, state_order="first", smoother=True)

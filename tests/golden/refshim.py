@@ -111,9 +111,13 @@ def set_default_dtype(dt):
 
 
 def _chol(A):
+    """jnp.linalg.cholesky: jax 0.4.13 forwards to lax.linalg.cholesky(x, symmetrize_input=True), i.e. it factors
+    (A + A^T) / 2.  (Exact no-op for a symmetric A; it matters where the reference hands it a non-symmetric matrix: the
+    1-D `emissions.cov` broadcast in cd_linear/inference.py:613.)"""
     A = np.asarray(A)
     if not np.all(np.isfinite(A)):
         return np.full_like(A, np.nan)
+    A = 0.5 * (A + np.swapaxes(A, -1, -2))
     try:
         return np.linalg.cholesky(A)
     except np.linalg.LinAlgError:

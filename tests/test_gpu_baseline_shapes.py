@@ -88,20 +88,24 @@ def _l96_case(N, K, seed, n=40, m=20):
     return g, po, t, y
 
 
+@pytest.mark.parametrize("sigma_points", [False, True])
 @pytest.mark.parametrize("solver,dt0", [("rk4", 0.005), ("dopri5", 0.01)])
-def test_c4_ukf_l96_n40_m20_vs_oracle(solver, dt0):
-    """BASELINE config 4 shape: n = 40, m = 20 -- the blocked Cholesky runs 5 panels, RK4 (a chain tableau with m <= n)
-    takes the aliased two-CTAs-per-SM layout, Dopri5 the six-stage one."""
+def test_c4_ukf_l96_n40_m20_vs_oracle(solver, dt0, sigma_points, monkeypatch):
+    """BASELINE config 4 shape: n = 40, m = 20, against the oracle's literal sigma points.  Closed-form kernel (default):
+    stencil Jacobian, RK4 takes the aliased 84 KB layout.  Sigma-point kernel: the blocked Cholesky runs 5 panels, RK4 (a
+    chain tableau with m <= n) takes the aliased two-CTAs-per-SM layout, Dopri5 the six-stage one."""
     cd = api()
+    monkeypatch.setenv("CDK_UKF_SIGMA_POINTS", "1" if sigma_points else "0")
+    solver_tag = solver + ("_sigma" if sigma_points else "_closed")
     g, po, t, y = _l96_case(N=6, K=40, seed=40)
     hp = cd.UKFHyperParams(diffeqsolve_settings={"solver": solver, "dt0": dt0})
     f = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], hp)
     r = o.unscented_kalman_filter(po, y, t, settings=o.SolverSettings(solver, dt0))
     assert np.isfinite(r["marginal_loglik"]).all()
     e = max_rel_err(f.marginal_loglik, r["marginal_loglik"])
-    record(f"c4_ukf_n40_{solver}:marginal_loglik", e)
+    record(f"c4_ukf_n40_{solver_tag}:marginal_loglik", e)
     assert e < TOL
-    check_moments(f, r, f"c4_ukf_n40_{solver}")
+    check_moments(f, r, f"c4_ukf_n40_{solver_tag}")
 
 
 @pytest.mark.parametrize("solver", ["euler", "heun"])

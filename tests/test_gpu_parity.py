@@ -116,15 +116,19 @@ def test_ekf_and_eks_vs_reference_golden(name):
             assert scaled_err(getattr(s, fld), g["smooth_" + fld]) < 1e-8, fld
 
 
+@pytest.mark.parametrize("sigma_points", [False, True])
 @pytest.mark.parametrize("name", golden_cases("ukf_"))
-def test_ukf_vs_reference_golden(name):
+def test_ukf_vs_reference_golden(name, sigma_points, monkeypatch):
+    """Both UKF kernels against the reference's output: the closed-form unscented predict (default) and the literal
+    sigma-point evaluation (CDK_UKF_SIGMA_POINTS=1)."""
     cd = api()
+    monkeypatch.setenv("CDK_UKF_SIGMA_POINTS", "1" if sigma_points else "0")
     g = load_golden(name)
     p = nonlinear_params_api(g)
     hp = cd.UKFHyperParams(dt_final=float(g["dt_final"]), diffeqsolve_settings=settings_api(g))
     f = cd.cdnlgssm_filter(p, g["y"], g["t"][..., None], hp)
     assert max_rel_err(f.marginal_loglik, g["filt_marginal_loglik"]) < TOL
-    check_moments(f, g, name, prefix="filt_")
+    check_moments(f, g, name + ("_sigma" if sigma_points else "_closed"), prefix="filt_")
 
 
 def _tag():
@@ -229,12 +233,28 @@ def test_batched_parameters_and_shared_data():
     assert scaled_err(f.predicted_covariances, r["predicted_covariances"]) < TOL
 
 
-def test_nonfinite_and_max_steps_status():
-    """Numerical failure is not an error: NaN outputs + status (SURVEY 8b 'Errors')."""
+def test_nonfinite_and_max_steps_status(monkeypatch):
+    """Numerical failure is not an error at the C ABI: NaN outputs + status (SURVEY 8b 'Errors').  The Python shim turns
+    status 2 into an exception for host callers, as diffrax does when max_steps is reached."""
     import torch
+    from cd_dynamax_b200 import _engine as E
     from cd_dynamax_b200 import _lib as L
     from cd_dynamax_b200.continuous_discrete_nonlinear_gaussian_ssm._common import run_filter
     cd = api()
+    t0, y0 = c3_problem(4, 6)
+    with pytest.raises(E.MaxStepsReached):
+        cd.cdnlgssm_filter(nonlinear_params_api(dict(
+            m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]), L=np.eye(3),
+            Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))), y0, t0[..., None],
+            cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025, "max_steps": 2}))
+    # device-resident callers stay asynchronous: no exception, the status tensor is there to inspect
+    fdev = cd.cdnlgssm_filter(nonlinear_params_api(dict(
+        m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]), L=np.eye(3),
+        Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))), torch.as_tensor(y0).cuda(),
+        torch.as_tensor(t0).cuda()[..., None],
+        cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025, "max_steps": 2}))
+    assert fdev.marginal_loglik.is_cuda and (E.last_status().cpu().numpy() == 2).all()
+    monkeypatch.setattr(E, "RAISE_ON_MAX_STEPS", False)
     N, K = 8, 10
     t, y = c3_problem(N, K)
     g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]),

@@ -152,9 +152,51 @@ def test_call_conventions_of_the_notebooks():
     assert cum.marginal_loglik.shape == (K,) and abs(cum.marginal_loglik[-1] - full.marginal_loglik) < 1e-12 * abs(full.marginal_loglik)
     nm = cd.ContDiscreteNonlinearGaussianSSM(state_dim=4, emission_dim=2)
     assert nm.marginal_log_prob(pn, y) == full.marginal_loglik
+    # batched emissions with a SHARED time grid (t_emissions=None, one [K,1] column, or a [1,K,1] array) broadcast it
+    Yb = rng.standard_normal((5, K, 2))
+    tg = np.cumsum(rng.uniform(0.5, 1.5, K))
+    fb0 = cd.cdlgssm_filter(p, Yb)
+    fb1 = cd.cdlgssm_filter(p, Yb, np.arange(K, dtype=np.float64)[:, None])
+    assert np.array_equal(fb0.filtered_means, fb1.filtered_means)
+    fb2 = cd.cdlgssm_filter(p, Yb, tg[:, None])
+    fb3 = cd.cdlgssm_filter(p, Yb, np.repeat(tg[None, :, None], 5, 0))
+    fb4 = cd.cdnlgssm_filter(pn, Yb, tg[None, :, None])
+    assert np.array_equal(fb2.predicted_covariances, fb3.predicted_covariances)
+    assert np.array_equal(fb4.filtered_means[3], cd.cdnlgssm_filter(pn, Yb[3], tg[:, None]).filtered_means)
+    # the nonlinear registry models take no inputs: zeros are accepted, anything else is refused (never dropped silently)
+    assert np.array_equal(cd.cdnlgssm_filter(pn, y, inputs=np.zeros((K, 1))).filtered_means, full.filtered_means)
+    with pytest.raises(NotImplementedError):
+        cd.cdnlgssm_filter(pn, y, inputs=np.ones((K, 1)))
     # an empty batch is legal and returns empty arrays
     e = cd.cdlgssm_filter(p, np.zeros((0, K, 2)), np.zeros((0, K, 1)))
     assert e.filtered_means.shape == (0, K, 4) and e.marginal_loglik.shape == (0,)
+
+
+def test_diagonal_emission_covariance_takes_the_woodbury_branch():
+    """A 1-D emissions.cov (cd_linear/inference.py:240-254).  The Woodbury update is algebraically the diag(R) update, so
+    filtered and smoothed moments must agree with the full-matrix call (up to where the 1e-9 boost enters); the
+    log-likelihood does NOT (the reference broadcasts the vector over H P H^T, :613) except for a scalar emission.  The
+    literal numbers are pinned by the kf_diagR_* goldens (reference code on the NumPy shims)."""
+    cd = api()
+    g = _linear_model(seed=9)
+    rng = np.random.default_rng(2)
+    K = 20
+    y = rng.standard_normal((3, K, 2))
+    t = np.cumsum(rng.uniform(0.02, 0.08, (3, K)), axis=1)
+    Rd = np.array([0.3, 0.45])
+    p_full, p_diag = _lin_params(cd, dict(g, R=np.diag(Rd))), _lin_params(cd, dict(g, R=Rd))
+    hp = cd.KFHyperParams(dt_final=0.05, diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
+    a, b = cd.cdlgssm_smoother(p_full, y, t[..., None], hp), cd.cdlgssm_smoother(p_diag, y, t[..., None], hp)
+    # the 1e-9 boost sits on I + U^T X here and on S there: agreement to ~1e-8, not to rounding
+    np.testing.assert_allclose(b.filtered_means, a.filtered_means, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(b.filtered_covariances, a.filtered_covariances, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(b.smoothed_covariances, a.smoothed_covariances, rtol=1e-6, atol=1e-7)
+    assert not np.allclose(b.marginal_loglik, a.marginal_loglik, rtol=1e-6)  # the reference's broadcast, reproduced
+    g1 = dict(g, H=g["H"][:1])
+    a1 = cd.cdlgssm_filter(_lin_params(cd, dict(g1, R=np.array([[0.3]]))), y[..., :1], t[..., None], hp)
+    b1 = cd.cdlgssm_filter(_lin_params(cd, dict(g1, R=np.array([0.3]))), y[..., :1], t[..., None], hp)
+    np.testing.assert_allclose(b1.marginal_loglik, a1.marginal_loglik, rtol=1e-7)
+    np.testing.assert_allclose(b1.predicted_covariances, a1.predicted_covariances, rtol=1e-6, atol=1e-7)
 
 
 def test_loud_failures():
