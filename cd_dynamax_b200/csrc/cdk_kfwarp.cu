@@ -16,7 +16,7 @@
 //  * one warp = one trajectory also makes every per-step output row (n + n^2 doubles) one contiguous, coalesced store.
 //  * dimensions are padded to 16 x 16 / 8 x 16 with zeros (identity block for A), which leaves the arithmetic on the real
 //    entries unchanged.
-// Everything this fast path does not cover (Dopri5, inputs, fp32, n > 16, smoothers) stays on generic_filter_kernel.
+// Everything this fast path does not cover (inputs, fp32, n > 16, the type-2 smoother) stays on generic_filter_kernel.
 #include <stdlib.h>
 
 #include "cdk_common.cuh"
@@ -34,6 +34,14 @@ struct KwTab {
   int S;
   double a[6];  // chain tableau: stage i reads only stage i-1, with coefficient a[i]
   double b[6];
+  // poly != 0 (any tableau that is not a chain, i.e. Dopri5 -- the reference's DEFAULT solver, diffrax_utils.py:121-124):
+  // the pushforward ODEs are linear with constant coefficients, y' = Ly + g, and one explicit RK step of ANY tableau is
+  // then y + h sum_{j>=1} c_j (h L)^{j-1} (L y + g) with c_j = b^T A^{j-1} 1 (its stability polynomial): the same
+  // S applications of L as the S stages, evaluated by Horner's rule with THREE matrices in registers instead of the
+  // S stage increments a non-chain tableau would have to keep (6 x 2 x 2 KB per warp for Dopri5).  Same result as
+  // stepping through the stages up to rounding.
+  int poly;
+  double c[7];  // c[1..S]
 };
 
 struct F16 {
@@ -150,6 +158,7 @@ __device__ __forceinline__ void store_global(const double (&d)[2][2][2], double*
 // (A, Q) over [t0, t1] from (I, 0): dA = F A, dQ = F Q + Q F^T + L Qc L^T (cd_linear/inference.py:105-144) with the diffrax
 // ConstantStepSize stepping rule.  Results stay in registers (C-fragment layout); sYA / sYQ / sT are the warp's stage
 // buffers.  Returns true when max_steps was exceeded (results are NaN then, as in the reference).
+template <bool POLY>
 __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, const double tol, const int max_steps,
                                             const double t0, const double t1, const double* sF, const double* sLQL,
                                             const double* sRk, double* sYA, double* sYQ, double* sT, F16& yA, F16& yQ,
@@ -189,6 +198,54 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
       mm<false, false, 16, 2, 2>(accA.v, sRk, sYA);
       __syncwarp();
     }
+    if constexpr (POLY) {
+      // Horner evaluation of the step polynomial (see KwTab): v = L y + g, w = c_S v, w = c_j v + dt L w (j = S-1 .. 1),
+      // y += dt w; for A: L = F . , g = 0; for Q: L = F . + (F .)^T, g = L Qc L^T.  kA / kQ hold v, iA / iQ hold w.
+      F16 wA, wQ;
+#pragma unroll 1
+      for (int j = tab.S; j >= 1; --j) {
+        const bool first = j == tab.S;
+        // operand of this application of L: y for the first pass (-> v), w afterwards
+        if (!fastA) store_c<2, 2>(first ? yA.v : wA.v, sYA);
+        store_c<2, 2>(first ? yQ.v : wQ.v, sYQ);
+        __syncwarp();
+        F16 fa, fq, fqt;
+        if (fastA) {
+          mm<false, false, 16, 2, 2>(fq.v, sF, sYQ);
+        } else {
+          mm2_shared_a(fa.v, fq.v, sF, sYA, sYQ);
+        }
+        store_c<2, 2>(fq.v, sT);
+        __syncwarp();
+        load_ct(fqt.v, sT);
+        if (first) {
+          F16 lq;
+          load_c<2, 2>(lq.v, sLQL);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            (&kQ.v[0][0][0])[i] = ((&fq.v[0][0][0])[i] + (&fqt.v[0][0][0])[i]) + (&lq.v[0][0][0])[i];
+            (&wQ.v[0][0][0])[i] = tab.c[j] * (&kQ.v[0][0][0])[i];
+            if (!fastA) {
+              (&kA.v[0][0][0])[i] = (&fa.v[0][0][0])[i];
+              (&wA.v[0][0][0])[i] = tab.c[j] * (&fa.v[0][0][0])[i];
+            }
+          }
+        }
+        if (!first) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            (&wQ.v[0][0][0])[i] = fma(dt, (&fq.v[0][0][0])[i] + (&fqt.v[0][0][0])[i], tab.c[j] * (&kQ.v[0][0][0])[i]);
+            if (!fastA) (&wA.v[0][0][0])[i] = fma(dt, (&fa.v[0][0][0])[i], tab.c[j] * (&kA.v[0][0][0])[i]);
+          }
+        }
+        __syncwarp();
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        (&accQ.v[0][0][0])[i] = fma(dt, (&wQ.v[0][0][0])[i], (&yQ.v[0][0][0])[i]);
+        if (!fastA) (&accA.v[0][0][0])[i] = fma(dt, (&wA.v[0][0][0])[i], (&yA.v[0][0][0])[i]);
+      }
+    } else {
 #pragma unroll 1
     for (int st = 0; st < tab.S; ++st) {
       // stage input y + a dt k_{st-1} -> shared memory (B operand)
@@ -231,6 +288,7 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
       }
       __syncwarp();
     }
+    }
     yA = accA;
     yQ = accQ;
     ++nsteps;
@@ -243,6 +301,7 @@ __device__ __forceinline__ bool pushforward(const KwTab& tab, const double dt0, 
 }
 
 // Rk = one explicit RK step of length dt0 of dA = F A applied to the identity (chain tableau), into sRk.
+template <bool POLY>
 __device__ __forceinline__ void rk_map(const KwTab& tab, const double dt0, const double* sF, double* sRk, double* sYA) {
   const int lane = threadIdx.x & 31, gid = lane >> 2, tig = lane & 3;
   F16 eye, acc, kA;
@@ -253,6 +312,31 @@ __device__ __forceinline__ void rk_map(const KwTab& tab, const double dt0, const
 #pragma unroll
       for (int r = 0; r < 2; ++r) eye.v[rb][cb][r] = (8 * rb + gid == 8 * cb + 2 * tig + r) ? 1.0 : 0.0;
   acc = eye;
+  if constexpr (POLY) {  // Rk = I + h sum_j c_j (h F)^{j-1} F by Horner: v = F, w = c_S v, w = c_j v + h F w, Rk = I + h w
+    F16 v, w;
+#pragma unroll 1
+    for (int j = tab.S; j >= 1; --j) {
+      const bool first = j == tab.S;
+      store_c<2, 2>(first ? eye.v : w.v, sYA);
+      __syncwarp();
+      mm<false, false, 16, 2, 2>(kA.v, sF, sYA);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (first) {
+          (&v.v[0][0][0])[i] = (&kA.v[0][0][0])[i];
+          (&w.v[0][0][0])[i] = tab.c[j] * (&kA.v[0][0][0])[i];
+        } else {
+          (&w.v[0][0][0])[i] = fma(dt0, (&kA.v[0][0][0])[i], tab.c[j] * (&v.v[0][0][0])[i]);
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) (&acc.v[0][0][0])[i] = fma(dt0, (&w.v[0][0][0])[i], (&eye.v[0][0][0])[i]);
+    store_c<2, 2>(acc.v, sRk);
+    __syncwarp();
+    return;
+  }
 #pragma unroll 1
   for (int st = 0; st < tab.S; ++st) {
     F16 iA = eye;
@@ -336,6 +420,7 @@ struct KwSmemCounts {
   static constexpr int PER_MODEL = KW_MODEL;  // F, LQL, H, R, b, d, Rk
 };
 
+template <bool POLY>
 __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp, const int use_rk) {
   extern __shared__ __align__(16) double kw_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gid = lane >> 2, tig = lane & 3;
@@ -401,7 +486,7 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
       sLQL[i * KW_LD + j] = s;
     }
     __syncwarp();
-    rk_map(tab, d.dt0, sF, model + KW_RK_OFF, sYA);
+    rk_map<POLY>(tab, d.dt0, sF, model + KW_RK_OFF, sYA);
   }
   __syncthreads();  // the only CTA-wide barrier: the shared model block is ready
   if (traj >= d.N) return;
@@ -534,7 +619,7 @@ __global__ void __launch_bounds__(32 * KW_WPC, 3) kf_warp_filter(const KArgs<dou
     }
     // ================= pushforward (A, Q) over [t0, t1] from (I, 0)  (:105-144; diffrax ConstantStepSize) =================
     F16 yA, yQ;
-    if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sRk, sYA, sYQ, sT, yA, yQ, (use_rk & 2) != 0)) status = 2;
+    if (pushforward<POLY>(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sRk, sYA, sYQ, sT, yA, yQ, (use_rk & 2) != 0)) status = 2;
     if (AQ && k + 1 < K) {  // CDK_FLAG_KEEP_PUSHFORWARD: the type-1 smoother will read (A_k, Q_k) back
       double* dst = AQ + ((traj * (long long)(K - 1) + k) * 2) * n * n;
       store_global(yA.v, dst, n);
@@ -585,6 +670,7 @@ struct KsSmemCounts {
   static constexpr int PER_WARP = 6 * KW_MAT + 5 * 16;
 };
 
+template <bool POLY>
 __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<double> a, const __grid_constant__ KwTab tab, const int model_per_warp, const int use_rk) {
   extern __shared__ __align__(16) double kw_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -613,7 +699,7 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
   if (model_per_warp || warp == 0) {
     load_model_kw(a, tj, model, sYA, sYQ, sT);
     __syncwarp();
-    rk_map(tab, d.dt0, sF, model + KW_RK_OFF, sYA);
+    rk_map<POLY>(tab, d.dt0, sF, model + KW_RK_OFF, sYA);
   }
   __syncthreads();  // the only CTA-wide barrier: the shared model block is ready
   if (traj >= d.N) return;
@@ -654,7 +740,7 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
       const double* src = AQ + ((traj * (long long)(K - 1) + k) * 2) * n * n;
       load_global(yA.v, src, n);
       load_global(yQ.v, src + n * n, n);  // (zero padding: the padded rows of P_f are zero, so A's identity pad is moot)
-    } else if (pushforward(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sRk, sYA, sYQ, sT, yA, yQ, (use_rk & 2) != 0)) {
+    } else if (pushforward<POLY>(tab, dt0, tol, d.max_steps, t0, t1, sF, sLQL, sRk, sYA, sYQ, sT, yA, yQ, (use_rk & 2) != 0)) {
       status = 2;
     }
     store_c<2, 2>(yA.v, sYA);
@@ -767,8 +853,8 @@ __global__ void __launch_bounds__(32 * KS_WPC, 2) kf_warp_smooth(const KArgs<dou
 
 }  // namespace
 
-// Fast path coverage: KF filter and type-1 smoother, fp64, n <= 16, m <= 8, no inputs, chain tableaux (every solver
-// except Dopri5).
+// Fast path coverage: KF filter and type-1 smoother, fp64, n <= 16, m <= 8, no inputs, every solver of the registry (chain
+// tableaux through their stages, Dopri5 -- the reference default -- through its step polynomial).
 template <typename T>
 int launch_kf_warp(int algo, const KArgs<T>& a, cudaStream_t s) {
   return CDK_E_UNSUPPORTED;
@@ -779,14 +865,11 @@ bool kf_warp_eligible(const cdk_desc& d, bool smooth) {
     const char* e = getenv("CDK_KF_WARP");
     return e && e[0] == '0';
   }();
-  if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0 || d.solver == CDK_DOPRI5) return false;
+  if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0) return false;
   if (!smooth && (d.reserved[2] & CDK_FLAG_DIAG_R)) return false;  // the Woodbury update lives in the generic kernel
   if (smooth && d.smoother_type != 1) return false;  // type 2 (backward ODE) stays on the generic kernel
   RtTab rt;
-  if (!fill_rt_tab(d.solver, rt)) return false;
-  for (int i = 0; i < 6; ++i)
-    if (rt.nnz[i] > 1 || (rt.nnz[i] == 1 && rt.col[i][0] != i - 1)) return false;  // not a chain tableau
-  return true;
+  return fill_rt_tab(d.solver, rt);  // chain tableaux step through the stages, the others (Dopri5) through the polynomial
 }
 
 template <>
@@ -798,10 +881,29 @@ int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
   if (!fill_rt_tab(d.solver, rt)) return CDK_E_ENUM;
   KwTab tab;
   tab.S = rt.S;
+  tab.poly = 0;
   for (int i = 0; i < 6; ++i) {
-    if (rt.nnz[i] > 1 || (rt.nnz[i] == 1 && rt.col[i][0] != i - 1)) return CDK_E_UNSUPPORTED;  // not a chain tableau
+    if (rt.nnz[i] > 1 || (rt.nnz[i] == 1 && rt.col[i][0] != i - 1)) tab.poly = 1;  // not a chain tableau
     tab.a[i] = rt.nnz[i] ? rt.val[i][0] : 0.0;
     tab.b[i] = rt.b[i];
+  }
+  {
+    // c_j = b^T A^{j-1} 1, j = 1 .. S (the coefficients of the step polynomial; c_1 = sum b = 1 for a consistent method)
+    double Adense[6][6] = {};
+    for (int i = 0; i < rt.S; ++i)
+      for (int q = 0; q < rt.nnz[i]; ++q) Adense[i][rt.col[i][q]] = rt.val[i][q];
+    double vec[6];
+    for (int i = 0; i < 6; ++i) vec[i] = i < rt.S ? 1.0 : 0.0;
+    for (int j = 0; j < 7; ++j) tab.c[j] = 0.0;
+    for (int j = 1; j <= rt.S; ++j) {
+      double cj = 0.0;
+      for (int i = 0; i < rt.S; ++i) cj += rt.b[i] * vec[i];
+      tab.c[j] = cj;
+      double nv[6] = {};
+      for (int i = 0; i < rt.S; ++i)
+        for (int q = 0; q < rt.S; ++q) nv[i] += Adense[i][q] * vec[q];
+      for (int i = 0; i < 6; ++i) vec[i] = nv[i];
+    }
   }
   const uint32_t model_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) | (1u << CDK_IN_R) |
                               (1u << CDK_IN_B) | (1u << CDK_IN_D);
@@ -814,18 +916,20 @@ int launch_kf_warp<double>(int algo, const KArgs<double>& a, cudaStream_t s) {
     const size_t smem = sizeof(double) * ((model_per_warp ? KS_WPC : 1) * KwSmemCounts::PER_MODEL + KS_WPC * KsSmemCounts::PER_WARP);
     const long long blocks = (d.N + KS_WPC - 1) / KS_WPC;
     if (blocks > 2147483647LL) return CDK_E_SIZE;
-    if (cudaFuncSetAttribute(kf_warp_smooth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    auto ks = tab.poly ? kf_warp_smooth<true> : kf_warp_smooth<false>;
+    if (cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(kf_warp_smooth)");
-    kf_warp_smooth<<<(unsigned)blocks, 32 * KS_WPC, smem, s>>>(a, tab, model_per_warp, use_rk);
+    ks<<<(unsigned)blocks, 32 * KS_WPC, smem, s>>>(a, tab, model_per_warp, use_rk);
     note_launch();
     return check_launch("kf_warp_smooth");
   }
   const size_t smem = sizeof(double) * ((model_per_warp ? KW_WPC : 1) * KwSmemCounts::PER_MODEL + KW_WPC * KwSmemCounts::PER_WARP);
   const long long blocks = (d.N + KW_WPC - 1) / KW_WPC;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
-  if (cudaFuncSetAttribute(kf_warp_filter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  auto kf = tab.poly ? kf_warp_filter<true> : kf_warp_filter<false>;
+  if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(kf_warp_filter)");
-  kf_warp_filter<<<(unsigned)blocks, 32 * KW_WPC, smem, s>>>(a, tab, model_per_warp, use_rk);
+  kf<<<(unsigned)blocks, 32 * KW_WPC, smem, s>>>(a, tab, model_per_warp, use_rk);
   note_launch();
   return check_launch("kf_warp_filter");
 }

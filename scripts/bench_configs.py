@@ -85,12 +85,17 @@ def c2(scale):
     hp = cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
     ms_f = timeit(lambda: cd.cdlgssm_filter(p, y, t[..., None], hp))
     ms_s = timeit(lambda: cd.cdlgssm_smoother(p, y, t[..., None], hp))
+    hp_def = cd.KFHyperParams()  # the reference's defaults: Dopri5, dt0 = 0.01 (diffrax_utils.py:50, :121-124)
+    ms_fd = timeit(lambda: cd.cdlgssm_filter(p, y, t[..., None], hp_def))
+    ms_sd = timeit(lambda: cd.cdlgssm_smoother(p, y, t[..., None], hp_def))
     q = 4.5
     fl_f = (74752 * q + 23915) * N * K
     fl_s = fl_f + 52500 * N * K  # the type-1 smoother reads the filter's (A, Q) back instead of re-integrating them
     return dict(config=f"C2 KF n=16 m=4 N={N} (of 262,144) K=500", filter_ms=ms_f, filter_obs_steps_per_s=N * K / ms_f * 1e3,
                 filter_tflops_survey=fl_f / ms_f / 1e9, smoother_ms=ms_s, smoother_obs_steps_per_s=N * K / ms_s * 1e3,
-                smoother_tflops_executed=fl_s / ms_s / 1e9)
+                smoother_tflops_executed=fl_s / ms_s / 1e9,
+                default_hyperparams_dopri5=dict(filter_ms=ms_fd, filter_obs_steps_per_s=N * K / ms_fd * 1e3,
+                                                smoother_ms=ms_sd, smoother_obs_steps_per_s=N * K / ms_sd * 1e3))
 
 
 def c3(scale):
