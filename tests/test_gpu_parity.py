@@ -571,3 +571,33 @@ def test_ekf_loglik_gradient_all_parameter_groups():
     assert np.allclose(grads["diffusion_cov"], np.swapaxes(grads["diffusion_cov"], 1, 2))
     ll2, g2 = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp)
     assert set(g2) == {"sigma", "rho", "beta"} and np.array_equal(g2["rho"], grads["rho"]) and np.array_equal(ll2, ll)
+
+
+def test_streaming_filter_in_chunks_matches_one_call():
+    """cd_dynamax_b200.streaming.filter_in_chunks (how BASELINE config 2's 285 GB of moments are produced and consumed
+    chunk by chunk): double-buffered host->device staging must give bit-identical results to one resident call."""
+    import torch
+    from cd_dynamax_b200 import streaming
+    cd = api()
+    gl = load_golden("kf_n16_rk4")
+    rng = np.random.default_rng(0)
+    N, K = 53, 20
+    y = torch.as_tensor(rng.standard_normal((N, K, 4))).pin_memory()
+    t = torch.as_tensor(np.cumsum(0.04 * rng.uniform(0.5, 1.5, (N, K)), axis=1)[..., None]).pin_memory()
+    p = linear_params_api({k: (torch.as_tensor(v).cuda() if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.size else v)
+                           for k, v in gl.items() if k in ("m0", "P0", "F", "b", "B", "L", "Qc", "H", "d", "D", "R")})
+    p = p._replace(dynamics=p.dynamics._replace(input_weights=None), emissions=p.emissions._replace(input_weights=None))
+    hp = cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
+    ref = cd.cdlgssm_filter(p, y.cuda(), t.cuda(), hp)
+    got_ll = torch.empty(N, dtype=torch.float64, device="cuda")
+    got_pp = torch.empty_like(ref.predicted_covariances)
+    seen = []
+
+    def consume(post, lo, hi):
+        got_ll[lo:hi] = post.marginal_loglik
+        got_pp[lo:hi] = post.predicted_covariances
+        seen.append((lo, hi))
+
+    streaming.filter_in_chunks(lambda yy, tt: cd.cdlgssm_filter(p, yy, tt, hp), y, t, 16, consume)
+    assert seen == [(0, 16), (16, 32), (32, 48), (48, 53)]
+    assert torch.equal(got_ll, ref.marginal_loglik) and torch.equal(got_pp, ref.predicted_covariances)
