@@ -10,7 +10,9 @@ from .continuous_discrete_nonlinear_gaussian_ssm import (ContDiscreteNonlinearGa
                                                          LearnableLorenz96, LearnableMatrix, LearnableQuadratic,
                                                          LearnableVector, ParamsCDNLGSSM, ParamsCDNLGSSMDynamics,
                                                          ParamsCDNLGSSMEmissions, UKFHyperParams, cdnlgssm_filter,
-                                                         cdnlgssm_smoother, ekf_marginal_log_prob_and_grad)
+                                                         cdnlgssm_smoother, ekf_marginal_log_prob_and_grad, GSSMForecast,
+                                                         MultivariateNormalFullCovariance, cdnlgssm_emissions,
+                                                         cdnlgssm_forecast, cdnlgssm_path_sample)
 from .types import (ParameterProperties, ParamsLGSSMEmissions, ParamsLGSSMInitial, PosteriorGSSMFiltered,
                     PosteriorGSSMSmoothed)
 

@@ -114,7 +114,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
         desc_fields: dict, theta_core_ndim: int = 1, scross_rows: Optional[int] = None,
         status: Optional[torch.Tensor] = None, host_out: bool = False,
         dev_inputs: Optional[dict] = None, scratch: Optional[torch.Tensor] = None,
-        core_ndim_override: Optional[dict] = None) -> Dict[int, torch.Tensor]:
+        core_ndim_override: Optional[dict] = None, t_cols: Optional[int] = None,
+        out_shapes: Optional[dict] = None) -> Dict[int, torch.Tensor]:
     """Call one C-ABI entry point. `inputs` maps slot -> array-like (None = absent); a leading N marks it batched.
     Returns slot -> tensor for every slot in `want` (+ OUT_STATUS): device tensors, or -- with `host_out`, which the
     API shims set when the caller handed in host arrays -- pinned host tensors whose copies have completed.
@@ -167,7 +168,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     d.batched_mask = mask
     nchunks = STREAM_CHUNKS if (stream_bytes >= STREAM_MIN_BYTES and N >= 2 * STREAM_CHUNKS) else 1
     if host_out and N >= 2 * STREAM_CHUNKS:
-        out_bytes = sum(int(np.prod(_out_shape(s, N, K, n, scross_rows, int(desc_fields.get("n_theta", 0))),
+        out_bytes = sum(int(np.prod(out_shapes[s] if out_shapes and s in out_shapes else
+                                    _out_shape(s, N, K, n, scross_rows, int(desc_fields.get("n_theta", 0))),
                                     dtype=np.int64)) * esz for s in want)
         if out_bytes >= STREAM_MIN_BYTES:
             nchunks = STREAM_CHUNKS
@@ -190,8 +192,9 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     # ---- outputs ----
     out = {}
     for slot in want:
-        out[slot] = torch.empty(_out_shape(slot, N, K, n, scross_rows, int(desc_fields.get("n_theta", 0))), dtype=tdt,
-                                device=dev)
+        shp = out_shapes[slot] if out_shapes and slot in out_shapes else \
+            _out_shape(slot, N, K, n, scross_rows, int(desc_fields.get("n_theta", 0)))
+        out[slot] = torch.empty(shp, dtype=tdt, device=dev)
     if status is None:
         status = torch.zeros((N,), dtype=torch.int32, device=dev)
     out[L.OUT_STATUS] = status

@@ -15,10 +15,13 @@ ORDERS = {"zeroth": 0, "first": 1, "second": 2}
 FLAG_KEEP_PUSHFORWARD = 1  # CDK_FLAG_KEEP_PUSHFORWARD (desc.reserved[2])
 FLAG_UKF_SIGMA_POINTS = 2  # CDK_FLAG_UKF_SIGMA_POINTS
 FLAG_DIAG_R = 4  # CDK_FLAG_DIAG_R: in[IN_R] is the [m] diagonal of the emission covariance
+FLAG_PREDICT_ONLY = 8  # CDK_FLAG_PREDICT_ONLY: forecast (no updates), in[IN_T] is [N, K+1]
+FLAG_FIXED_INIT = 16  # CDK_FLAG_FIXED_INIT: cdk_sample_path starts from in[IN_M0] at t_init
 GRAD_COLS_L63 = 23  # CDK_GRAD_COLS_L63: columns of out[CDK_OUT_GRAD]
 ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
 ENTRY_POINTS.append("cdk_ekf_grad_f64")
+ENTRY_POINTS += ["cdk_sample_path_f64", "cdk_sample_path_f32", "cdk_emission_moments_f64", "cdk_emission_moments_f32"]
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
                  "cdk_xla_custom_call", "cdk_xla_custom_call_status", "cdk_xla_last_rc", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
                  "cdk_last_error"]

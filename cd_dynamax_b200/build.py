@@ -16,7 +16,7 @@ CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "build")
 LIBDIR = os.path.join(PKG, "lib")
 LIB = os.path.join(LIBDIR, "libcdk.so")
-SOURCES = ["cdk_api.cu", "cdk_small.cu", "cdk_generic.cu", "cdk_enkf.cu", "cdk_kfwarp.cu"]
+SOURCES = ["cdk_api.cu", "cdk_small.cu", "cdk_generic.cu", "cdk_enkf.cu", "cdk_kfwarp.cu", "cdk_aux.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr",
     "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC,

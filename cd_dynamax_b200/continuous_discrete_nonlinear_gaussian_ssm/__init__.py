@@ -1,4 +1,4 @@
-# mirrors src/continuous_discrete_nonlinear_gaussian_ssm/__init__.py:1-7 (cdnlgssm_forecast is out of scope)
+# mirrors src/continuous_discrete_nonlinear_gaussian_ssm/__init__.py:1-7
 from .cdnlgssm_utils import (GSSMForecast, LearnableLinear, LearnableLorenz63, LearnableLorenz96, LearnableMatrix,
                              LearnableQuadratic, LearnableVector, ParamsCDNLGSSM, ParamsCDNLGSSMDynamics,
                              ParamsCDNLGSSMEmissions)
@@ -8,3 +8,5 @@ from .inference_ekf import (EKFHyperParams, ekf_marginal_log_prob_and_grad, exte
 from .inference_enkf import EnKFHyperParams, ensemble_kalman_filter
 from .inference_ukf import UKFHyperParams, unscented_kalman_filter
 from .models import ContDiscreteNonlinearGaussianSSM, cdnlgssm_filter, cdnlgssm_smoother
+from .forecast import (MultivariateNormalFullCovariance, cdnlgssm_emissions, cdnlgssm_forecast,  # noqa: E402
+                       cdnlgssm_path_sample)

@@ -1,6 +1,6 @@
 """Drop-in for the dispatchers and the model shell in src/continuous_discrete_nonlinear_gaussian_ssm/models.py:
 cdnlgssm_filter :658-718, cdnlgssm_smoother :720-764, ContDiscreteNonlinearGaussianSSM.initialize :172-290 and
-.marginal_log_prob :393-408.  Sampling / forecasting helpers are out of scope."""
+.marginal_log_prob :393-408.  Forecasts, emission moments and path sampling live in forecast.py (models.py:525-656, :767-1047)."""
 from typing import List, Optional
 
 import numpy as np
@@ -12,6 +12,7 @@ from .cdnlgssm_utils import (LearnableLinear, LearnableMatrix, LearnableVector, 
 from .inference_ekf import EKFHyperParams, iterated_extended_kalman_filter, iterated_extended_kalman_smoother
 from .inference_enkf import EnKFHyperParams, ensemble_kalman_filter
 from .inference_ukf import UKFHyperParams, unscented_kalman_filter
+from .forecast import cdnlgssm_path_sample
 
 
 def cdnlgssm_filter(params, emissions, t_emissions=None, hyperparams=EKFHyperParams(), inputs=None,
@@ -106,8 +107,23 @@ class ContDiscreteNonlinearGaussianSSM:
 
     smoother = filter
 
-    def _unsupported(self, *a, **k):
-        raise NotImplementedError("outside the hot path this package replaces (sampling / forecast / fit_*); "
-                                  "use the reference implementation for these")
+    def sample(self, params, key, num_timesteps, t_emissions=None, inputs=None, transition_type="distribution"):
+        """SSM.sample (src/ssm_temissions.py:227-330) for transition_type="path": one SDE sample path and its emissions
+        (cdnlgssm_path_sample, models.py:525-656).  The Gaussian-transition sampler ("distribution") is not provided."""
+        if transition_type != "path":
+            raise NotImplementedError('only transition_type="path" (the SDE sampler) is provided; the Gaussian-transition '
+                                      'sampler ("distribution") stays with the reference')
+        return cdnlgssm_path_sample(params, key, num_timesteps, t_emissions, inputs, self._diffeqsolve_settings)
 
-    sample = fit_sgd = fit_mcmc = fit_em = _unsupported
+    def sample_batch(self, params, key, num_sequences, num_timesteps, t_emissions=None, inputs=None,
+                     transition_type="distribution"):
+        """SSM.sample_batch (src/ssm_temissions.py:187-225): all `num_sequences` paths in one kernel launch."""
+        if transition_type != "path":
+            raise NotImplementedError('only transition_type="path" (the SDE sampler) is provided')
+        return cdnlgssm_path_sample(params, key, num_timesteps, t_emissions, inputs, self._diffeqsolve_settings,
+                                    num_sequences=num_sequences)
+
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("outside the hot path this package replaces (fit_*); use the reference implementation")
+
+    fit_sgd = fit_mcmc = fit_em = _unsupported

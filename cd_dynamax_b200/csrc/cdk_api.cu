@@ -34,7 +34,7 @@ static long long slot_elems(const cdk_desc& d, int slot, int algo) {
   const long long n = d.n, m = d.m, K = d.K, du = d.d_u;
   switch (slot) {
     case CDK_IN_Y: return K * m;
-    case CDK_IN_T: return K;
+    case CDK_IN_T: return (d.reserved[2] & (CDK_FLAG_PREDICT_ONLY | CDK_FLAG_FIXED_INIT)) ? K + 1 : K;
     case CDK_IN_U: return K * du;
     case CDK_IN_M0: return n;
     case CDK_IN_P0: return n * n;
@@ -74,7 +74,7 @@ static int validate(const cdk_desc* d, const void* const* in, void* const* out, 
   if (d->max_steps < 1) return fail(CDK_E_SIZE, "max_steps must be >= 1");
   const bool linear = algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH;
   const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
-  if (!linear) {
+  if (!linear && algo != ALGO_EMISSIONS) {
     if (d->drift_id < CDK_DRIFT_LINEAR || d->drift_id > CDK_DRIFT_QUADRATIC) return fail(CDK_E_ENUM, "unknown drift_id");
     if (d->emission_id != CDK_EMISSION_LINEAR) return fail(CDK_E_ENUM, "unknown emission_id");
     if (d->n_theta != expected_theta(*d)) return fail(CDK_E_SIZE, "n_theta does not match drift_id / n");
@@ -92,16 +92,35 @@ static int validate(const cdk_desc* d, const void* const* in, void* const* out, 
     if (d->E < 2 || d->E > 65536) return fail(CDK_E_SIZE, "E out of range");
     if (d->solver != CDK_EULER && d->solver != CDK_HEUN) return fail(CDK_E_UNSUPPORTED, "EnKF supports solver euler (Euler-Maruyama) or heun");
   }
+  if (algo == ALGO_EMISSIONS) {
+    if (d->N > 0 && (!in[CDK_IN_FM] || !in[CDK_IN_H] || !in[CDK_IN_D] || !in[CDK_IN_R]))
+      return fail(CDK_E_NULL, "emission moments need the state means, H, d and R");
+    return CDK_OK;
+  }
+  if (algo == ALGO_SAMPLE) {
+    if (d->solver != CDK_EULER && d->solver != CDK_HEUN) return fail(CDK_E_UNSUPPORTED, "the sampler supports solver euler (Euler-Maruyama) or heun");
+    static const int req_s[] = {CDK_IN_T, CDK_IN_M0, CDK_IN_F, CDK_IN_L, CDK_IN_QC, CDK_IN_H, CDK_IN_D, CDK_IN_R};
+    if (d->N > 0) {
+      for (int s : req_s)
+        if (!in[s]) return fail(CDK_E_NULL, "a required input of the sampler is NULL");
+      if (!(d->reserved[2] & CDK_FLAG_FIXED_INIT) && !in[CDK_IN_P0]) return fail(CDK_E_NULL, "sampling x_0 needs P0");
+    }
+    return CDK_OK;
+  }
+  const bool ponly = (d->reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
+  if (ponly && smooth) return fail(CDK_E_UNSUPPORTED, "CDK_FLAG_PREDICT_ONLY applies to the filter entry points");
+  if (ponly && d->N > 0 && (out[CDK_OUT_FM] || out[CDK_OUT_FP] || out[CDK_OUT_LLCUM]))
+    return fail(CDK_E_UNSUPPORTED, "a forecast produces predicted moments only (PM / PP)");
   static const int req_lin[] = {CDK_IN_Y, CDK_IN_T, CDK_IN_M0, CDK_IN_P0, CDK_IN_F, CDK_IN_B, CDK_IN_L, CDK_IN_QC, CDK_IN_H, CDK_IN_D, CDK_IN_R};
   static const int req_nl[] = {CDK_IN_Y, CDK_IN_T, CDK_IN_M0, CDK_IN_P0, CDK_IN_F, CDK_IN_L, CDK_IN_QC, CDK_IN_H, CDK_IN_D, CDK_IN_R};
   if (d->N > 0) {
     if (linear) {
       for (int s : req_lin)
-        if (!in[s]) return fail(CDK_E_NULL, "a required input of the linear model is NULL");
+        if (!in[s] && !(ponly && s == CDK_IN_Y)) return fail(CDK_E_NULL, "a required input of the linear model is NULL");
       if (d->d_u > 0 && (!in[CDK_IN_U] || !in[CDK_IN_BU] || !in[CDK_IN_DU])) return fail(CDK_E_NULL, "d_u > 0 needs U, BU and DU");
     } else {
       for (int s : req_nl)
-        if (!in[s]) return fail(CDK_E_NULL, "a required input of the nonlinear model is NULL");
+        if (!in[s] && !(ponly && s == CDK_IN_Y)) return fail(CDK_E_NULL, "a required input of the nonlinear model is NULL");
     }
     if (smooth && (!in[CDK_IN_FM] || !in[CDK_IN_FP])) return fail(CDK_E_NULL, "smoothing needs the filtered moments");
     if (smooth && (!out[CDK_OUT_SM] || !out[CDK_OUT_SP])) return fail(CDK_E_NULL, "smoothing needs SM and SP outputs");
@@ -141,6 +160,14 @@ static int run(int algo, const cdk_desc* d, const void* const* in, void* const* 
     if (rc != CDK_E_UNSUPPORTED) return rc;
   }
   if (algo == ALGO_ENKF_FILTER) return launch_enkf<T>(a, s);
+  if (algo == ALGO_SAMPLE) {
+    rc = launch_sample_path<T>(a, s);
+    return rc == CDK_E_UNSUPPORTED ? fail(rc, "cdk_sample_path: model parameters must not be batched; solver euler or heun") : rc;
+  }
+  if (algo == ALGO_EMISSIONS) {
+    rc = launch_emission_moments<T>(a, s);
+    return rc == CDK_E_UNSUPPORTED ? fail(rc, "cdk_emission_moments: H, d, R must not be batched") : rc;
+  }
   return launch_generic<T>(algo, a, s);
 }
 
@@ -279,6 +306,10 @@ CDK_DEF(cdk_ukf_filter_f64, double, ALGO_UKF_FILTER)
 CDK_DEF(cdk_ukf_filter_f32, float, ALGO_UKF_FILTER)
 CDK_DEF(cdk_enkf_filter_f64, double, ALGO_ENKF_FILTER)
 CDK_DEF(cdk_enkf_filter_f32, float, ALGO_ENKF_FILTER)
+CDK_DEF(cdk_sample_path_f64, double, ALGO_SAMPLE)
+CDK_DEF(cdk_sample_path_f32, float, ALGO_SAMPLE)
+CDK_DEF(cdk_emission_moments_f64, double, ALGO_EMISSIONS)
+CDK_DEF(cdk_emission_moments_f32, float, ALGO_EMISSIONS)
 
 int cdk_ekf_grad_f64(const cdk_desc* d, const void* const* in, void* const* out, cdk_stream_t stream) {
   int rc = validate(d, in, out, ALGO_EKF_FILTER);
@@ -346,7 +377,9 @@ static int xla_dispatch(cdk_stream_t stream, void** buffers, const char* opaque,
       {"cdk_ekf_smooth_f64", cdk_ekf_smooth_f64}, {"cdk_ekf_smooth_f32", cdk_ekf_smooth_f32},
       {"cdk_ukf_filter_f64", cdk_ukf_filter_f64}, {"cdk_ukf_filter_f32", cdk_ukf_filter_f32},
       {"cdk_enkf_filter_f64", cdk_enkf_filter_f64}, {"cdk_enkf_filter_f32", cdk_enkf_filter_f32},
-      {"cdk_ekf_grad_f64", cdk_ekf_grad_f64}};
+      {"cdk_ekf_grad_f64", cdk_ekf_grad_f64},
+      {"cdk_sample_path_f64", cdk_sample_path_f64}, {"cdk_sample_path_f32", cdk_sample_path_f32},
+      {"cdk_emission_moments_f64", cdk_emission_moments_f64}, {"cdk_emission_moments_f32", cdk_emission_moments_f32}};
   for (auto& e : table)
     if (strcmp(e.name, op.entry_point) == 0) return e.fn(&op.desc, in, out, stream);
   return fail(CDK_E_ENUM, "xla custom call: unknown entry point");

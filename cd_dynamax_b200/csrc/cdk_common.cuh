@@ -180,6 +180,12 @@ int launch_enkf(const KArgs<T>& a, cudaStream_t s);
 template <typename T>
 int launch_kf_warp(int algo, const KArgs<T>& a, cudaStream_t s);
 
-enum { ALGO_KF_FILTER = 0, ALGO_KF_SMOOTH, ALGO_EKF_FILTER, ALGO_EKF_SMOOTH, ALGO_UKF_FILTER, ALGO_ENKF_FILTER };
+template <typename T>
+int launch_sample_path(const KArgs<T>& a, cudaStream_t s);
+template <typename T>
+int launch_emission_moments(const KArgs<T>& a, cudaStream_t s);
+
+enum { ALGO_KF_FILTER = 0, ALGO_KF_SMOOTH, ALGO_EKF_FILTER, ALGO_EKF_SMOOTH, ALGO_UKF_FILTER, ALGO_ENKF_FILTER, ALGO_SAMPLE,
+       ALGO_EMISSIONS };
 
 }  // namespace cdk

@@ -726,28 +726,32 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
   int status = 0;
   T* yv = c.p(L.YV);
   T* uv = c.p(L.UV);
+  // forecast (CDK_FLAG_PREDICT_ONLY): no updates; Tm holds K + 1 stamps, t_init first
+  const bool ponly = (d.reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
   for (int k = 0; k < K; ++k) {
     FOR_T(i, du) uv[i] = U[(long long)k * du + i];
     __syncthreads();
-    FOR_T(i, m) {
-      T v = Y[(long long)k * m + i];
-      if (du > 0) {  // y - D u (cd_linear/inference.py:258, :613)
-        const T* DU = c.p(L.DU);
-        for (int q = 0; q < du; ++q) v -= DU[i * du + q] * uv[q];
+    if (!ponly) {
+      FOR_T(i, m) {
+        T v = Y[(long long)k * m + i];
+        if (du > 0) {  // y - D u (cd_linear/inference.py:258, :613)
+          const T* DU = c.p(L.DU);
+          for (int q = 0; q < du; ++q) v -= DU[i * du + q] * uv[q];
+        }
+        yv[i] = v;
       }
-      yv[i] = v;
+      __syncthreads();
+      if (linear && (d.reserved[2] & CDK_FLAG_DIAG_R)) {
+        ll += condition_on_diag_r<T>(c);
+      } else {
+        ll += condition_on<T>(c, algo, algo == ALGO_EKF_FILTER ? d.num_iter : 1);
+      }
+      if (FM) FOR_T(i, n) FM[(row0 + k) * n + i] = mu[i];
+      if (FP) store_mat<T>(FP + (row0 + k) * n * n, P, n, n, ldn);
+      if (LLC && threadIdx.x == 0) LLC[row0 + k] = ll;
     }
-    __syncthreads();
-    if (linear && (d.reserved[2] & CDK_FLAG_DIAG_R)) {
-      ll += condition_on_diag_r<T>(c);
-    } else {
-      ll += condition_on<T>(c, algo, algo == ALGO_EKF_FILTER ? d.num_iter : 1);
-    }
-    if (FM) FOR_T(i, n) FM[(row0 + k) * n + i] = mu[i];
-    if (FP) store_mat<T>(FP + (row0 + k) * n * n, P, n, n, ldn);
-    if (LLC && threadIdx.x == 0) LLC[row0 + k] = ll;
     const T t0 = Tm[k];
-    const T t1 = k + 1 < K ? Tm[k + 1] : t0 + T(d.dt_final);
+    const T t1 = (ponly || k + 1 < K) ? Tm[k + 1] : t0 + T(d.dt_final);
     bool hit = false;
     if (linear) {
       // pushforward from (I, 0), then m = A m + B u + b, P = A P A^T + Q (cd_linear/inference.py:619-620)

@@ -867,6 +867,7 @@ bool kf_warp_eligible(const cdk_desc& d, bool smooth) {
   }();
   if (disabled || d.n > 16 || d.m > 8 || d.d_u != 0) return false;
   if (!smooth && (d.reserved[2] & CDK_FLAG_DIAG_R)) return false;  // the Woodbury update lives in the generic kernel
+  if (d.reserved[2] & CDK_FLAG_PREDICT_ONLY) return false;          // forecasts (no updates): generic kernel
   if (smooth && d.smoother_type != 1) return false;  // type 2 (backward ODE) stays on the generic kernel
   RtTab rt;
   return fill_rt_tab(d.solver, rt);  // chain tableaux step through the stages, the others (Dopri5) through the polynomial

@@ -469,12 +469,17 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
     for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
   }
-  const T* __restrict__ Yg = a.in[CDK_IN_Y] + trc * a.in_stride[CDK_IN_Y];
+  const T* __restrict__ Yg = a.in[CDK_IN_Y] ? a.in[CDK_IN_Y] + trc * a.in_stride[CDK_IN_Y] : nullptr;
   const T* __restrict__ Tg = a.in[CDK_IN_T] + trc * a.in_stride[CDK_IN_T];
+  // forecast (CDK_FLAG_PREDICT_ONLY): no updates, no observations; Tg holds K + 1 stamps per trajectory, t_init first
+  const bool ponly = (a.d.reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
+  const int KT = ponly ? K + 1 : K;
   auto prefetch = [&](int kk) {
-    if (kk < K) {
+    if (kk < KT) {
+      if (!ponly) {
 #pragma unroll
-      for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (LW_RING - 1)][c][lane], Yg + (long long)kk * NY + c);
+        for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (LW_RING - 1)][c][lane], Yg + (long long)kk * NY + c);
+      }
       cp_async_elem(&sm.inT[kk & (LW_RING - 1)][lane], Tg + kk);
     }
     cp_async_commit();
@@ -578,8 +583,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
 #pragma unroll
     for (int c = 0; c < NY; ++c) y[c] = sm.inY[k & (LW_RING - 1)][c][lane];
     T tprev = sm.inT[k & (LW_RING - 1)][lane];
-    const T t1 = k + 1 < K ? sm.inT[(k + 1) & (LW_RING - 1)][lane] : tprev + dtf;
-    if constexpr (NY == 1) {
+    const T t1 = k + 1 < KT ? sm.inT[(k + 1) & (LW_RING - 1)][lane] : tprev + dtf;
+    if (ponly) {
+      // forecast: the state is propagated, never updated
+    } else if constexpr (NY == 1) {
       if (lean) {
         // log N(y; H m + d, S) = -r^2 / (2 S) - log(S) / 2 - log(2 pi) / 2,  K = P H^T / (S + 1e-9),  P -= K S K^T
         // (inference_ekf.py:285-289, :153-199; psd_solve boost utils.py:204); the constant is added after the loop

@@ -143,6 +143,15 @@ typedef struct cdk_desc {
  * the update takes the reference's Woodbury branch (cd_linear/inference.py:240-254) and the log-likelihood its broadcast
  * of the vector over H P H^T (:613), both restated literally (csrc/cdk_generic.cu: condition_on_diag_r). */
 #define CDK_FLAG_DIAG_R 4
+/* reserved[2] bit 3: FORECAST (cdk_ekf_filter_*, cdk_ukf_filter_*, cdk_enkf_filter_*, cdk_kf_filter_*): no measurement
+ * updates.  in[CDK_IN_T] is [N, K+1] -- t_init followed by the K forecast times --, in[CDK_IN_Y] is ignored (may be NULL),
+ * (M0, P0) is the distribution at t_init and out[CDK_OUT_PM] / out[CDK_OUT_PP] [N, K, ...] receive the forecasted moments
+ * (forecast_extended_kalman_filter inference_ekf.py:679-761 and its UKF / EnKF twins: the same _predict, scanned). */
+#define CDK_FLAG_PREDICT_ONLY 8
+/* reserved[2] bit 4: cdk_sample_path_*: start from the given state in[CDK_IN_M0] at t_init instead of sampling
+ * x_0 ~ N(m0, P0); in[CDK_IN_T] is then [N, K+1] (t_init, then the K output times) and no emission is drawn at t_init
+ * (the point-estimate branch of cdnlgssm_forecast, cd_nonlinear/models.py:840-936). */
+#define CDK_FLAG_FIXED_INIT 16
 
 #define CDK_MAX_N 64
 #define CDK_MAX_M 64
@@ -175,6 +184,21 @@ CDK_DECL(cdk_enkf_filter_f32);
  * Lorenz-63 drift, scalar emission, num_iter = 1, state_order first / second; anything else returns CDK_E_UNSUPPORTED. */
 #define CDK_GRAD_COLS_L63 23
 CDK_DECL(cdk_ekf_grad_f64);
+
+/* Forward sample paths of the model (cdnlgssm_path_sample, cd_nonlinear/models.py:525-656; what
+ * SSM.sample_batch(..., transition_type="path") vmaps, src/ssm_temissions.py:187-225): x_0 ~ N(m0, P0), x_k = SDE solve of
+ * dx = f(x) dt + L chol(Qc) dW over [t_{k-1}, t_k] (desc.solver = CDK_HEUN, the reference default for SDEs, or CDK_EULER =
+ * Euler-Maruyama; diffrax stepping rule with desc.dt0), y_k ~ N(H x_k + d, R).  out[CDK_OUT_FM] = states [N, K, n],
+ * out[CDK_OUT_PM] = emissions [N, K, m] (either may be NULL), out[CDK_OUT_STATUS].  Philox4x32-10 stream keyed by
+ * desc.rng_seed / rng_offset (the reference's jax.random stream is not reproducible outside JAX).  Model parameters must
+ * not be batched (in[CDK_IN_M0] may be). */
+CDK_DECL(cdk_sample_path_f64);
+CDK_DECL(cdk_sample_path_f32);
+/* Emission moments of Gaussian state estimates under the linear emission (emissions_extended_kalman_filter,
+ * inference_ekf.py:762-855, and its unscented twin): in[CDK_IN_FM] [N, K, n], in[CDK_IN_FP] [N, K, n, n] or NULL (point
+ * estimates) -> out[CDK_OUT_PM] = H m + d [N, K, m], out[CDK_OUT_PP] = H P H^T + R [N, K, m, m]. */
+CDK_DECL(cdk_emission_moments_f64);
+CDK_DECL(cdk_emission_moments_f32);
 
 /* Bytes of device scratch the given entry point needs in out[CDK_OUT_SCRATCH] (0 for most). algo: "kf_filter", ... */
 size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point);

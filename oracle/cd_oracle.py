@@ -548,8 +548,11 @@ def extended_kalman_filter(
     num_iter=1,
     cov_rescaling=1.0,
     dtype=np.float64,
+    forecast=False,
 ):
-    """inference_ekf.py:202-326. y[N,K,m], t[N,K]."""
+    """inference_ekf.py:202-326. y[N,K,m], t[N,K].  forecast=True: forecast_extended_kalman_filter (:679-761) -- the same
+    _predict scanned with no updates; y is ignored (only its shape [N,K,m]), t is [N,K+1] with t_init first and
+    predicted_* hold the forecasted moments."""
     y = np.asarray(y, dtype)
     t = np.asarray(t, dtype)
     N, K, mdim = y.shape
@@ -559,7 +562,7 @@ def extended_kalman_filter(
     d = c(p.d if p.d is not None else np.zeros(mdim), 1)
     LQL = L @ Qc @ _mT(L)
     m, P = c(p.m0, 1).copy(), c(p.P0, 2).copy()
-    t0s, t1s = _gap_times(t, dt_final)
+    t0s, t1s = (t[:, :-1], t[:, 1:]) if forecast else _gap_times(t, dt_final)
     out = dict(
         filtered_means=np.zeros((N, K, n), dtype),
         filtered_covariances=np.zeros((N, K, n, n), dtype),
@@ -570,8 +573,11 @@ def extended_kalman_filter(
     ll = np.zeros(N, dtype)
     status = np.zeros(N, np.int32)
     for k in range(K):
-        ll = ll + mvn_logpdf(y[:, k], _mv(H, m) + d, H @ P @ _mT(H) + R)  # :285-286
-        mf, Pf = _ekf_condition_on(m, P, H, d, R, y[:, k], num_iter)  # :289
+        if forecast:
+            mf, Pf = m, P
+        else:
+            ll = ll + mvn_logpdf(y[:, k], _mv(H, m) + d, H @ P @ _mT(H) + R)  # :285-286
+            mf, Pf = _ekf_condition_on(m, P, H, d, R, y[:, k], num_iter)  # :289
         m, P, hit = _ekf_predict(mf, Pf, p.drift, LQL, t0s[:, k], t1s[:, k], state_order, settings, cov_rescaling, L, Qc)
         status[hit] = 2
         out["filtered_means"][:, k], out["filtered_covariances"][:, k] = mf, Pf
@@ -637,9 +643,10 @@ def _sigmas(m, P, n, lamb):
 
 
 def unscented_kalman_filter(
-    p: NonlinearParams, y, t, dt_final=1e-10, alpha=math.sqrt(3.0), beta=2.0, kappa=1.0, settings=SolverSettings(), dtype=np.float64
+    p: NonlinearParams, y, t, dt_final=1e-10, alpha=math.sqrt(3.0), beta=2.0, kappa=1.0, settings=SolverSettings(), dtype=np.float64,
+    forecast=False,
 ):
-    """inference_ukf.py:206-308."""
+    """inference_ukf.py:206-308.  forecast=True: forecast_unscented_kalman_filter (no updates; t is [N,K+1], t_init first)."""
     y = np.asarray(y, dtype)
     t = np.asarray(t, dtype)
     N, K, mdim = y.shape
@@ -650,7 +657,7 @@ def unscented_kalman_filter(
     LQL = L @ Qc @ _mT(L)
     lamb, w_m, w_c, W = ukf_weights(n, alpha, beta, kappa, np.dtype(dtype).type)
     m, P = c(p.m0, 1).copy(), c(p.P0, 2).copy()
-    t0s, t1s = _gap_times(t, dt_final)
+    t0s, t1s = (t[:, :-1], t[:, 1:]) if forecast else _gap_times(t, dt_final)
     out = dict(
         filtered_means=np.zeros((N, K, n), dtype),
         filtered_covariances=np.zeros((N, K, n, n), dtype),
@@ -670,17 +677,20 @@ def unscented_kalman_filter(
         return (dm, foo + _mT(foo) + LQL)
 
     for k in range(K):
-        # _condition_on :162-203
-        X = _sigmas(m, P, n, lamb)
-        Yp = np.einsum("nij,npj->npi", H, X) + d[:, None, :]
-        yhat = np.einsum("p,npi->ni", w_m, Yp)
-        dY = Yp - yhat[:, None, :]
-        S = np.einsum("p,npi,npj->nij", w_c, dY, dY) + R
-        C = np.einsum("p,npi,npj->nij", w_c, X - m[:, None, :], dY)
-        ll = ll + mvn_logpdf(y[:, k], yhat, S)  # :197
-        Kg = _mT(psd_solve(S, _mT(C)))  # :200
-        mf = m + _mv(Kg, y[:, k] - yhat)
-        Pf = P - Kg @ S @ _mT(Kg)  # :202 (no symmetrize)
+        if forecast:
+            mf, Pf = m, P
+        else:
+            # _condition_on :162-203
+            X = _sigmas(m, P, n, lamb)
+            Yp = np.einsum("nij,npj->npi", H, X) + d[:, None, :]
+            yhat = np.einsum("p,npi->ni", w_m, Yp)
+            dY = Yp - yhat[:, None, :]
+            S = np.einsum("p,npi,npj->nij", w_c, dY, dY) + R
+            C = np.einsum("p,npi,npj->nij", w_c, X - m[:, None, :], dY)
+            ll = ll + mvn_logpdf(y[:, k], yhat, S)  # :197
+            Kg = _mT(psd_solve(S, _mT(C)))  # :200
+            mf = m + _mv(Kg, y[:, k] - yhat)
+            Pf = P - Kg @ S @ _mT(Kg)  # :202 (no symmetrize)
         (m, P), _, hit = rk_solve(rhs, t0s[:, k], t1s[:, k], (mf, Pf), settings)
         status[hit] = 2
         out["filtered_means"][:, k], out["filtered_covariances"][:, k] = mf, Pf
@@ -758,8 +768,10 @@ def ensemble_kalman_filter(
     rng_offset=0,
     settings=SolverSettings(solver="euler"),
     dtype=np.float64,
+    forecast=False,
 ):
-    """inference_enkf.py:151-276 with an Euler-Maruyama (or Heun) SDE step and the shared Philox stream."""
+    """inference_enkf.py:151-276 with an Euler-Maruyama (or Heun) SDE step and the shared Philox stream.  forecast=True:
+    forecast_ensemble_kalman_filter (no updates; t is [N,K+1], t_init first)."""
     y = np.asarray(y, dtype)
     t = np.asarray(t, dtype)
     N, K, mdim = y.shape
@@ -773,7 +785,7 @@ def ensemble_kalman_filter(
     m0, P0 = c(p.m0, 1), c(p.P0, 2)
     z = enkf_normals(RNG_INIT, traj, 0, 0, E, n, seed, rng_offset).astype(dtype)
     X = m0[:, None, :] + np.einsum("nij,nej->nei", cholesky(P0), z)  # :260-262 (cholesky method)
-    t0s, t1s = _gap_times(t, dt_final)
+    t0s, t1s = (t[:, :-1], t[:, 1:]) if forecast else _gap_times(t, dt_final)
     out = dict(
         filtered_means=np.zeros((N, K, n), dtype),
         filtered_covariances=np.zeros((N, K, n, n), dtype),
@@ -792,7 +804,7 @@ def ensemble_kalman_filter(
         A = Z - mu[:, None, :]
         return mu, np.einsum("nei,nej->nij", A, A) / Em1
 
-    for k in range(K):
+    def update(X, k, ll):
         # _condition_on :92-148
         Y = np.einsum("nij,nej->nei", H, X) + d[:, None, :]
         ybar = np.mean(Y, axis=1)
@@ -810,6 +822,13 @@ def ensemble_kalman_filter(
         Kg = _mT(psd_solve(S, _mT(Cxy)))  # :143
         X = X + np.einsum("nij,nej->nei", Kg, Yobs - Y)  # :146
         mf, Pf = moments(X)  # :225-228
+        return X, ll, mf, Pf
+
+    for k in range(K):
+        if forecast:
+            mf, Pf = moments(X)
+        else:
+            X, ll, mf, Pf = update(X, k, ll)
         # _predict :47-89 -- per-member SDE solve over the gap
         tprev = t0s[:, k].copy()
         t1 = t1s[:, k]
@@ -852,3 +871,86 @@ def ensemble_kalman_filter(
     out["marginal_loglik"] = ll
     out["status"] = _finalize_status(status, ll)
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Forward sample paths (cd_nonlinear/models.py:525-656 cdnlgssm_path_sample; the point-estimate branch of
+# cdnlgssm_forecast :840-936) on the shared Philox stream -- restates csrc/cdk_aux.cu:sample_path_kernel.
+# --------------------------------------------------------------------------------------------------------------------
+def sample_paths(p: NonlinearParams, t, seed=0, rng_offset=0, settings=SolverSettings(solver="heun"), fixed_init=False,
+                 dtype=np.float64):
+    """States [N,K,n] and emissions [N,K,m].  x_0 ~ N(m0, P0) and y_0 at t[:,0]; then x_k = SDE solve over [t_{k-1}, t_k]
+    (Heun = the reference default for SDEs, diffrax_utils.py:121-127, or Euler-Maruyama), y_k ~ N(H x_k + d, R).
+    fixed_init: t is [N,K+1] (t_init first), the path starts AT m0 and the K outputs are the forecast times."""
+    t = np.asarray(t, dtype)
+    N = t.shape[0]
+    K = t.shape[1] - 1 if fixed_init else t.shape[1]
+    c = lambda x, core: _bN(np.asarray(x, dtype), N, core)
+    L, Qc, H, R = c(p.L, 2), c(p.Qc, 2), c(p.H, 2), c(p.R, 2)
+    n, mdim = L.shape[-1], H.shape[-2]
+    d = c(p.d if p.d is not None else np.zeros(mdim), 1)
+    G = L @ cholesky(Qc)
+    cholR = cholesky(R)
+    traj = np.arange(N)
+    m0 = c(p.m0, 1)
+    dt0 = np.dtype(dtype).type(settings.dt0)
+    tol = np.dtype(dtype).type(_tol_for(dtype))
+    xs, ys = np.zeros((N, K, n), dtype), np.zeros((N, K, mdim), dtype)
+
+    def emit(x, row, step):
+        z = enkf_normals(RNG_OBS, traj, step, 0, 1, mdim, seed, rng_offset)[:, 0].astype(dtype)
+        xs[:, row] = x
+        ys[:, row] = _mv(H, x) + d + _mv(cholR, z)
+
+    if fixed_init:
+        x = m0.copy()
+    else:
+        z = enkf_normals(RNG_INIT, traj, 0, 0, 1, n, seed, rng_offset)[:, 0].astype(dtype)
+        x = m0 + _mv(cholesky(c(p.P0, 2)), z)
+        emit(x, 0, 0)
+    for k in range(0 if fixed_init else 1, K):
+        tprev = (t[:, k] if fixed_init else t[:, k - 1]).copy()
+        t1 = t[:, k + 1] if fixed_init else t[:, k]
+        tnext = np.minimum(tprev + dt0, t1)
+        sub = 0
+        nst = np.zeros(N, np.int64)
+        while True:
+            active = tprev < t1
+            over = active & (nst >= settings.max_steps)
+            if over.any():
+                x[over] = np.nan
+                active &= ~over
+                tprev = np.where(over, t1, tprev)
+            if not active.any():
+                break
+            dt = np.where(active, tnext - tprev, 0.0).astype(dtype)
+            zd = enkf_normals(RNG_DYN, traj, k, sub, 1, n, seed, rng_offset)[:, 0].astype(dtype)
+            noise = _mv(G, np.sqrt(dt)[:, None] * zd)
+            f0 = p.drift.f(x)
+            xe = x + dt[:, None] * f0 + noise
+            if settings.solver == "heun":
+                xn = xe + dt[:, None] * np.dtype(dtype).type(0.5) * (p.drift.f(xe) - f0)
+            elif settings.solver == "euler":
+                xn = xe
+            else:
+                raise ValueError("the sampler supports solver 'euler' (Euler-Maruyama) or 'heun'")
+            x = np.where(active[:, None], xn, x)
+            nst += active
+            sub += 1
+            tprev = np.where(active, tnext, tprev)
+            cand = tprev + dt0
+            tnext = np.where(cand > t1 - tol, t1, cand)
+        emit(x, k, k + 1 if fixed_init else k)
+    return xs, ys
+
+
+def emission_moments(p: NonlinearParams, state_means, state_covs=None):
+    """emissions_extended_kalman_filter (inference_ekf.py:762-855) for h(x) = H x + d: (H m + d, H P H^T + R); without
+    covariances the model's own (H m + d, R) (cd_nonlinear/models.py:1000-1047)."""
+    sm = np.asarray(state_means)
+    H, R = np.asarray(p.H), np.asarray(p.R)
+    d = np.asarray(p.d) if p.d is not None else np.zeros(H.shape[0])
+    em = sm @ H.T + d
+    if state_covs is None:
+        return em, np.broadcast_to(R, sm.shape[:-1] + R.shape).copy()
+    return em, H @ np.asarray(state_covs) @ H.T + R

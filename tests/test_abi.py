@@ -98,8 +98,11 @@ def test_scratch_bytes_of_the_pushforward_cache(lib):
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_smooth") == want
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_ekf_filter") == 0
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_ekf_smooth") == 0
-    d.solver = _lib.SOLVERS["dopri5"]  # not a chain tableau: the warp kernels (and with them the cache) do not apply
+    d.solver = _lib.SOLVERS["dopri5"]  # the reference default runs on the warp kernels too (step polynomial): same cache
+    assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == want
+    d.reserved[2] = _lib.FLAG_KEEP_PUSHFORWARD | _lib.FLAG_DIAG_R  # the Woodbury update runs on the generic kernel: no cache
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == 0
+    d.reserved[2] = _lib.FLAG_KEEP_PUSHFORWARD
     d.solver, d.n = _lib.SOLVERS["rk4"], 17
     assert lib.cdk_scratch_bytes(ctypes.byref(d), b"cdk_kf_filter") == 0
     d.n, d.smoother_type = 16, 2  # the backward-ODE smoother never reads the cache
