@@ -76,6 +76,33 @@ def l63(x, s=10.0, r=28.0, b=8.0 / 3.0):
     return torch.stack([s * (x[:, 1] - x[:, 0]), x[:, 0] * (r - x[:, 2]) - x[:, 1], x[:, 0] * x[:, 1] - b * x[:, 2]], 1)
 
 
+def make_emissions(t, seed, first_traj, device):
+    """Synthetic data from the library's own batched sampler (cdk_sample_path, ONE launch): the stochastic
+    Lorenz-63 truth started near the attractor (x_0 ~ N([1, 1, 20], I)), Euler-Maruyama with 8 substeps per mean gap,
+    Qc = I, observe x with unit noise.  The Philox counter is the GLOBAL trajectory index (rng_offset = first_traj), so a
+    shard of the strong-scaling run sees the same data whatever the number of GPUs.  Setup only, never timed."""
+    import torch
+
+    import cd_dynamax_b200 as cd
+    f64 = dict(dtype=torch.float64, device=device)
+    truth = cd.ParamsCDNLGSSM(
+        initial=cd.ParamsLGSSMInitial(mean=cd.LearnableVector(torch.tensor([1.0, 1.0, 20.0], **f64)),
+                                      cov=cd.LearnableMatrix(torch.eye(3, **f64))),
+        dynamics=cd.ParamsCDNLGSSMDynamics(
+            drift=cd.LearnableLorenz63(sigma=torch.tensor(10.0, **f64), rho=torch.tensor(28.0, **f64),
+                                       beta=torch.tensor(8.0 / 3.0, **f64)),
+            diffusion_coefficient=cd.LearnableMatrix(torch.eye(3, **f64)), diffusion_cov=cd.LearnableMatrix(torch.eye(3, **f64))),
+        emissions=cd.ParamsCDNLGSSMEmissions(
+            emission_function=cd.LearnableLinear(weights=torch.tensor([[1.0, 0.0, 0.0]], **f64), bias=torch.zeros(1, **f64)),
+            emission_cov=cd.LearnableMatrix(torch.eye(1, **f64))))
+    if t.shape[0] == 0:
+        return torch.empty(0, t.shape[1], 1, **f64)
+    _, y = cd.cdnlgssm_path_sample(truth, seed, t.shape[1], t[..., None],
+                                   diffeqsolve_settings={"solver": "euler", "dt0": CFG["mean_gap"] / 8},
+                                   rng_offset=first_traj, device_resident=True)
+    return y
+
+
 def make_emissions_torch(t, seed, device):
     """Synthetic data: simulate the stochastic Lorenz-63 truth (Euler-Maruyama, 8 substeps per gap, Qc = I) and
     observe x with unit noise.  Runs in torch on `device` (setup only, never timed)."""
@@ -215,7 +242,7 @@ class Job:
             gen.manual_seed(CFG["seed"] + first_traj)
             self.y_dev = 8.0 * torch.randn(n_local, K, 1, generator=gen, device=dev, dtype=torch.float64)
         else:
-            self.y_dev = make_emissions_torch(self.t_dev, CFG["seed"] + first_traj, dev)
+            self.y_dev = make_emissions(self.t_dev, CFG["seed"], first_traj, dev)
         self.sum_q = substeps_total(self.t_np, CFG["dt0"]) if n_local else 0
         f64 = dict(dtype=torch.float64, device=dev)
         self.params = cd.ParamsCDNLGSSM(

@@ -118,11 +118,12 @@ __global__ void __launch_bounds__(SP_TPB) sample_path_kernel(const KArgs<T> a) {
   int status = 0;
 
   auto normals = [&](int stream, int step, int substep, int dim, T* out) {
-    for (int j = 0; j < dim; j += 2) {
-      double z0, z1;
-      normal_pair(0u, ctr, (uint32_t)step, rng_c3(stream, substep, j >> 1), seed, z0, z1);
-      out[j] = (T)z0;
-      if (j + 1 < dim) out[j + 1] = (T)z1;
+    for (int j = 0; j < dim; j += 4) {
+      double z4[4];
+      normal_quad(0u, ctr, (uint32_t)step, rng_c3(stream, substep, j >> 2), seed, z4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j + u < dim) out[j + u] = (T)z4[u];
     }
   };
   auto emit = [&](int row, int step) {  // y ~ N(H x + d, R) and the state itself -> row `row` of the outputs

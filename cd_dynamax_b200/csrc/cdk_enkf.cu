@@ -193,7 +193,7 @@ template <typename T, int NX>
 __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
   constexpr int NXA = NX > 0 ? NX : CDK_MAX_N;
   constexpr int UF = NX > 0 ? NX : 1;             // unroll factor of loops over the state dimension
-  constexpr int UFP = NX > 0 ? (NX + 1) / 2 : 1;  // ... over normal pairs
+  constexpr int UFP = NX > 0 ? (NX + 3) / 4 : 1;  // ... over normal quads (four normals per Philox call)
   extern __shared__ __align__(16) unsigned char sh[];
   cg::cluster_group cluster = cg::this_cluster();
   const KArgs<T>& a = g.k;
@@ -289,12 +289,13 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
     for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
       T z[NXA];
 #pragma unroll UFP
-      for (int j = 0; j < NXA; j += 2) {
+      for (int j = 0; j < NXA; j += 4) {
         if (j < n) {
-          double z0, z1;
-          normal_pair((uint32_t)(e_base + el), ctr_traj, 0u, rng_c3(RNG_INIT, 0, j >> 1), seed, z0, z1);
-          z[j] = (T)z0;
-          if (j + 1 < NXA) z[j + 1] = (T)z1;
+          double z4[4];
+          normal_quad((uint32_t)(e_base + el), ctr_traj, 0u, rng_c3(RNG_INIT, 0, j >> 2), seed, z4);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (j + u < NXA) z[j + u] = (T)z4[u];
         }
       }
 #pragma unroll UF
@@ -360,18 +361,7 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
     }
     __syncthreads();
     chol<T>(Sm, Sl, m, ldm, T(0));  // MVN(ybar, S).log_prob(y): un-boosted Cholesky (:129)
-    if (threadIdx.x == 0) {
-      T quad = T(0), logdet = T(0);
-      for (int i = 0; i < m; ++i) {
-        T v = rv[i];
-        for (int q = 0; q < i; ++q) v -= Sl[i * ldm + q] * zv[q];
-        v /= Sl[i * ldm + i];
-        zv[i] = v;
-        quad += v * v;
-        logdet += log(Sl[i * ldm + i]);
-      }
-      *llsh = T(-0.5) * quad - logdet - T(m) * half_log_2pi<T>();
-    }
+    mvn_ll_warp<T>(Sl, ldm, rv, m, llsh);
     // K^T = psd_solve(S, C_xy^T): chol(sym(S) + 1e-9 I)  (:141-143)
     T* Sb = SK;
     FOR_T(e, m * m) {
@@ -395,11 +385,12 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
         if (i < n) x[i] = X[(size_t)i * ldE + el];
       T r[CDK_MAX_M];
       if (d.perturb_measurements) {
-        for (int p = 0; p < m; p += 2) {
-          double z0, z1;
-          normal_pair((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_OBS, 0, p >> 1), seed, z0, z1);
-          r[p] = (T)z0;
-          if (p + 1 < m) r[p + 1] = (T)z1;
+        for (int p = 0; p < m; p += 4) {
+          double z4[4];
+          normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_OBS, 0, p >> 2), seed, z4);
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (p + u < m) r[p + u] = (T)z4[u];
         }
         for (int p = m - 1; p >= 0; --p) {  // r <- chol(R) z, in place from the bottom row up
           T s = T(0);
@@ -454,25 +445,27 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
           if (i < n) x[i] = X[(size_t)i * ldE + el];
         if (diagG) {
 #pragma unroll UFP
-          for (int j = 0; j < NXA; j += 2) {
+          for (int j = 0; j < NXA; j += 4) {
             if (j < n) {
-              double z0, z1;
-              normal_pair((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 1), seed, z0, z1);
-              xe[j] = G[j * ldn + j] * (sqdt * (T)z0);
-              if (j + 1 < NXA && j + 1 < n) xe[j + 1] = G[(j + 1) * ldn + j + 1] * (sqdt * (T)z1);
+              double z4[4];
+              normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 2), seed, z4);
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                if (j + u < NXA && j + u < n) xe[j + u] = G[(j + u) * ldn + j + u] * (sqdt * (T)z4[u]);
             }
           }
         } else {
 #pragma unroll UF
           for (int i = 0; i < NXA; ++i) xe[i] = T(0);
-          for (int j = 0; j < n; j += 2) {  // pairs stay a runtime loop: the rank-2 update below is the unrolled part
-            double z0, z1;
-            normal_pair((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 1), seed, z0, z1);
-            const T dw0 = sqdt * (T)z0, dw1 = j + 1 < n ? sqdt * (T)z1 : T(0);
-            const int j1 = j + 1 < n ? j + 1 : j;
+          for (int j = 0; j < n; j += 4) {  // quads stay a runtime loop: the rank-4 update below is the unrolled part
+            double z4[4];
+            normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 2), seed, z4);
+            for (int u = 0; u < 4 && j + u < n; ++u) {
+              const T dw = sqdt * (T)z4[u];
 #pragma unroll UF
-            for (int i = 0; i < NXA; ++i)
-              if (i < n) xe[i] += G[i * ldn + j] * dw0 + G[i * ldn + j1] * dw1;
+              for (int i = 0; i < NXA; ++i)
+                if (i < n) xe[i] += G[i * ldn + j + u] * dw;
+            }
           }
         }
 #pragma unroll UF

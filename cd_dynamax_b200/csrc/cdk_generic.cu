@@ -11,6 +11,8 @@
 // (up to ~200 KB of the 227 KB a B200 CTA may use); the threads of the CTA split every small matrix product by
 // output element.  Matrices are stored with an odd leading dimension so that row-strided accesses (Cholesky,
 // triangular solves, A B^T products) are bank-conflict free for 64-bit words.
+#include <stdlib.h>
+
 #include "cdk_dense.cuh"
 
 namespace cdk {
@@ -29,6 +31,7 @@ struct GArgs {
   RtTab tab;
   int nslots;  // RK stage buffers kept in shared memory (1 for "chain" tableaux, S otherwise)
   int algo;
+  int reg_ode;  // allow the register-resident Lorenz-96 moment ODE (ode_solve_stencil)
 };
 
 // shared-memory layout, computed identically on host (size) and device (offsets); units = elements of T
@@ -335,6 +338,130 @@ __device__ bool ode_solve(const Ctx<T>& c, int kind, T* y, int S, T t0, T t1, T 
   return false;
 }
 
+// Moment ODE of the Lorenz-96 drift (EKF first / second order -- identical for this drift, SURVEY F8 -- and the closed-form
+// unscented predict) for chain tableaux, with the RK state in REGISTERS: thread t owns the covariance entries
+// e = t + j * blockDim (j < EPT) and, for t < n, mean entry t; it keeps y, the running combination acc and its previous
+// stage increment k for them.  Only the STAGE INPUT lives in shared memory (two buffers, YS and KS, alternating), because a
+// covariance entry's derivative reads eight neighbours:
+//   d/dt P_rc = (J P)_rc + (J P)_cr + (L Qc L^T)_rc,   (J P)_rc = x_{r-1} (P_{r+1,c} - P_{r-2,c}) + (x_{r+1} - x_{r-2}) P_{r-1,c} - P_rc.
+// One barrier per RK stage and ~45 instructions per entry and stage, against four barriers and ~170 instructions (index
+// arithmetic of the run-time-n loops) for ode_solve + ode_rhs on the same ODE.
+constexpr int STENCIL_EPT = 7;  // 7 x 256 threads cover n = 40 (BASELINE config 4) and anything up to n = 42
+
+template <typename T>
+struct StencilRegs {
+  unsigned xrow[STENCIL_EPT];    // r | c << 8
+  unsigned nbr[STENCIL_EPT];     // r+1 | r-1 << 8 | r-2 << 16   (cyclic)
+  unsigned nbc[STENCIL_EPT];     // c+1 | c-1 << 8 | c-2 << 16
+  int cnt;                       // entries this thread owns
+};
+
+template <typename T>
+__device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R) {
+  const int n = c.L.n, ld = c.L.ldn;
+  R.cnt = 0;
+#pragma unroll
+  for (int j = 0; j < STENCIL_EPT; ++j) {
+    const int e = threadIdx.x + j * blockDim.x;
+    const bool v = e < n * n;
+    const int r = v ? e / n : 0, cc = v ? e - r * n : 0;
+    R.xrow[j] = (unsigned)r | ((unsigned)cc << 8);
+    {
+      const int rp = r + 1 == n ? 0 : r + 1, rm1 = r == 0 ? n - 1 : r - 1, rm2 = rm1 == 0 ? n - 1 : rm1 - 1;
+      const int cp = cc + 1 == n ? 0 : cc + 1, cm1 = cc == 0 ? n - 1 : cc - 1, cm2 = cm1 == 0 ? n - 1 : cm1 - 1;
+      R.nbr[j] = (unsigned)rp | ((unsigned)rm1 << 8) | ((unsigned)rm2 << 16);
+      R.nbc[j] = (unsigned)cp | ((unsigned)cm1 << 8) | ((unsigned)cm2 << 16);
+    }
+    if (v) R.cnt = j + 1;
+  }
+}
+
+// Integrate (m, P) (shared memory, [MU | P] layout of `y`) from t0 to t1.  UKFC adds the unscented second-order mean term.
+template <typename T, bool UKFC>
+__device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y, T t0, T t1, T dt0, int max_steps) {
+  const Lay& L = c.L;
+  const int n = L.n, ld = L.ldn, poff = L.P - L.MU;
+  const RtTab& tab = c.g.tab;
+  const T F = c.p(L.TH)[0];
+  const T* lql = c.p(L.LQL);
+  const int tid = threadIdx.x;
+  const bool own_m = tid < n;
+  const int mp = tid + 1 == n ? 0 : tid + 1, mm1 = tid == 0 ? n - 1 : tid - 1, mm2 = mm1 == 0 ? n - 1 : mm1 - 1;
+  T yP[STENCIL_EPT], aP[STENCIL_EPT], kP[STENCIL_EPT];
+  T ym = T(0), am = T(0), km = T(0);
+#pragma unroll
+  for (int j = 0; j < STENCIL_EPT; ++j) {
+    yP[j] = j < R.cnt ? y[poff + (R.xrow[j] & 0xff) * ld + (R.xrow[j] >> 8)] : T(0);
+    kP[j] = T(0);
+  }
+  if (own_m) ym = y[tid];
+  const T tol = clip_tol<T>();
+  T tprev = t0, tnext = fmin(t0 + dt0, t1);
+  int nsteps = 0;
+  bool hit = false;
+  while (tprev < t1) {
+    if (nsteps >= max_steps) {
+      hit = true;
+#pragma unroll
+      for (int j = 0; j < STENCIL_EPT; ++j) yP[j] = T(NAN);
+      ym = T(NAN);
+      break;
+    }
+    const T dt = tnext - tprev;
+    for (int st = 0; st < tab.S; ++st) {
+      const T a = tab.nnz[st] ? T(tab.val[st][0]) : T(0);  // chain tableau: only the previous stage
+      T* B = c.sh + ((st & 1) ? L.KS : L.YS);  // an integer select keeps the pointer in the shared window (LDS / STS)
+      // stage input y + a k_{st-1} -> shared memory
+#pragma unroll
+      for (int j = 0; j < STENCIL_EPT; ++j)
+        if (j < R.cnt) B[poff + (R.xrow[j] & 0xff) * ld + (R.xrow[j] >> 8)] = st == 0 ? yP[j] : yP[j] + a * kP[j];
+      if (own_m) B[tid] = st == 0 ? ym : ym + a * km;
+      if (st == 0) {
+#pragma unroll
+        for (int j = 0; j < STENCIL_EPT; ++j) aP[j] = yP[j];
+        am = ym;
+      }
+      __syncthreads();
+      const T* x = B;
+      const T* P = B + poff;
+      const T b = T(tab.b[st]);
+#pragma unroll
+      for (int j = 0; j < STENCIL_EPT; ++j) {
+        if (j < R.cnt) {
+          const int r = R.xrow[j] & 0xff, cc = R.xrow[j] >> 8;
+          const int rp = R.nbr[j] & 0xff, rm1 = (R.nbr[j] >> 8) & 0xff, rm2 = R.nbr[j] >> 16;
+          const int cp = R.nbc[j] & 0xff, cm1 = (R.nbc[j] >> 8) & 0xff, cm2 = R.nbc[j] >> 16;
+          const T jp_rc = x[rm1] * (P[rp * ld + cc] - P[rm2 * ld + cc]) + (x[rp] - x[rm2]) * P[rm1 * ld + cc] - P[r * ld + cc];
+          const T jp_cr = x[cm1] * (P[cp * ld + r] - P[cm2 * ld + r]) + (x[cp] - x[cm2]) * P[cm1 * ld + r] - P[cc * ld + r];
+          kP[j] = dt * ((jp_rc + jp_cr) + lql[r * ld + cc]);
+          aP[j] += b * kP[j];
+        }
+      }
+      if (own_m) {
+        T f = (x[mp] - x[mm2]) * x[mm1] - x[tid] + F;
+        if (UKFC)  // 0.5 tr(Hess f_r P) = sym(P)_{r+1,r-1} - sym(P)_{r-2,r-1}
+          f += T(0.5) * (P[mp * ld + mm1] + P[mm1 * ld + mp]) - T(0.5) * (P[mm2 * ld + mm1] + P[mm1 * ld + mm2]);
+        km = dt * f;
+        am += b * km;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < STENCIL_EPT; ++j) yP[j] = aP[j];
+    ym = am;
+    ++nsteps;
+    tprev = tnext;
+    const T cand = tprev + dt0;
+    tnext = cand > t1 - tol ? t1 : cand;
+  }
+  __syncthreads();  // the last stage's readers are done before the state block is rewritten
+#pragma unroll
+  for (int j = 0; j < STENCIL_EPT; ++j)
+    if (j < R.cnt) y[poff + (R.xrow[j] & 0xff) * ld + (R.xrow[j] >> 8)] = yP[j];
+  if (own_m) y[tid] = ym;
+  __syncthreads();
+  return hit;
+}
+
 // load a [r x c] row-major global matrix into shared memory with leading dimension ld
 template <typename T>
 __device__ void load_mat(T* dst, const T* src, int r, int c, int ld) {
@@ -456,18 +583,7 @@ __device__ T condition_on_diag_r(const Ctx<T>& c) {
   }
   __syncthreads();
   chol<T>(X, Sl, m, ldm, T(0));
-  if (threadIdx.x == 0) {
-    T quad = T(0), logdet = T(0);
-    for (int i = 0; i < m; ++i) {
-      T v = rv[i];
-      for (int q = 0; q < i; ++q) v -= Sl[i * ldm + q] * zv[q];
-      v /= Sl[i * ldm + i];
-      zv[i] = v;
-      quad += v * v;
-      logdet += log(Sl[i * ldm + i]);
-    }
-    ll_sh = T(-0.5) * quad - logdet - T(m) * half_log_2pi<T>();
-  }
+  mvn_ll_warp<T>(Sl, ldm, rv, m, &ll_sh);
   chol<T>(Ma, Lp, n, ldn, T(0));  // jnp.linalg.cholesky(P) symmetrises its input
   FOR_T(e, m * n) {  // U = H Lp (Lp lower), X = U / R[:, None]
     const int a = e / n, j = e - a * n;
@@ -630,18 +746,7 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
     if (it == 0) {
       // MVN(.).log_prob(y): un-boosted Cholesky (TFP)
       chol<T>(Sm, Sl, m, ldm, T(0));
-      if (threadIdx.x == 0) {
-        T quad = T(0), logdet = T(0);
-        for (int i = 0; i < m; ++i) {
-          T v = rv[i];
-          for (int q = 0; q < i; ++q) v -= Sl[i * ldm + q] * zv[q];
-          v /= Sl[i * ldm + i];
-          zv[i] = v;
-          quad += v * v;
-          logdet += log(Sl[i * ldm + i]);
-        }
-        ll_sh = T(-0.5) * quad - logdet - T(m) * half_log_2pi<T>();
-      }
+      mvn_ll_warp<T>(Sl, ldm, rv, m, &ll_sh);
       __syncthreads();
     }
     // psd_solve(S, .): chol(sym(S) + 1e-9 I); symmetrise into SK (scratch, [m x ldm] fits), then factor into Sl
@@ -693,8 +798,11 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
   return ll_sh;
 }
 
-template <typename T>
-__global__ void generic_filter_kernel(const GArgs<T> g) {
+// REGODE: the launcher has established that the predict step is the Lorenz-96 moment ODE with a chain tableau
+// (ode_solve_stencil, RK state in registers); that instantiation contains no other ODE code, so its register allocation is
+// not burdened by the shared-memory solver and vice versa.
+template <typename T, bool REGODE>
+__global__ void __launch_bounds__(256, 2) generic_filter_kernel(const GArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx<T> c(g, reinterpret_cast<T*>(smem_raw));
   const Lay& L = c.L;
@@ -728,6 +836,8 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
   T* uv = c.p(L.UV);
   // forecast (CDK_FLAG_PREDICT_ONLY): no updates; Tm holds K + 1 stamps, t_init first
   const bool ponly = (d.reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
+  StencilRegs<T> sreg;
+  if constexpr (REGODE) stencil_init<T>(c, sreg);
   for (int k = 0; k < K; ++k) {
     FOR_T(i, du) uv[i] = U[(long long)k * du + i];
     __syncthreads();
@@ -753,7 +863,13 @@ __global__ void generic_filter_kernel(const GArgs<T> g) {
     const T t0 = Tm[k];
     const T t1 = (ponly || k + 1 < K) ? Tm[k + 1] : t0 + T(d.dt_final);
     bool hit = false;
-    if (linear) {
+    if constexpr (REGODE) {
+      if (algo == ALGO_UKF_FILTER) {
+        hit = ode_solve_stencil<T, true>(c, sreg, mu, t0, t1, dt0, d.max_steps);
+      } else {
+        hit = ode_solve_stencil<T, false>(c, sreg, mu, t0, t1, dt0, d.max_steps);
+      }
+    } else if (linear) {
       // pushforward from (I, 0), then m = A m + B u + b, P = A P A^T + Q (cd_linear/inference.py:619-620)
       T* A = c.p(L.ODEY);
       T* Q = A + L.nn;
@@ -967,6 +1083,11 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
   }
   if (!fill_rt_tab(g.k.d.solver, g.tab)) return CDK_E_ENUM;
   g.nslots = g.k.d.solver == CDK_DOPRI5 ? g.tab.S : 1;
+  static const int reg_ode_env = []() {
+    const char* e = getenv("CDK_GENERIC_REG_ODE");
+    return e && e[0] == '0' ? 0 : 1;
+  }();
+  g.reg_ode = reg_ode_env;
   Lay L(g.k.d, algo, g.nslots);
   const size_t smem = (size_t)L.total * sizeof(T);
   int dev = 0, max_optin = 0;
@@ -976,7 +1097,12 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
   const int n = a.d.n > a.d.m ? a.d.n : a.d.m;
   const int threads = n <= 4 ? 32 : (n <= 8 ? 64 : (n <= 16 ? 128 : 256));
   const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
-  auto kern = smooth ? generic_smooth_kernel<T> : generic_filter_kernel<T>;
+  // Lorenz-96 moment ODE with a chain tableau: RK state in registers (ode_solve_stencil); CDK_GENERIC_REG_ODE=0 disables
+  const cdk_desc& dd = g.k.d;
+  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && g.nslots == 1 &&
+                       dd.n * dd.n <= STENCIL_EPT * threads && dd.n <= 255 &&
+                       ((algo == ALGO_EKF_FILTER && dd.state_order != CDK_ORDER_ZEROTH) || (algo == ALGO_UKF_FILTER && ukf_closed(dd)));
+  auto kern = smooth ? generic_smooth_kernel<T> : (reg_ode ? generic_filter_kernel<T, true> : generic_filter_kernel<T, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(generic)");

@@ -727,15 +727,15 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
-def philox_normal_pair(c0, c1, c2, c3, seed):
-    """Two standard normals per counter: 53-bit uniforms from word pairs, Box-Muller in fp64."""
+def philox_normal_quad(c0, c1, c2, c3, seed):
+    """Four standard normals per counter: four 32-bit uniforms (r + 0.5) 2^-32, two Box-Muller pairs in fp64
+    (csrc/cdk_rng.cuh:normal_quad)."""
     k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
-    r0, r1, r2, r3 = philox4x32(c0, c1, c2, c3, k0, k1)
-    u1 = ((r0 >> np.uint32(5)).astype(np.float64) * 67108864.0 + (r1 >> np.uint32(6)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
-    u2 = ((r2 >> np.uint32(5)).astype(np.float64) * 67108864.0 + (r3 >> np.uint32(6)).astype(np.float64) + 0.5) * (1.0 / 9007199254740992.0)
-    rad = np.sqrt(-2.0 * np.log(u1))
-    ang = 2.0 * math.pi * u2
-    return rad * np.cos(ang), rad * np.sin(ang)
+    r = philox4x32(c0, c1, c2, c3, k0, k1)
+    u = [(ri.astype(np.float64) + 0.5) * (1.0 / 4294967296.0) for ri in r]
+    rad0, rad1 = np.sqrt(-2.0 * np.log(u[0])), np.sqrt(-2.0 * np.log(u[2]))
+    a0, a1 = 2.0 * math.pi * u[1], 2.0 * math.pi * u[3]
+    return rad0 * np.cos(a0), rad0 * np.sin(a0), rad1 * np.cos(a1), rad1 * np.sin(a1)
 
 
 # stream ids (counter word c3 high byte)
@@ -744,16 +744,18 @@ RNG_INIT, RNG_OBS, RNG_DYN = 0, 1, 2
 
 def enkf_normals(stream, traj, step, substep, E, dim, seed, rng_offset=0):
     """z[len(traj), E, dim] standard normals. Counter layout (shared with csrc/cdk_enkf.cu):
-    c0 = member e, c1 = trajectory + rng_offset, c2 = observation index k, c3 = stream<<28 | substep<<8 | pair index."""
+    c0 = member e, c1 = trajectory + rng_offset, c2 = observation index k, c3 = stream<<28 | substep<<8 | quad index;
+    quad q supplies dimensions 4q .. 4q+3."""
     traj = np.asarray(traj, np.uint64)
-    npair = (dim + 1) // 2
+    nquad = (dim + 3) // 4
     e = np.arange(E, dtype=np.uint32)[None, :, None]
     c1 = ((traj + np.uint64(rng_offset)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)[:, None, None]
-    j = np.arange(npair, dtype=np.uint32)[None, None, :]
+    j = np.arange(nquad, dtype=np.uint32)[None, None, :]
     c3 = np.uint32((stream << 28) | ((substep & 0xFFFFF) << 8)) | j
-    z0, z1 = philox_normal_pair(e, c1, np.uint32(step), c3, seed)
-    z = np.empty((len(traj), E, 2 * npair))
-    z[..., 0::2], z[..., 1::2] = z0, z1
+    zs = philox_normal_quad(e, c1, np.uint32(step), c3, seed)
+    z = np.empty((len(traj), E, 4 * nquad))
+    for q in range(4):
+        z[..., q::4] = zs[q]
     return z[..., :dim]
 
 
