@@ -18,6 +18,7 @@ FLAG_DIAG_R = 4  # CDK_FLAG_DIAG_R: in[IN_R] is the [m] diagonal of the emission
 FLAG_PREDICT_ONLY = 8  # CDK_FLAG_PREDICT_ONLY: forecast (no updates), in[IN_T] is [N, K+1]
 FLAG_FIXED_INIT = 16  # CDK_FLAG_FIXED_INIT: cdk_sample_path starts from in[IN_M0] at t_init
 GRAD_COLS_L63 = 23  # CDK_GRAD_COLS_L63: columns of out[CDK_OUT_GRAD]
+GRAD_REVERSE = 128  # CDK_GRAD_REVERSE (desc.reserved[3] bit 7)
 ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth"), ("ekf", "filter"), ("ekf", "smooth"),
                                                   ("ukf", "filter"), ("enkf", "filter")) for t in ("f64", "f32")]
 ENTRY_POINTS.append("cdk_ekf_grad_f64")

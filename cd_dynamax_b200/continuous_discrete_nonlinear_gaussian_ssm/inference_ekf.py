@@ -84,9 +84,10 @@ def ekf_marginal_log_prob_and_grad(params, emissions, t_emissions=None, hyperpar
     "initial_cov" [3,3] to arrays, with a leading N for batched emissions.  `wrt` = any of those group names, or "all".
 
     This is what `jax.value_and_grad(lambda p: model.marginal_log_prob(p, ...))` yields upstream
-    (src/utils/optimize_utils.py:102, src/ssm_temissions.py:550-568) -- here as a forward-mode derivative of exactly the
-    discrete filter `cdnlgssm_filter` runs (cdk_ekf_grad_f64, one launch per direction), so that a `jax.custom_vjp`
-    around the filter can be fed.  Symmetric matrices (diffusion_cov, initial_cov) are differentiated
+    (src/utils/optimize_utils.py:102, src/ssm_temissions.py:550-568) -- here as the derivative of exactly the discrete
+    filter `cdnlgssm_filter` runs (cdk_ekf_grad_f64): REVERSE mode for more than the drift group (a forward filter pass
+    + one backward launch for all 23 columns, ~4 filter passes), forward mode otherwise (one launch per column), so that
+    a `jax.custom_vjp` around the filter can be fed.  Symmetric matrices (diffusion_cov, initial_cov) are differentiated
     along symmetric directions: the result is the symmetric part (G + G^T)/2 of the entry-wise gradient G, which is what
     any PSD parameterisation consumes; diffusion_coefficient's gradient is exact.  First step of SURVEY section 8f rank 1:
     LearnableLorenz63 drift, scalar emission, num_iter = 1, fp64; anything else raises NotImplementedError."""
@@ -113,7 +114,14 @@ def ekf_marginal_log_prob_and_grad(params, emissions, t_emissions=None, hyperpar
         raise NotImplementedError("gradients are fp64 only")
     ins, drift_fields = nonlinear_inputs(params, Y, T, n, m)
     fields = dict(E.parse_settings(hyperparams.diffeqsolve_settings), **drift_fields, **_ekf_fields(hyperparams, 1))
-    fields["grad_groups"] = groups
+    # more than the three drift columns: REVERSE mode (one backward launch for all 23 columns behind a forward filter pass
+    # whose moments go to device scratch, N*K*192 bytes) when that scratch is affordable; else forward mode, one launch
+    # per column.  CDK_GRAD_MODE=forward|reverse overrides.
+    import os
+    mode = os.environ.get("CDK_GRAD_MODE", "auto")
+    free, _ = torch.cuda.mem_get_info()
+    reverse = mode == "reverse" or (mode == "auto" and groups != 1 and N * K * 192 <= free // 2)
+    fields["grad_groups"] = groups | (L.GRAD_REVERSE if reverse else 0)
     dev_ins = {}
     try:
         out = E.run("cdk_ekf_grad", dt, N, K, n, m, ins, (L.OUT_LL, L.OUT_GRAD), fields, dev_inputs=dev_ins)

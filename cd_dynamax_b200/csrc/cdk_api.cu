@@ -330,6 +330,8 @@ size_t cdk_scratch_bytes(const cdk_desc* d, const char* entry_point) {
   const bool kf = strstr(entry_point, "kf_filter") != nullptr && strstr(entry_point, "ekf") == nullptr &&
                   strstr(entry_point, "ukf") == nullptr && strstr(entry_point, "enkf") == nullptr;
   const bool ks = strstr(entry_point, "kf_smooth") != nullptr && strstr(entry_point, "ekf") == nullptr;
+  if (strstr(entry_point, "ekf_grad") != nullptr)
+    return (d->reserved[3] & CDK_GRAD_REVERSE) ? (size_t)d->N * (size_t)d->K * 24u * sizeof(double) : 0;
   if ((kf || ks) && (d->reserved[2] & CDK_FLAG_KEEP_PUSHFORWARD) && cdk::kf_warp_eligible(*d, ks) && d->K > 1)
     return (size_t)d->N * (size_t)(d->K - 1) * 2u * (size_t)d->n * (size_t)d->n * sizeof(double);
   return 0;

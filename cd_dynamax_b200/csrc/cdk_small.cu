@@ -1269,6 +1269,290 @@ __global__ void __launch_bounds__(128) ekf_l63_grad_kernel(const KArgs<double> a
   grad[traj * grad_stride + col] = llt;
 }
 
+// ======================================================================================================================
+// REVERSE mode: every column of d log-likelihood / d parameters in ONE backward launch (what
+// jax.value_and_grad(marginal_log_prob) hands fit_sgd, src/utils/optimize_utils.py:102).  The forward filter
+// (ekf_small_lw) has written the filtered and predicted moments of every step to HBM; this kernel walks k = K-1 .. 0 with
+// the adjoint (am, AP) of the state:
+//   gap k (k < K-1; the last predict does not enter the likelihood): re-integrate from (m_f, P_f)_k keeping the start state
+//     of every substep (up to GR_CKPT of them in thread-local memory, otherwise recomputed from the gap start), then step
+//     backwards through the substeps; each RK step is differentiated stage by stage,
+//       cot(k_i) = b_i dt lam+ + dt sum_{j>i} a_ji lam(y_j),   lam(y_i) = VJP_rhs(y_i)[cot(k_i)],   lam = lam+ + sum_i lam(y_i),
+//     with the closed-form VJP of the moment right-hand side (f(m), J P + P J^T + L Qc L^T) below;
+//   update k: the scalar-emission update differentiated by hand (see the comments in the code).
+// Adjoint covariances are FULL-matrix entry-wise gradients kept symmetric (packed upper triangle); the output columns use
+// the convention of the forward-mode kernel: an off-diagonal column of a symmetric parameter moves both mirror entries,
+// i.e. it is twice the packed entry.  One lane per trajectory; cost ~4 filter passes for all 23 columns (forward mode: one
+// launch of ~2.2 filter passes per column).
+// ======================================================================================================================
+constexpr int GR_CKPT = 8;
+
+struct GradAcc {
+  double th[3], lql[6], R, d, H[3];
+};
+
+// VJP of the moment rhs at (m, P) with cotangent (cm, C): adds to (vm, V) and to the parameter accumulators.
+__device__ __forceinline__ void l63_rhs_vjp(const double* th, const double (&m)[3], const double (&P)[6], const double (&cm)[3],
+                                            const double (&C)[6], double (&vm)[3], double (&V)[6], GradAcc& g) {
+  const double s = th[0], rz = th[1] - m[2], b = th[2], x = m[0], y = m[1], z = m[2];
+  // J = [[-s, s, 0], [rz, -1, -x], [y, x, -b]];  full symmetric views of C and P
+  const double C00 = C[0], C01 = C[1], C02 = C[2], C11 = C[3], C12 = C[4], C22 = C[5];
+  const double P00 = P[0], P01 = P[1], P02 = P[2], P11 = P[3], P12 = P[4], P22 = P[5];
+  // W = J^T C:  W_ab = sum_i J_ia C_ib;  dL/dP = W + W^T
+  const double W00 = -s * C00 + rz * C01 + y * C02, W01 = -s * C01 + rz * C11 + y * C12, W02 = -s * C02 + rz * C12 + y * C22;
+  const double W10 = s * C00 - C01 + x * C02, W11 = s * C01 - C11 + x * C12, W12 = s * C02 - C12 + x * C22;
+  const double W20 = -x * C01 - b * C02, W21 = -x * C11 - b * C12, W22 = -x * C12 - b * C22;
+  V[0] += 2.0 * W00;
+  V[1] += W01 + W10;
+  V[2] += W02 + W20;
+  V[3] += 2.0 * W11;
+  V[4] += W12 + W21;
+  V[5] += 2.0 * W22;
+  // M = C P (only the entries the sparse dJ/dm, dJ/dtheta touch):  dL/dJ = 2 M
+  const double M00 = C00 * P00 + C01 * P01 + C02 * P02, M01 = C00 * P01 + C01 * P11 + C02 * P12;
+  const double M10 = C01 * P00 + C11 * P01 + C12 * P02, M12 = C01 * P02 + C11 * P12 + C12 * P22;
+  const double M20 = C02 * P00 + C12 * P01 + C22 * P02, M21 = C02 * P01 + C12 * P11 + C22 * P12, M22 = C02 * P02 + C12 * P12 + C22 * P22;
+  // mean: Jf^T cm + <dJ/dm, 2 M>   (J10 = rho - z, J12 = -x, J20 = y, J21 = x)
+  vm[0] += -s * cm[0] + rz * cm[1] + y * cm[2] + 2.0 * (M21 - M12);
+  vm[1] += s * cm[0] - cm[1] + x * cm[2] + 2.0 * M20;
+  vm[2] += -x * cm[1] - b * cm[2] - 2.0 * M10;
+  // parameters: df/dtheta^T cm + <dJ/dtheta, 2 M>;  d(L Qc L^T) enters dP entry-wise
+  g.th[0] += (y - x) * cm[0] + 2.0 * (M01 - M00);
+  g.th[1] += x * cm[1] + 2.0 * M10;
+  g.th[2] += -z * cm[2] - 2.0 * M22;
+#pragma unroll
+  for (int e = 0; e < 6; ++e) g.lql[e] += C[e];
+}
+
+template <int SOLVER>
+__device__ __forceinline__ void l63_rk_step_vjp(const double* th, const double* lql, const St<double, 3>& y, const double dt,
+                                                St<double, 3>& lam, GradAcc& g) {
+  using TB = Tab<SOLVER>;
+  constexpr int S = TB::S;
+  St<double, 3> yi[S], k[S];
+  // forward: stage inputs and increments (rhs WITHOUT dt, as rk_step)
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    yi[i] = y;
+#pragma unroll
+    for (int j = 0; j < i; ++j)
+      if (TB::a(i, j) != 0.0) {
+        const double c = TB::a(i, j) * dt;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) yi[i].m[e] = fma(c, k[j].m[e], yi[i].m[e]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) yi[i].P[e] = fma(c, k[j].P[e], yi[i].P[e]);
+      }
+    ekf_rhs<double, DriftL63>(th, lql, yi[i], k[i]);
+  }
+  // backward
+  St<double, 3> ly[S];
+  St<double, 3> out = lam;
+#pragma unroll
+  for (int i = S - 1; i >= 0; --i) {
+    double cm[3], C[6];
+#pragma unroll
+    for (int e = 0; e < 3; ++e) cm[e] = TB::b(i) * dt * lam.m[e];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) C[e] = TB::b(i) * dt * lam.P[e];
+#pragma unroll
+    for (int j = i + 1; j < S; ++j)
+      if (TB::a(j, i) != 0.0) {
+        const double c = TB::a(j, i) * dt;
+#pragma unroll
+        for (int e = 0; e < 3; ++e) cm[e] = fma(c, ly[j].m[e], cm[e]);
+#pragma unroll
+        for (int e = 0; e < 6; ++e) C[e] = fma(c, ly[j].P[e], C[e]);
+      }
+#pragma unroll
+    for (int e = 0; e < 3; ++e) ly[i].m[e] = 0.0;
+#pragma unroll
+    for (int e = 0; e < 6; ++e) ly[i].P[e] = 0.0;
+    l63_rhs_vjp(th, yi[i].m, yi[i].P, cm, C, ly[i].m, ly[i].P, g);
+#pragma unroll
+    for (int e = 0; e < 3; ++e) out.m[e] += ly[i].m[e];
+#pragma unroll
+    for (int e = 0; e < 6; ++e) out.P[e] += ly[i].P[e];
+  }
+  lam = out;
+}
+
+template <int SOLVER>
+__global__ void __launch_bounds__(128) ekf_l63_grad_rev_kernel(const KArgs<double> a, const double* __restrict__ FMg,
+                                                                 const double* __restrict__ FPg, const double* __restrict__ PMg,
+                                                                 const double* __restrict__ PPg, double* __restrict__ grad) {
+  constexpr int NX = 3;
+  const long long N = a.d.N;
+  const int K = a.d.K;
+  const long long traj = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (traj >= N) return;
+  double th[3], lql[6], H[3];
+  {
+    const double* thg = a.in[CDK_IN_F] + traj * a.in_stride[CDK_IN_F];
+    const double* Lm = a.in[CDK_IN_L] + traj * a.in_stride[CDK_IN_L];
+    const double* Qc = a.in[CDK_IN_QC] + traj * a.in_stride[CDK_IN_QC];
+    const double* Hg = a.in[CDK_IN_H] + traj * a.in_stride[CDK_IN_H];
+    for (int i = 0; i < 3; ++i) th[i] = thg[i];
+    for (int i = 0; i < 3; ++i) H[i] = Hg[i];
+    for (int i = 0; i < NX; ++i)
+      for (int j = i; j < NX; ++j) {
+        double acc = 0.0;
+        for (int q = 0; q < NX; ++q) {
+          double lq = 0.0;
+          for (int r = 0; r < NX; ++r) lq += Lm[i * NX + r] * Qc[r * NX + q];
+          acc += lq * Lm[j * NX + q];
+        }
+        lql[pidx<NX>(i, j)] = acc;
+      }
+  }
+  const double dv = (a.in[CDK_IN_D] + traj * a.in_stride[CDK_IN_D])[0];
+  const double R = (a.in[CDK_IN_R] + traj * a.in_stride[CDK_IN_R])[0];
+  const double* __restrict__ Y = a.in[CDK_IN_Y] + traj * a.in_stride[CDK_IN_Y];
+  const double* __restrict__ Tm = a.in[CDK_IN_T] + traj * a.in_stride[CDK_IN_T];
+  const double* fm = FMg + traj * (long long)K * 3;
+  const double* fp = FPg + traj * (long long)K * 9;
+  const double* pm = PMg + traj * (long long)K * 3;
+  const double* pp = PPg + traj * (long long)K * 9;
+  const double dt0 = a.d.dt0, tol = clip_tol<double>();
+  const int max_steps = a.d.max_steps;
+  GradAcc g;
+  for (int i = 0; i < 3; ++i) g.th[i] = g.H[i] = 0.0;
+  for (int i = 0; i < 6; ++i) g.lql[i] = 0.0;
+  g.R = g.d = 0.0;
+  St<double, 3> lam;  // adjoint of the PREDICTED state entering update k+1 (zero beyond the last observation)
+  for (int i = 0; i < 3; ++i) lam.m[i] = 0.0;
+  for (int i = 0; i < 6; ++i) lam.P[i] = 0.0;
+  auto load_state = [&](const double* mrow, const double* prow, St<double, 3>& s) {
+    for (int i = 0; i < 3; ++i) s.m[i] = mrow[i];
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) s.P[pidx<3>(i, j)] = prow[i * 3 + j];
+  };
+  for (int k = K - 1; k >= 0; --k) {
+    if (k < K - 1) {
+      // ---- predict over [t_k, t_{k+1}], backwards ----
+      St<double, 3> y0;
+      load_state(fm + (long long)k * 3, fp + (long long)k * 9, y0);
+      const double t0 = Tm[k], t1 = Tm[k + 1];
+      // number of substeps (diffrax stepping rule); the time grid does not depend on the state
+      int q = 0;
+      {
+        double tp = t0, tn = fmin(t0 + dt0, t1);
+        while (tp < t1 && q < max_steps) {
+          ++q;
+          tp = tn;
+          const double c = tp + dt0;
+          tn = c > t1 - tol ? t1 : c;
+        }
+      }
+      // start state of substep i for i % stride == 0 (i / stride < GR_CKPT) is kept; the others are re-integrated
+      const int stride = (q + GR_CKPT - 1) / GR_CKPT > 0 ? (q + GR_CKPT - 1) / GR_CKPT : 1;
+      St<double, 3> ck[GR_CKPT];
+      {
+        St<double, 3> s = y0;
+        double tp = t0, tn = fmin(t0 + dt0, t1);
+        for (int i = 0; i < q; ++i) {
+          if (i % stride == 0) ck[i / stride] = s;
+          rk_step<double, DriftL63, SOLVER>(th, lql, s, tn - tp);
+          tp = tn;
+          const double c = tp + dt0;
+          tn = c > t1 - tol ? t1 : c;
+        }
+      }
+      for (int i = q - 1; i >= 0; --i) {
+        // (tprev, tnext) and the start state of substep i
+        const int base = (i / stride) * stride;
+        double tp = t0, tn = fmin(t0 + dt0, t1);
+        for (int u = 0; u < base; ++u) {
+          tp = tn;
+          const double c = tp + dt0;
+          tn = c > t1 - tol ? t1 : c;
+        }
+        St<double, 3> s = ck[i / stride];
+        for (int u = base; u < i; ++u) {
+          rk_step<double, DriftL63, SOLVER>(th, lql, s, tn - tp);
+          tp = tn;
+          const double c = tp + dt0;
+          tn = c > t1 - tol ? t1 : c;
+        }
+        l63_rk_step_vjp<SOLVER>(th, lql, s, tn - tp, lam, g);
+      }
+    }
+    // ---- update k, backwards.  Forward (ekf_update, scalar emission):  HP = H P, S = HP.H + R, r = y - H.m - d,
+    //      ll = -r^2 / (2 S) - log(S) / 2 - c,  rb = 1 / (S + 1e-9),  K = HP rb,  P_f = P - S K K^T,  m_f = m + K r ----
+    St<double, 3> sp;  // the predicted state that entered the update
+    if (k == 0) {
+      const double* m0 = a.in[CDK_IN_M0] + traj * a.in_stride[CDK_IN_M0];
+      const double* P0 = a.in[CDK_IN_P0] + traj * a.in_stride[CDK_IN_P0];
+      load_state(m0, P0, sp);
+    } else {
+      load_state(pm + (long long)(k - 1) * 3, pp + (long long)(k - 1) * 9, sp);
+    }
+    double Pf[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Pf[i][j] = sp.P[pidx<3>(i, j)];
+    double HP[3], S = R, hm = dv;
+    for (int j = 0; j < 3; ++j) HP[j] = H[0] * Pf[0][j] + H[1] * Pf[1][j] + H[2] * Pf[2][j];
+    for (int q2 = 0; q2 < 3; ++q2) {
+      S += HP[q2] * H[q2];
+      hm += H[q2] * sp.m[q2];
+    }
+    const double r = Y[k] - hm, iS = 1.0 / S, rb = 1.0 / (S + 1e-9);
+    double Kg[3];
+    for (int j = 0; j < 3; ++j) Kg[j] = HP[j] * rb;
+    // adjoints in: lam.m = dL/dm_f, lam.P = dL/dP_f (full-matrix, symmetric)
+    double A[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) A[i][j] = lam.P[pidx<3>(i, j)];
+    double AK[3];  // A K
+    for (int i = 0; i < 3; ++i) AK[i] = A[i][0] * Kg[0] + A[i][1] * Kg[1] + A[i][2] * Kg[2];
+    double aK[3], a_r = 0.0, a_S = 0.0;
+    // m_f = m + K r
+    for (int i = 0; i < 3; ++i) {
+      aK[i] = lam.m[i] * r;
+      a_r += Kg[i] * lam.m[i];
+    }
+    // P_f = P - S K K^T
+    a_S -= Kg[0] * AK[0] + Kg[1] * AK[1] + Kg[2] * AK[2];
+    for (int i = 0; i < 3; ++i) aK[i] -= 2.0 * S * AK[i];
+    // K = HP rb
+    double aHP[3], a_rb = 0.0;
+    for (int j = 0; j < 3; ++j) {
+      aHP[j] = aK[j] * rb;
+      a_rb += HP[j] * aK[j];
+    }
+    a_S -= rb * rb * a_rb;  // rb = 1 / (S + eps)
+    // ll_k
+    a_r += -r * iS;
+    a_S += 0.5 * r * r * iS * iS - 0.5 * iS;
+    // r = y - hm, hm = H.m + d
+    const double a_hm = -a_r;
+    g.d += a_hm;
+    // S = HP.H + R
+    g.R += a_S;
+    for (int j = 0; j < 3; ++j) {
+      aHP[j] += a_S * H[j];
+      g.H[j] += a_S * HP[j] + a_hm * sp.m[j];
+    }
+    // HP_j = sum_i H_i P_ij
+    for (int i = 0; i < 3; ++i) g.H[i] += Pf[i][0] * aHP[0] + Pf[i][1] * aHP[1] + Pf[i][2] * aHP[2];
+    // adjoint of the predicted state: dL/dm = lam.m + H a_hm;  dL/dP = A + sym(H aHP^T)
+    for (int i = 0; i < 3; ++i) lam.m[i] += H[i] * a_hm;
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) lam.P[pidx<3>(i, j)] += 0.5 * (H[i] * aHP[j] + H[j] * aHP[i]);
+  }
+  // ---- columns: theta 3 | LQL packed 6 | R | d | H 3 | m0 3 | P0 packed 6 (off-diagonals of symmetric parameters: both
+  //      mirror entries move, i.e. twice the symmetric entry-wise gradient) ----
+  double* out = grad + traj * CDK_GRAD_COLS_L63;
+  for (int i = 0; i < 3; ++i) out[i] = g.th[i];
+  const bool offd[6] = {false, true, true, false, true, false};
+  for (int e = 0; e < 6; ++e) out[3 + e] = offd[e] ? 2.0 * g.lql[e] : g.lql[e];
+  out[9] = g.R;
+  out[10] = g.d;
+  for (int i = 0; i < 3; ++i) out[11 + i] = g.H[i];
+  for (int i = 0; i < 3; ++i) out[14 + i] = lam.m[i];
+  for (int e = 0; e < 6; ++e) out[17 + e] = offd[e] ? 2.0 * lam.P[e] : lam.P[e];
+}
+
 typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1447,7 +1731,33 @@ int launch_ekf_l63_grad(const KArgs<double>& a, double* grad, cudaStream_t s) {
   if (d.N == 0) return CDK_OK;
   const long long blocks = (d.N + 127) / 128;
   if (blocks > 2147483647LL) return CDK_E_SIZE;
-  const int groups = d.reserved[3] ? d.reserved[3] : 1;
+  if (a.out[CDK_OUT_SCRATCH] && (d.reserved[3] & CDK_GRAD_REVERSE)) {
+    // reverse mode: forward filter into the scratch block (FM | FP | PM | PP, N*K*24 doubles), then ONE backward launch
+    double* sc = static_cast<double*>(a.out[CDK_OUT_SCRATCH]);
+    const long long NK = d.N * (long long)d.K;
+    KArgs<double> f = a;
+    f.d.reserved[3] = 0;
+    f.out[CDK_OUT_FM] = sc;
+    f.out[CDK_OUT_FP] = sc + NK * 3;
+    f.out[CDK_OUT_PM] = sc + NK * 12;
+    f.out[CDK_OUT_PP] = sc + NK * 15;
+    f.out[CDK_OUT_LLCUM] = nullptr;
+    f.out[CDK_OUT_GRAD] = nullptr;
+    f.out[CDK_OUT_SCRATCH] = nullptr;
+    int rc = launch_ekf_small<double>(f, s);
+    if (rc != CDK_OK) return rc;
+    const double *FM = sc, *FP = sc + NK * 3, *PM = sc + NK * 12, *PP = sc + NK * 15;
+    switch (d.solver) {
+      case CDK_RK4: ekf_l63_grad_rev_kernel<CDK_RK4><<<(unsigned)blocks, 128, 0, s>>>(a, FM, FP, PM, PP, grad); break;
+      case CDK_DOPRI5: ekf_l63_grad_rev_kernel<CDK_DOPRI5><<<(unsigned)blocks, 128, 0, s>>>(a, FM, FP, PM, PP, grad); break;
+      case CDK_EULER: ekf_l63_grad_rev_kernel<CDK_EULER><<<(unsigned)blocks, 128, 0, s>>>(a, FM, FP, PM, PP, grad); break;
+      case CDK_HEUN: ekf_l63_grad_rev_kernel<CDK_HEUN><<<(unsigned)blocks, 128, 0, s>>>(a, FM, FP, PM, PP, grad); break;
+      default: return CDK_E_UNSUPPORTED;
+    }
+    note_launch();
+    return check_launch("ekf_l63_grad_rev_kernel");
+  }
+  const int groups = (d.reserved[3] & 127) ? (d.reserved[3] & 127) : 1;
   static const int kinds[7] = {CDK_GRAD_THETA, CDK_GRAD_LQL, CDK_GRAD_R, CDK_GRAD_D, CDK_GRAD_H, CDK_GRAD_M0, CDK_GRAD_P0};
   static const int count[7] = {3, 6, 1, 1, 3, 3, 6};
   int col = 0;

@@ -183,6 +183,10 @@ CDK_DECL(cdk_enkf_filter_f32);
  * bit mask of the column groups to compute, in that order (0 = theta only); other columns are left untouched.  Today:
  * Lorenz-63 drift, scalar emission, num_iter = 1, state_order first / second; anything else returns CDK_E_UNSUPPORTED. */
 #define CDK_GRAD_COLS_L63 23
+/* desc.reserved[3] bit 7: REVERSE mode -- all 23 columns from ONE backward launch behind a forward filter pass whose moments
+ * go to out[CDK_OUT_SCRATCH] (cdk_scratch_bytes(desc, "cdk_ekf_grad") = N*K*24*8 bytes); ~4 filter passes in total instead
+ * of ~2.2 per column.  Without the bit (or without scratch) the forward-mode kernels run, one launch per requested column. */
+#define CDK_GRAD_REVERSE 128
 CDK_DECL(cdk_ekf_grad_f64);
 
 /* Forward sample paths of the model (cdnlgssm_path_sample, cd_nonlinear/models.py:525-656; what

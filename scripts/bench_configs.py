@@ -116,7 +116,9 @@ def c3(scale):
     ms = timeit(lambda: cd.cdnlgssm_filter(p, y32, t32[..., None], hp))
     out["fp32 variant, all outputs"] = dict(ms=ms, obs_steps_per_s=N * K / ms * 1e3)
     ms = timeit(lambda: cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp), reps=2)
-    out["ll + d ll / d (sigma, rho, beta)"] = dict(ms=ms, obs_steps_per_s=N * K / ms * 1e3)
+    out["ll + d ll / d (sigma, rho, beta), forward mode"] = dict(ms=ms, obs_steps_per_s=N * K / ms * 1e3)
+    ms = timeit(lambda: cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp, wrt="all"), reps=2)
+    out["ll + gradient w.r.t. ALL parameters (23 columns), reverse mode"] = dict(ms=ms, obs_steps_per_s=N * K / ms * 1e3)
     return dict(config=f"C3 EKF Lorenz-63 N={N} K=1000", **out)
 
 

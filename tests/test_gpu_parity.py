@@ -570,7 +570,9 @@ def test_ekf_loglik_gradient_all_parameter_groups():
     # the gradient matrices of symmetric parameters are symmetric; the default group is the drift alone
     assert np.allclose(grads["diffusion_cov"], np.swapaxes(grads["diffusion_cov"], 1, 2))
     ll2, g2 = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp)
-    assert set(g2) == {"sigma", "rho", "beta"} and np.array_equal(g2["rho"], grads["rho"]) and np.array_equal(ll2, ll)
+    # (the drift-only default runs the forward-mode kernels, wrt="all" the reverse-mode one: equal to rounding)
+    assert set(g2) == {"sigma", "rho", "beta"} and np.allclose(g2["rho"], grads["rho"], rtol=1e-10, atol=0)
+    assert np.allclose(ll2, ll, rtol=1e-13, atol=0)
 
 
 def test_streaming_filter_in_chunks_matches_one_call():
@@ -601,3 +603,40 @@ def test_streaming_filter_in_chunks_matches_one_call():
     streaming.filter_in_chunks(lambda yy, tt: cd.cdlgssm_filter(p, yy, tt, hp), y, t, 16, consume)
     assert seen == [(0, 16), (16, 32), (32, 48), (48, 53)]
     assert torch.equal(got_ll, ref.marginal_loglik) and torch.equal(got_pp, ref.predicted_covariances)
+
+
+@pytest.mark.parametrize("solver,dt0", [("rk4", 0.0025), ("rk4", 0.0006), ("heun", 0.002), ("euler", 0.002), ("dopri5", 0.01)])
+def test_ekf_loglik_gradient_reverse_mode_matches_forward_mode(solver, dt0, monkeypatch):
+    """the reverse-mode kernel (forward filter + ONE backward launch for all 23 columns) against the
+    forward-mode kernels (one launch per column, themselves checked against central differences of the oracle above): both
+    are exact derivatives of the same discrete filter, so they agree to rounding.  dt0 = 0.0006 gives ~17 substeps per gap:
+    more than the 8 substep checkpoints, i.e. the re-integration path."""
+    cd = api()
+    N, K = 7, 40
+    t, y = c3_problem(N, K, seed=33)
+    rng = np.random.default_rng(4)
+    A = rng.standard_normal((3, 3))
+    g = dict(m0=np.array([1.0, 1.0, 20.0]), P0=2 * np.eye(3) + 0.1 * (A + A.T), drift="lorenz63",
+             theta=np.array([10.0, 28.0, 8.0 / 3.0]), L=np.eye(3) + 0.2 * rng.standard_normal((3, 3)),
+             Qc=np.eye(3) + 0.05 * (A @ A.T), H=np.array([[1.0, 0.3, -0.2]]), R=0.7 * np.eye(1), d=np.array([0.1]))
+    hp = cd.EKFHyperParams(dt_final=0.004, diffeqsolve_settings={"solver": solver, "dt0": dt0})
+    monkeypatch.setenv("CDK_GRAD_MODE", "forward")
+    ll_f, gf = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp, wrt="all")
+    monkeypatch.setenv("CDK_GRAD_MODE", "reverse")
+    ll_r, gr = cd.ekf_marginal_log_prob_and_grad(nonlinear_params_api(g), y, t[..., None], hp, wrt="all")
+    assert set(gf) == set(gr) and max_rel_err(ll_r, ll_f) < 1e-12
+    for name in sorted(gf):
+        scale = np.max(np.abs(gf[name]))
+        err = np.max(np.abs(gr[name] - gf[name])) / scale
+        record(f"grad_reverse_vs_forward_{solver}_{dt0}:{name}", err)
+        assert err < 1e-9, (name, err)
+    # the default ("auto") picks reverse mode as soon as more than the drift group is requested; per-trajectory parameters
+    monkeypatch.setenv("CDK_GRAD_MODE", "auto")
+    th = np.array([10.0, 28.0, 8.0 / 3.0])[None] * (1 + 0.03 * rng.standard_normal((N, 3)))
+    p = nonlinear_params_api(g)
+    p = p._replace(dynamics=p.dynamics._replace(drift=cd.LearnableLorenz63(sigma=th[:, 0], rho=th[:, 1], beta=th[:, 2])))
+    _, ga = cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp, wrt=("drift", "initial_mean"))
+    monkeypatch.setenv("CDK_GRAD_MODE", "forward")
+    _, gb = cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp, wrt=("drift", "initial_mean"))
+    for name in ("sigma", "rho", "beta", "initial_mean"):
+        assert np.max(np.abs(ga[name] - gb[name])) < 1e-9 * np.max(np.abs(gb[name])), name
