@@ -640,3 +640,53 @@ def test_ekf_loglik_gradient_reverse_mode_matches_forward_mode(solver, dt0, monk
     _, gb = cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp, wrt=("drift", "initial_mean"))
     for name in ("sigma", "rho", "beta", "initial_mean"):
         assert np.max(np.abs(ga[name] - gb[name])) < 1e-9 * np.max(np.abs(gb[name])), name
+
+
+def test_torch_autograd_wrapper_around_the_reverse_mode_kernel():
+    """cd_dynamax_b200.autograd.ekf_marginal_log_prob: the custom_vjp-shaped wrapper (forward = CUDA filter, backward = the
+    reverse-mode kernel).  `(-ll.sum()).backward()` -- fit_sgd's loss -- must put the summed gradients on shared leaves."""
+    import torch
+    from cd_dynamax_b200 import autograd
+    cd = api()
+    N, K = 5, 30
+    t, y = c3_problem(N, K, seed=3)
+    dev = torch.device("cuda")
+    T = lambda a, rg=True: torch.tensor(np.asarray(a, dtype=np.float64), device=dev, requires_grad=rg)
+    leaves = dict(sigma=T(10.0), rho=T(28.0), beta=T(8.0 / 3.0), L=T(np.eye(3)), Qc=T(np.eye(3) + 0.05), R=T([[0.7]]), d=T([0.1]),
+                  H=T([[1.0, 0.3, -0.2]]), m0=T([1.0, 1.0, 20.0]), P0=T(2 * np.eye(3)))
+    p = cd.ParamsCDNLGSSM(
+        initial=cd.ParamsLGSSMInitial(mean=cd.LearnableVector(leaves["m0"]), cov=cd.LearnableMatrix(leaves["P0"])),
+        dynamics=cd.ParamsCDNLGSSMDynamics(drift=cd.LearnableLorenz63(sigma=leaves["sigma"], rho=leaves["rho"], beta=leaves["beta"]),
+                                           diffusion_coefficient=cd.LearnableMatrix(leaves["L"]),
+                                           diffusion_cov=cd.LearnableMatrix(leaves["Qc"])),
+        emissions=cd.ParamsCDNLGSSMEmissions(emission_function=cd.LearnableLinear(weights=leaves["H"], bias=leaves["d"]),
+                                             emission_cov=cd.LearnableMatrix(leaves["R"])))
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    yd, td = torch.as_tensor(y, device=dev), torch.as_tensor(t, device=dev)[..., None]
+    ll = autograd.ekf_marginal_log_prob(p, yd, td, hp)
+    assert ll.shape == (N,) and ll.requires_grad
+    (-ll.sum()).backward()
+    with torch.no_grad():
+        pd = jax_like_detach(p)
+        ll0, g = cd.ekf_marginal_log_prob_and_grad(pd, yd, td, hp, wrt="all")
+    assert torch.allclose(ll.detach(), ll0, rtol=1e-13, atol=0)
+    for leaf, name in (("sigma", "sigma"), ("rho", "rho"), ("Qc", "diffusion_cov"), ("L", "diffusion_coefficient"), ("R", "emission_cov"),
+                       ("H", "emission_weights"), ("m0", "initial_mean"), ("P0", "initial_cov"), ("d", "emission_bias")):
+        want = -g[name].sum(0)
+        assert torch.allclose(leaves[leaf].grad, want.reshape(leaves[leaf].shape), rtol=1e-10, atol=1e-12), name
+
+
+def jax_like_detach(p):
+    """The same parameter tuple with every torch leaf detached."""
+    import torch
+    det = lambda x: x.detach() if isinstance(x, torch.Tensor) else x
+    cd = api()
+    return cd.ParamsCDNLGSSM(
+        initial=cd.ParamsLGSSMInitial(mean=cd.LearnableVector(det(p.initial.mean.params)), cov=cd.LearnableMatrix(det(p.initial.cov.params))),
+        dynamics=cd.ParamsCDNLGSSMDynamics(
+            drift=cd.LearnableLorenz63(sigma=det(p.dynamics.drift.sigma), rho=det(p.dynamics.drift.rho), beta=det(p.dynamics.drift.beta)),
+            diffusion_coefficient=cd.LearnableMatrix(det(p.dynamics.diffusion_coefficient.params)),
+            diffusion_cov=cd.LearnableMatrix(det(p.dynamics.diffusion_cov.params))),
+        emissions=cd.ParamsCDNLGSSMEmissions(
+            emission_function=cd.LearnableLinear(weights=det(p.emissions.emission_function.weights), bias=det(p.emissions.emission_function.bias)),
+            emission_cov=cd.LearnableMatrix(det(p.emissions.emission_cov.params))))
