@@ -7,7 +7,7 @@ from .continuous_discrete_linear_gaussian_ssm import (ContDiscreteLinearGaussian
                                                       make_cdlgssm_params)
 from .continuous_discrete_nonlinear_gaussian_ssm import (ContDiscreteNonlinearGaussianSSM, EKFHyperParams,
                                                          EnKFHyperParams, LearnableLinear, LearnableLorenz63,
-                                                         LearnableLorenz96, LearnableMatrix, LearnableQuadratic,
+                                                         LearnableLorenz96, LearnableMatrix, LearnableQuadratic, LearnableUserDrift,
                                                          LearnableVector, ParamsCDNLGSSM, ParamsCDNLGSSMDynamics,
                                                          ParamsCDNLGSSMEmissions, UKFHyperParams, cdnlgssm_filter,
                                                          cdnlgssm_smoother, ekf_marginal_log_prob_and_grad, GSSMForecast,

@@ -123,7 +123,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
     `desc_fields["flags"]` sets the CDK_FLAG_* bits (desc.reserved[2]); when the entry point then asks for device scratch
     (cdk_scratch_bytes, sized per trajectory) it is allocated here -- or taken from `scratch`, which is how the type-1
     smoother gets the pushforward cache its filter wrote -- and returned as out[OUT_SCRATCH]."""
-    lib = L.lib()
+    desc_fields = dict(desc_fields)
+    lib = L.lib(desc_fields.pop("lib_path", None))  # a variant library for a user-defined drift, else the stock one
     dev = device()
     d = L.new_desc()
     d.N, d.K, d.n, d.m = N, K, n, m
@@ -247,7 +248,8 @@ def run(entry: str, dt: str, N: int, K: int, n: int, m: int, inputs: Dict[int, o
         if scratch_row:
             out_ptrs[L.OUT_SCRATCH] = scratch.data_ptr() + lo * scratch_row
         rc = fn(ctypes.byref(d), in_ptrs, out_ptrs, ctypes.c_void_p(ks.cuda_stream))
-        L.check(rc, f"{entry}_{dt}")
+        if rc != 0:
+            raise L.CdkError(f"{entry}_{dt} failed with code {rc}: {lib.cdk_last_error().decode()}")
         if host_out:
             d2h.wait_stream(ks)
             with torch.cuda.stream(d2h):

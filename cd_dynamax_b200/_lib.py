@@ -10,7 +10,7 @@ NUM_IN, NUM_OUT = 16, 12
 (OUT_LL, OUT_FM, OUT_FP, OUT_PM, OUT_PP, OUT_LLCUM, OUT_SM, OUT_SP, OUT_SCROSS, OUT_STATUS, OUT_SCRATCH,
  OUT_GRAD) = range(12)
 SOLVERS = {"euler": 0, "heun": 1, "midpoint": 2, "ralston": 3, "bosh3": 4, "rk4": 5, "dopri5": 6}
-DRIFT_LINEAR, DRIFT_LORENZ63, DRIFT_LORENZ96, DRIFT_QUADRATIC = 0, 1, 2, 3
+DRIFT_LINEAR, DRIFT_LORENZ63, DRIFT_LORENZ96, DRIFT_QUADRATIC, DRIFT_USER = 0, 1, 2, 3, 4
 ORDERS = {"zeroth": 0, "first": 1, "second": 2}
 FLAG_KEEP_PUSHFORWARD = 1  # CDK_FLAG_KEEP_PUSHFORWARD (desc.reserved[2])
 FLAG_UKF_SIGMA_POINTS = 2  # CDK_FLAG_UKF_SIGMA_POINTS
@@ -24,7 +24,7 @@ ENTRY_POINTS = [f"cdk_{a}_{d}_{t}" for a, d in (("kf", "filter"), ("kf", "smooth
 ENTRY_POINTS.append("cdk_ekf_grad_f64")
 ENTRY_POINTS += ["cdk_sample_path_f64", "cdk_sample_path_f32", "cdk_emission_moments_f64", "cdk_emission_moments_f32"]
 OTHER_SYMBOLS = ["cdk_desc_init", "cdk_scratch_bytes", "cdk_ll_sum_f64", "cdk_ll_sum_f32", "cdk_ll_allreduce",
-                 "cdk_xla_custom_call", "cdk_xla_custom_call_status", "cdk_xla_last_rc", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_version",
+                 "cdk_xla_custom_call", "cdk_xla_custom_call_status", "cdk_xla_last_rc", "cdk_fma_probe_f64", "cdk_fma_probe_f32", "cdk_fma3_probe_f64", "cdk_dmma_probe_f64", "cdk_launch_count", "cdk_debug_set_trace", "cdk_has_user_drift", "cdk_version",
                  "cdk_last_error"]
 
 
@@ -48,18 +48,23 @@ class CdkError(RuntimeError):
 
 
 _lib = None
+_variants = {}
 
 
-def lib():
-    """Load libcdk.so once. Raises (never falls back) if the CUDA extension has not been built."""
+def lib(path=None):
+    """Load libcdk.so once (or, with `path`, a variant built by build.build_user_drift: same ABI, user drift compiled
+    in). Raises (never falls back) if the CUDA extension has not been built."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if path is not None and path in _variants:
+        return _variants[path]
+    target = path or LIB_PATH
+    if not os.path.exists(target):
         raise ImportError(
-            f"{LIB_PATH} is missing: build the CUDA extension first (python -m cd_dynamax_b200.build). "
+            f"{target} is missing: build the CUDA extension first (python -m cd_dynamax_b200.build). "
             "cd_dynamax_b200 has no CPU fallback.")
-    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    L = ctypes.CDLL(target, mode=ctypes.RTLD_GLOBAL if path is None else ctypes.RTLD_LOCAL)
     pp = ctypes.POINTER(ctypes.c_void_p)
     for name in ENTRY_POINTS:
         fn = getattr(L, name)
@@ -92,7 +97,11 @@ def lib():
     L.cdk_version.restype = ctypes.c_int
     L.cdk_last_error.restype = ctypes.c_char_p
     assert ctypes.sizeof(CdkDesc) == _c_sizeof_desc(L), "cdk_desc layout mismatch between Python and C"
-    _lib = L
+    L.cdk_has_user_drift.restype = ctypes.c_int
+    if path is None:
+        _lib = L
+    else:
+        _variants[path] = L
     return L
 
 

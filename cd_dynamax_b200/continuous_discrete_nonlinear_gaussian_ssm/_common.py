@@ -32,7 +32,11 @@ def nonlinear_inputs(params, Y, T, n, m):
         L.IN_L: _val(params.dynamics.diffusion_coefficient), L.IN_QC: _val(params.dynamics.diffusion_cov),
         L.IN_H: em.weights, L.IN_D: em.bias, L.IN_R: _val(params.emissions.emission_cov),
     }
-    return ins, dict(drift_id=drift_id, n_theta=n_theta, emission_id=0)
+    fields = dict(drift_id=drift_id, n_theta=n_theta, emission_id=0)
+    if drift_id == L.DRIFT_USER:
+        from .. import build as _build
+        fields["lib_path"] = _build.build_user_drift(params.dynamics.drift.device_code)
+    return ins, fields
 
 
 def run_filter(entry, params, emissions, t_emissions, inputs, output_fields, desc_fields, settings_sde=False,

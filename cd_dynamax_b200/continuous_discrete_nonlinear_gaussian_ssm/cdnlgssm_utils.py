@@ -74,6 +74,22 @@ class LearnableQuadratic(NamedTuple):
         return _np(self.a) + _np(self.B) @ x + np.einsum("ijk,j,k->i", _np(self.C), x, x)
 
 
+class LearnableUserDrift(NamedTuple):
+    """A user-defined drift (upstream: any `LearnableFunction.f`, cdnlgssm_utils.py:13-36).  A CUDA kernel
+    needs device code, so the drift is given as CUDA C++ source (see cd_dynamax_b200.build.build_user_drift for the three
+    functions it must define in `namespace cdk_user`) plus its parameter vector `theta` ([n_theta] or [N, n_theta]); the
+    first use compiles a variant of libcdk.so with that code in the drift registry (cached by content hash).  `py_f` is an
+    optional NumPy callable f(x, theta) for host-side use (e.g. the reference-style `.f`)."""
+    device_code: str
+    theta: Any
+    py_f: Any = None
+
+    def f(self, x, u=None, t=None):
+        if self.py_f is None:
+            raise NotImplementedError("no host-side callable was given for this user drift")
+        return self.py_f(_np(x), _np(self.theta))
+
+
 class ParamsCDNLGSSMDynamics(NamedTuple):
     """cdnlgssm_utils.py:88-130"""
     drift: Any
@@ -144,6 +160,10 @@ def drift_to_theta(drift, n: int):
             raise NotImplementedError("batched LearnableQuadratic parameters are not supported")
         theta = torch.cat([a.reshape(-1), B.reshape(-1), C.reshape(-1)])
         return L.DRIFT_QUADRATIC, theta, n + n * n + n * n * n
+    if name == "LearnableUserDrift":
+        th = T(drift.theta)
+        return L.DRIFT_USER, th, int(th.shape[-1]) if th.dim() else 1
     raise NotImplementedError(
         f"drift {name!r} is not in the kernel registry (LearnableLinear, LearnableLorenz63, LearnableLorenz96, "
-        "LearnableQuadratic): arbitrary Python drift callables cannot run inside a CUDA kernel")
+        "LearnableQuadratic) and is not a LearnableUserDrift (CUDA device code): arbitrary Python drift callables cannot "
+        "run inside a CUDA kernel")

@@ -59,6 +59,7 @@ static int expected_theta(const cdk_desc& d) {
     case CDK_DRIFT_LORENZ63: return 3;
     case CDK_DRIFT_LORENZ96: return 1;
     case CDK_DRIFT_QUADRATIC: return d.n + d.n * d.n + d.n * d.n * d.n;
+    case CDK_DRIFT_USER: return d.n_theta >= 0 ? d.n_theta : -1;
   }
   return -1;
 }
@@ -75,7 +76,9 @@ static int validate(const cdk_desc* d, const void* const* in, void* const* out, 
   const bool linear = algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH;
   const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
   if (!linear && algo != ALGO_EMISSIONS) {
-    if (d->drift_id < CDK_DRIFT_LINEAR || d->drift_id > CDK_DRIFT_QUADRATIC) return fail(CDK_E_ENUM, "unknown drift_id");
+    if (d->drift_id < CDK_DRIFT_LINEAR || d->drift_id > CDK_DRIFT_USER) return fail(CDK_E_ENUM, "unknown drift_id");
+    if (d->drift_id == CDK_DRIFT_USER && !cdk::has_user_drift())
+      return fail(CDK_E_UNSUPPORTED, "CDK_DRIFT_USER needs a variant library built with the user's device code (build_user_drift)");
     if (d->emission_id != CDK_EMISSION_LINEAR) return fail(CDK_E_ENUM, "unknown emission_id");
     if (d->n_theta != expected_theta(*d)) return fail(CDK_E_SIZE, "n_theta does not match drift_id / n");
     if (d->drift_id == CDK_DRIFT_LORENZ63 && d->n != 3) return fail(CDK_E_SIZE, "lorenz63 needs n == 3");
@@ -428,6 +431,7 @@ int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream)
 
 int cdk_debug_set_trace(void* devbuf) { return cdk::set_lw_trace(devbuf); }
 int64_t cdk_launch_count(void) { return (int64_t)g_launches.load(); }
+int cdk_has_user_drift(void) { return cdk::has_user_drift() ? 1 : 0; }
 int cdk_version(void) { return CDK_VERSION; }
 const char* cdk_last_error(void) { return g_err; }
 

@@ -161,6 +161,8 @@ inline bool fill_rt_tab(int solver, RtTab& t) {
   return false;
 }
 
+bool has_user_drift();  // cdk_generic.cu: was this library compiled with CDK_USER_DRIFT_HEADER?
+
 // host-side launch bookkeeping (cdk_api.cu)
 void note_launch();
 int check_launch(const char* what);

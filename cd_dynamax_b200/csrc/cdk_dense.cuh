@@ -9,6 +9,18 @@ namespace cdk {
 __host__ __device__ inline int ldp(int c) { return c | 1; }
 
 
+// ---- user-defined drift (CDK_DRIFT_USER): only in a variant library built with -DCDK_USER_DRIFT_HEADER="file" --------
+// The header defines, in namespace cdk_user:
+//   template <typename T, class XF> __device__ T f(const T* th, int n, int i, XF x);     // f_i; x(j) reads component j
+//   template <typename T> __device__ T jac(const T* th, int n, int i, int j, const T* x); // d f_i / d x_j
+//   template <typename T> __device__ T graddiv(const T* th, int n, int k, const T* x);    // sum_i d2 f_i / dx_i dx_k (or 0)
+#ifdef CDK_USER_DRIFT_HEADER
+#include CDK_USER_DRIFT_HEADER
+#define CDK_HAS_USER_DRIFT 1
+#else
+#define CDK_HAS_USER_DRIFT 0
+#endif
+
 // ---- drift registry, element-wise, on an arbitrary accessor x(j) ---------------------------------------------------
 template <typename T, class XF>
 __device__ __forceinline__ T drift_f(int id, const T* th, int n, int i, XF x) {
@@ -26,6 +38,9 @@ __device__ __forceinline__ T drift_f(int id, const T* th, int n, int i, XF x) {
       const int ip = i + 1 == n ? 0 : i + 1, im1 = i == 0 ? n - 1 : i - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
       return (x(ip) - x(im2)) * x(im1) - x(i) + th[0];
     }
+#if CDK_HAS_USER_DRIFT
+    case CDK_DRIFT_USER: return cdk_user::f<T>(th, n, i, x);
+#endif
     default: {  // quadratic
       const T* B = th + n;
       const T* C = th + n + n * n;
@@ -59,6 +74,9 @@ __device__ __forceinline__ T drift_jac(int id, const T* th, int n, int i, int j,
       if (j == i) v -= T(1);
       return v;
     }
+#if CDK_HAS_USER_DRIFT
+    case CDK_DRIFT_USER: return cdk_user::jac<T>(th, n, i, j, x);
+#endif
     default: {
       const T* B = th + n;
       const T* C = th + n + n * n;

@@ -23,7 +23,10 @@ enum { ODE_PUSH = 0, ODE_EKF = 1, ODE_MEAN = 2, ODE_BACK = 3, ODE_UKF = 4, ODE_U
 // Drifts whose Jacobian is a fixed sparse stencil evaluated on the fly (no n x n Jacobian buffer, no dense J P product)
 __host__ __device__ inline bool stencil_drift(int id) { return id == CDK_DRIFT_LORENZ63 || id == CDK_DRIFT_LORENZ96; }
 // The UKF runs in closed form (see ode_rhs, ODE_UKFC) unless the caller asks for literal sigma points
-__host__ __device__ inline bool ukf_closed(const cdk_desc& d) { return !(d.reserved[2] & CDK_FLAG_UKF_SIGMA_POINTS); }
+// (and always for a user-defined drift, which need not be a polynomial of degree <= 2)
+__host__ __device__ inline bool ukf_closed(const cdk_desc& d) {
+  return !(d.reserved[2] & CDK_FLAG_UKF_SIGMA_POINTS) && d.drift_id != CDK_DRIFT_USER;
+}
 
 template <typename T>
 struct GArgs {
@@ -163,11 +166,16 @@ __device__ void ode_rhs(const Ctx<T>& c, int kind, const T* ys, T* k, T dt) {
       J[i * ld + j] = drift_jac<T>(d.drift_id, th, n, i, j, mm);
     }
     __syncthreads();
-    const bool second = d.state_order == CDK_ORDER_SECOND && d.drift_id == CDK_DRIFT_QUADRATIC;
+    const bool second = d.state_order == CDK_ORDER_SECOND && (d.drift_id == CDK_DRIFT_QUADRATIC || d.drift_id == CDK_DRIFT_USER);
     FOR_T(i, n) {
       T f = drift_f<T>(d.drift_id, th, n, i, [&](int j) { return mm[j]; });
       if (second) {
         T s = T(0);
+#if CDK_HAS_USER_DRIFT
+        if (d.drift_id == CDK_DRIFT_USER) {
+          for (int q = 0; q < n; ++q) s += cdk_user::graddiv<T>(th, n, q, mm) * P[q * ld + i];
+        } else
+#endif
         for (int q = 0; q < n; ++q) s += drift_graddiv<T>(d.drift_id, th, n, q) * P[q * ld + i];
         f += T(0.5) * s;
       }
@@ -1112,6 +1120,8 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
   note_launch();
   return check_launch(smooth ? "generic_smooth_kernel" : "generic_filter_kernel");
 }
+
+bool has_user_drift() { return CDK_HAS_USER_DRIFT != 0; }
 
 template int launch_generic<double>(int, const KArgs<double>&, cudaStream_t);
 template int launch_generic<float>(int, const KArgs<float>&, cudaStream_t);

@@ -58,7 +58,13 @@ enum { CDK_EULER = 0, CDK_HEUN = 1, CDK_MIDPOINT = 2, CDK_RALSTON = 3, CDK_BOSH3
  *                LORENZ63  sigma, rho, beta                   (LearnableLorenz63 cdnlgssm_utils.py:63-83)
  *                LORENZ96  forcing F                          (BASELINE configs 4-5; not in the reference)
  *                QUADRATIC a[n], B[n*n], C[n*n*n]: f_i = a_i + B_ij x_j + C_ijk x_j x_k                      */
-enum { CDK_DRIFT_LINEAR = 0, CDK_DRIFT_LORENZ63 = 1, CDK_DRIFT_LORENZ96 = 2, CDK_DRIFT_QUADRATIC = 3 };
+enum { CDK_DRIFT_LINEAR = 0, CDK_DRIFT_LORENZ63 = 1, CDK_DRIFT_LORENZ96 = 2, CDK_DRIFT_QUADRATIC = 3,
+       /* USER: a drift compiled INTO a variant of this library (the reference takes any Python callable,
+        * cdnlgssm_utils.py:13-36).  The caller supplies CUDA device code for f_i(x; theta) and dJ_ij(x; theta) (and,
+        * for EKF state_order 'second', g_k = sum_i d2 f_i / dx_i dx_k); cd_dynamax_b200.build.build_user_drift() compiles
+        * csrc/ with -DCDK_USER_DRIFT_HEADER=<that code> into lib/user/libcdk_user_<hash>.so, which exports this same ABI.
+        * theta: any n_theta >= 0 doubles.  The stock libcdk.so rejects this id. */
+       CDK_DRIFT_USER = 4 };
 /* emission registry: h(x) = H x + d (LearnableLinear) */
 enum { CDK_EMISSION_LINEAR = 0 };
 /* EKFHyperParams.state_order (inference_ekf.py:40) */
@@ -253,6 +259,8 @@ int cdk_debug_set_trace(void* devbuf);
 /* Number of kernels this library has launched since load (for bench.py's gpu_launches accounting). */
 int64_t cdk_launch_count(void);
 
+/* 1 when this library is a variant compiled with a user-defined drift (CDK_DRIFT_USER), 0 for the stock build. */
+int cdk_has_user_drift(void);
 int cdk_version(void);
 const char* cdk_last_error(void);
 

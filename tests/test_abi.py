@@ -185,3 +185,19 @@ def test_xla_status_returning_adaptor_reports_failures(lib, tmp_path):
     st = Status()
     lib.cdk_xla_custom_call_status(None, bufs, blob, len(blob), ctypes.byref(st))
     assert st.failed == 0 and lib.cdk_xla_last_rc() == 0
+
+
+def test_user_drift_variant_library_is_not_interposed_by_the_stock_one(lib):
+    """A variant built by build_user_drift exports the same symbols as libcdk.so and is loaded next to it; both are linked
+    -Bsymbolic so that each binds its own definitions (host-side validation only: no GPU needed)."""
+    from cd_dynamax_b200 import _lib
+    from cd_dynamax_b200 import build as b
+    example = os.path.join(ROOT, "cd_dynamax_b200", "examples", "vdp_drift.cuh")
+    var = _lib.lib(b.build_user_drift(open(example).read()))
+    assert lib.cdk_has_user_drift() == 0 and var.cdk_has_user_drift() == 1
+    ins = (ctypes.c_void_p * _lib.NUM_IN)()
+    outs = (ctypes.c_void_p * _lib.NUM_OUT)()
+    d = _lib.new_desc()
+    d.N, d.K, d.n, d.m, d.drift_id, d.n_theta = 0, 3, 2, 1, _lib.DRIFT_USER, 2
+    assert lib.cdk_ekf_filter_f64(ctypes.byref(d), ins, outs, None) == -4  # stock: CDK_E_UNSUPPORTED
+    assert var.cdk_ekf_filter_f64(ctypes.byref(d), ins, outs, None) == 0   # variant: valid (N = 0 is a no-op)
