@@ -347,62 +347,70 @@ __device__ bool ode_solve(const Ctx<T>& c, int kind, T* y, int S, T t0, T t1, T 
 }
 
 // Moment ODE of the Lorenz-96 drift (EKF first / second order -- identical for this drift, SURVEY F8 -- and the closed-form
-// unscented predict) for chain tableaux, with the RK state in REGISTERS: thread t owns the covariance entries
-// e = t + j * blockDim (j < EPT) and, for t < n, mean entry t; it keeps y, the running combination acc and its previous
-// stage increment k for them.  Only the STAGE INPUT lives in shared memory (two buffers, YS and KS, alternating), because a
-// covariance entry's derivative reads eight neighbours:
-//   d/dt P_rc = (J P)_rc + (J P)_cr + (L Qc L^T)_rc,   (J P)_rc = x_{r-1} (P_{r+1,c} - P_{r-2,c}) + (x_{r+1} - x_{r-2}) P_{r-1,c} - P_rc.
-// One barrier per RK stage and ~45 instructions per entry and stage, against four barriers and ~170 instructions (index
-// arithmetic of the run-time-n loops) for ode_solve + ode_rhs on the same ODE.
-constexpr int STENCIL_EPT = 7;  // 7 x 256 threads cover n = 40 (BASELINE config 4) and anything up to n = 42
+// unscented predict) for chain tableaux, with the RK state in REGISTERS.  Thread t owns a SEGMENT of one covariance row:
+// row r = t % n, columns [c0, c0 + SEG), c0 = SEG * (t / n) (and, for the first segment of a row, mean entry r); it keeps y,
+// the running combination and its previous stage increment for those entries.  Only the STAGE INPUT lives in shared memory
+// (two buffers, YS and KS, alternating: ONE barrier per stage), because an entry's derivative reads its neighbours:
+//   d/dt P_rc = (J P)_rc + (J P)_cr + (L Qc L^T)_rc,   (J P)_rc = x_{r-1} (P_{r+1,c} - P_{r-2,c}) + (x_{r+1} - x_{r-2}) P_{r-1,c} - P_rc,
+// and with P_{c',r} read as P_{r,c'} the transposed term needs only a sliding window of row r and of x.  Per stage and
+// thread: 10 + 10 window loads, 3 row coefficients, 3 column loads per entry -- ~190 instructions for 7 entries, against
+// ~500 with one entry per (thread, slot) and ~1,200 (index arithmetic of the run-time-n loops, four barriers) for
+// ode_solve + ode_rhs on the same ODE.
+constexpr int STENCIL_SEG = 7;  // 6 segments x 40 rows = 240 threads for n = 40 (BASELINE config 4)
+
+__host__ __device__ inline bool stencil_fits(int n, int threads) { return n >= 4 && n * ((n + STENCIL_SEG - 1) / STENCIL_SEG) <= threads; }
 
 template <typename T>
 struct StencilRegs {
-  unsigned xrow[STENCIL_EPT];    // r | c << 8
-  unsigned nbr[STENCIL_EPT];     // r+1 | r-1 << 8 | r-2 << 16   (cyclic)
-  unsigned nbc[STENCIL_EPT];     // c+1 | c-1 << 8 | c-2 << 16
-  int cnt;                       // entries this thread owns
+  int r, c0, cnt;              // row, first column, number of owned columns (0: idle thread)
+  int rp, rm1, rm2;            // cyclic row neighbours
+  int wc[STENCIL_SEG + 3];     // cyclic column indices c0 - 2 .. c0 + SEG
+  T lql[STENCIL_SEG];
 };
 
 template <typename T>
 __device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R) {
   const int n = c.L.n, ld = c.L.ldn;
-  R.cnt = 0;
+  const T* lql = c.p(c.L.LQL);
+  const int t = threadIdx.x;
+  R.r = t % n;
+  R.c0 = STENCIL_SEG * (t / n);
+  R.cnt = R.c0 < n ? (n - R.c0 < STENCIL_SEG ? n - R.c0 : STENCIL_SEG) : 0;
+  if (R.cnt == 0) R.c0 = 0;
+  R.rp = R.r + 1 == n ? 0 : R.r + 1;
+  R.rm1 = R.r == 0 ? n - 1 : R.r - 1;
+  R.rm2 = R.rm1 == 0 ? n - 1 : R.rm1 - 1;
 #pragma unroll
-  for (int j = 0; j < STENCIL_EPT; ++j) {
-    const int e = threadIdx.x + j * blockDim.x;
-    const bool v = e < n * n;
-    const int r = v ? e / n : 0, cc = v ? e - r * n : 0;
-    R.xrow[j] = (unsigned)r | ((unsigned)cc << 8);
-    {
-      const int rp = r + 1 == n ? 0 : r + 1, rm1 = r == 0 ? n - 1 : r - 1, rm2 = rm1 == 0 ? n - 1 : rm1 - 1;
-      const int cp = cc + 1 == n ? 0 : cc + 1, cm1 = cc == 0 ? n - 1 : cc - 1, cm2 = cm1 == 0 ? n - 1 : cm1 - 1;
-      R.nbr[j] = (unsigned)rp | ((unsigned)rm1 << 8) | ((unsigned)rm2 << 16);
-      R.nbc[j] = (unsigned)cp | ((unsigned)cm1 << 8) | ((unsigned)cm2 << 16);
-    }
-    if (v) R.cnt = j + 1;
+  for (int q = 0; q < STENCIL_SEG + 3; ++q) {
+    int col = R.c0 - 2 + q;
+    col = col < 0 ? col + n : col;
+    col = col >= n ? col - n : col;
+    col = col >= n ? col - n : col;  // (a short last segment can overshoot by more than one lap only for n < 4: excluded)
+    R.wc[q] = col;
   }
+#pragma unroll
+  for (int j = 0; j < STENCIL_SEG; ++j) R.lql[j] = j < R.cnt ? lql[R.r * ld + R.c0 + j] : T(0);
 }
 
 // Integrate (m, P) (shared memory, [MU | P] layout of `y`) from t0 to t1.  UKFC adds the unscented second-order mean term.
 template <typename T, bool UKFC>
 __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y, T t0, T t1, T dt0, int max_steps) {
+  constexpr int SEG = STENCIL_SEG;
   const Lay& L = c.L;
-  const int n = L.n, ld = L.ldn, poff = L.P - L.MU;
+  const int ld = L.ldn, poff = L.P - L.MU;
   const RtTab& tab = c.g.tab;
   const T F = c.p(L.TH)[0];
-  const T* lql = c.p(L.LQL);
-  const int tid = threadIdx.x;
-  const bool own_m = tid < n;
-  const int mp = tid + 1 == n ? 0 : tid + 1, mm1 = tid == 0 ? n - 1 : tid - 1, mm2 = mm1 == 0 ? n - 1 : mm1 - 1;
-  T yP[STENCIL_EPT], aP[STENCIL_EPT], kP[STENCIL_EPT];
+  const bool act = R.cnt > 0, own_m = act && R.c0 == 0;
+  const int rowoff = poff + R.r * ld + R.c0;
+  T yP[SEG], aP[SEG], kP[SEG];
   T ym = T(0), am = T(0), km = T(0);
 #pragma unroll
-  for (int j = 0; j < STENCIL_EPT; ++j) {
-    yP[j] = j < R.cnt ? y[poff + (R.xrow[j] & 0xff) * ld + (R.xrow[j] >> 8)] : T(0);
+  for (int j = 0; j < SEG; ++j) {
+    yP[j] = j < R.cnt ? y[rowoff + j] : T(0);
     kP[j] = T(0);
+    aP[j] = T(0);
   }
-  if (own_m) ym = y[tid];
+  if (own_m) ym = y[R.r];
   const T tol = clip_tol<T>();
   T tprev = t0, tnext = fmin(t0 + dt0, t1);
   int nsteps = 0;
@@ -411,7 +419,7 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
     if (nsteps >= max_steps) {
       hit = true;
 #pragma unroll
-      for (int j = 0; j < STENCIL_EPT; ++j) yP[j] = T(NAN);
+      for (int j = 0; j < SEG; ++j) yP[j] = T(NAN);
       ym = T(NAN);
       break;
     }
@@ -421,40 +429,50 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
       T* B = c.sh + ((st & 1) ? L.KS : L.YS);  // an integer select keeps the pointer in the shared window (LDS / STS)
       // stage input y + a k_{st-1} -> shared memory
 #pragma unroll
-      for (int j = 0; j < STENCIL_EPT; ++j)
-        if (j < R.cnt) B[poff + (R.xrow[j] & 0xff) * ld + (R.xrow[j] >> 8)] = st == 0 ? yP[j] : yP[j] + a * kP[j];
-      if (own_m) B[tid] = st == 0 ? ym : ym + a * km;
+      for (int j = 0; j < SEG; ++j)
+        if (j < R.cnt) B[rowoff + j] = st == 0 ? yP[j] : yP[j] + a * kP[j];
+      if (own_m) B[R.r] = st == 0 ? ym : ym + a * km;
       if (st == 0) {
 #pragma unroll
-        for (int j = 0; j < STENCIL_EPT; ++j) aP[j] = yP[j];
+        for (int j = 0; j < SEG; ++j) aP[j] = yP[j];
         am = ym;
       }
       __syncthreads();
-      const T* x = B;
-      const T* P = B + poff;
-      const T b = T(tab.b[st]);
+      if (act) {
+        const T* x = B;
+        const T* P = B + poff;
+        const T b = T(tab.b[st]);
+        T xw[SEG + 3], pr[SEG + 3];
 #pragma unroll
-      for (int j = 0; j < STENCIL_EPT; ++j) {
-        if (j < R.cnt) {
-          const int r = R.xrow[j] & 0xff, cc = R.xrow[j] >> 8;
-          const int rp = R.nbr[j] & 0xff, rm1 = (R.nbr[j] >> 8) & 0xff, rm2 = R.nbr[j] >> 16;
-          const int cp = R.nbc[j] & 0xff, cm1 = (R.nbc[j] >> 8) & 0xff, cm2 = R.nbc[j] >> 16;
-          const T jp_rc = x[rm1] * (P[rp * ld + cc] - P[rm2 * ld + cc]) + (x[rp] - x[rm2]) * P[rm1 * ld + cc] - P[r * ld + cc];
-          const T jp_cr = x[cm1] * (P[cp * ld + r] - P[cm2 * ld + r]) + (x[cp] - x[cm2]) * P[cm1 * ld + r] - P[cc * ld + r];
-          kP[j] = dt * ((jp_rc + jp_cr) + lql[r * ld + cc]);
-          aP[j] += b * kP[j];
+        for (int q = 0; q < SEG + 3; ++q) {
+          xw[q] = x[R.wc[q]];
+          pr[q] = P[R.r * ld + R.wc[q]];
         }
-      }
-      if (own_m) {
-        T f = (x[mp] - x[mm2]) * x[mm1] - x[tid] + F;
-        if (UKFC)  // 0.5 tr(Hess f_r P) = sym(P)_{r+1,r-1} - sym(P)_{r-2,r-1}
-          f += T(0.5) * (P[mp * ld + mm1] + P[mm1 * ld + mp]) - T(0.5) * (P[mm2 * ld + mm1] + P[mm1 * ld + mm2]);
-        km = dt * f;
-        am += b * km;
+        const T ar = x[R.rm1], br = x[R.rp] - x[R.rm2];
+        const T* Pu = P + R.rp * ld + R.c0;
+        const T* Pd1 = P + R.rm1 * ld + R.c0;
+        const T* Pd2 = P + R.rm2 * ld + R.c0;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+          if (j < R.cnt) {
+            const int q = j + 2;
+            const T jp_rc = ar * (Pu[j] - Pd2[j]) + br * Pd1[j] - pr[q];
+            const T jp_cr = xw[q - 1] * (pr[q + 1] - pr[q - 2]) + (xw[q + 1] - xw[q - 2]) * pr[q - 1] - pr[q];
+            kP[j] = dt * ((jp_rc + jp_cr) + R.lql[j]);
+            aP[j] += b * kP[j];
+          }
+        }
+        if (own_m) {
+          T f = br * ar - x[R.r] + F;
+          if (UKFC)  // 0.5 tr(Hess f_r P) = sym(P)_{r+1,r-1} - sym(P)_{r-2,r-1}
+            f += T(0.5) * (P[R.rp * ld + R.rm1] + P[R.rm1 * ld + R.rp]) - T(0.5) * (P[R.rm2 * ld + R.rm1] + P[R.rm1 * ld + R.rm2]);
+          km = dt * f;
+          am += b * km;
+        }
       }
     }
 #pragma unroll
-    for (int j = 0; j < STENCIL_EPT; ++j) yP[j] = aP[j];
+    for (int j = 0; j < SEG; ++j) yP[j] = aP[j];
     ym = am;
     ++nsteps;
     tprev = tnext;
@@ -463,9 +481,9 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
   }
   __syncthreads();  // the last stage's readers are done before the state block is rewritten
 #pragma unroll
-  for (int j = 0; j < STENCIL_EPT; ++j)
-    if (j < R.cnt) y[poff + (R.xrow[j] & 0xff) * ld + (R.xrow[j] >> 8)] = yP[j];
-  if (own_m) y[tid] = ym;
+  for (int j = 0; j < SEG; ++j)
+    if (j < R.cnt) y[rowoff + j] = yP[j];
+  if (own_m) y[R.r] = ym;
   __syncthreads();
   return hit;
 }
@@ -1107,8 +1125,7 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
   const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
   // Lorenz-96 moment ODE with a chain tableau: RK state in registers (ode_solve_stencil); CDK_GENERIC_REG_ODE=0 disables
   const cdk_desc& dd = g.k.d;
-  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && g.nslots == 1 &&
-                       dd.n * dd.n <= STENCIL_EPT * threads && dd.n <= 255 &&
+  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && g.nslots == 1 && stencil_fits(dd.n, threads) &&
                        ((algo == ALGO_EKF_FILTER && dd.state_order != CDK_ORDER_ZEROTH) || (algo == ALGO_UKF_FILTER && ukf_closed(dd)));
   auto kern = smooth ? generic_smooth_kernel<T> : (reg_ode ? generic_filter_kernel<T, true> : generic_filter_kernel<T, false>);
   if (smem > 48 * 1024) {
