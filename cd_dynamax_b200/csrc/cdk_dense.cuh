@@ -111,6 +111,9 @@ __device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
 template <typename T, bool TRANSA, bool TRANSB, class Epi>
 __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
                                         int Kd, Epi epi);
+template <typename T, bool TRANSA, bool TRANSB, class Epi>
+__device__ __forceinline__ void mm_dmma_w(int warp, int nwarp, const T* __restrict__ A, int lda, const T* __restrict__ B,
+                                          int ldb, int M, int N, int Kd, Epi epi);
 
 template <typename T>
 __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
@@ -171,26 +174,148 @@ __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
   }
 }
 
-// Solve (L L^T) X = B in place, B is [n x c] with leading dimension ldb; one thread per column. Ends with a barrier.
-// The reciprocal of the pivot is formed BEFORE the dependent dot-product chain of its row, so the long division latency
-// overlaps the chain instead of extending it (v * (1 / L_ii) is within an ulp of v / L_ii).
-template <typename T>
-__device__ void chol_solve(const T* L, int n, int ld, T* B, int c, int ldb) {
-  FOR_T(col, c) {
-    for (int i = 0; i < n; ++i) {
-      const T rinv = T(1) / L[i * ld + i];
-      T v = B[i * ldb + col];
-      for (int k = 0; k < i; ++k) v -= L[i * ld + k] * B[k * ldb + col];
-      B[i * ldb + col] = v * rinv;
+// The same factorisation run by ONE WARP (warp `w` of the CTA; the others return at once): register panels as above, the
+// trailing update on that warp's tensor-core tiles, __syncwarp instead of CTA barriers.  For the m x m innovation covariance
+// (m ~ 20) a CTA-wide trailing update buys nothing and its 2 barriers per panel park seven warps behind one; and the two
+// factorisations every measurement update needs -- chol(S) for the log-density, chol(sym(S) + 1e-9 I) for psd_solve -- are
+// independent, so two warps run them side by side (condition_on).  SYM: factor 0.5 (A + A^T) + boost I.
+// No barrier inside; the caller synchronises the CTA before other warps read L.
+template <typename T, bool SYM>
+__device__ void chol_warp(int w, const T* A, T* L, int n, int ld, T boost) {
+  if ((threadIdx.x >> 5) != w) return;
+  const int lane = threadIdx.x & 31;
+  for (int e = lane; e < n * ld; e += 32) {
+    const int i = e / ld, j = e - i * ld;
+    T v = T(0);
+    if (j < i) v = SYM ? T(0.5) * (A[e] + A[j * ld + i]) : A[e];
+    if (j == i) v = A[e] + boost;
+    L[e] = v;
+  }
+  __syncwarp();
+  for (int j0 = 0; j0 < n; j0 += 8) {
+    const int bs = n - j0 < 8 ? n - j0 : 8;
+    const int r0 = j0 + lane, r1 = r0 + 32;
+    const bool v0 = r0 < n, v1 = r1 < n;
+    T x[8], y[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      x[q] = (v0 && q < bs) ? L[r0 * ld + j0 + q] : T(0);
+      y[q] = (v1 && q < bs) ? L[r1 * ld + j0 + q] : T(0);
     }
-    for (int i = n - 1; i >= 0; --i) {
-      const T rinv = T(1) / L[i * ld + i];
-      T v = B[i * ldb + col];
-      for (int k = i + 1; k < n; ++k) v -= L[k * ld + i] * B[k * ldb + col];
-      B[i * ldb + col] = v * rinv;
+#pragma unroll
+    for (int jj = 0; jj < 8; ++jj) {
+      if (jj < bs) {
+        T a = x[jj], b = y[jj];
+#pragma unroll
+        for (int q = 0; q < jj; ++q) {
+          const T pq = __shfl_sync(0xffffffffu, x[q], jj);
+          a -= x[q] * pq;
+          b -= y[q] * pq;
+        }
+        const T sjj = __shfl_sync(0xffffffffu, a, jj);
+        const T rinv = rsqrt(sjj);
+        x[jj] = lane == jj ? sjj * rinv : (lane > jj ? a * rinv : T(0));
+        y[jj] = b * rinv;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      if (q < bs) {
+        if (v0) L[r0 * ld + j0 + q] = x[q];
+        if (v1) L[r1 * ld + j0 + q] = y[q];
+      }
+    }
+    __syncwarp();
+    const int M = n - j0 - bs;
+    if (M > 0) {
+      const T* Pn = L + (j0 + bs) * ld + j0;
+      T* W = L + (j0 + bs) * ld + (j0 + bs);
+      mm_dmma_w<T, false, true>(0, 1, Pn, ld, Pn, ld, M, M, bs, [&](int i, int c, double v) {
+        if (c <= i) W[i * ld + c] -= (T)v;
+      });
+      __syncwarp();
     }
   }
+}
+
+// Solve (L L^T) X = B, B is [n x c] with leading dimension ldb, X written to `X` (may alias B).  Ends with a barrier.
+// Each warp takes chunks of CB right-hand sides and keeps them in registers (lane r: rows r and r + 32); the substitutions
+// are column-oriented: at step i the lane owning row i scales its entries by the reciprocal pivot (all reciprocals formed up
+// front), CB shuffles broadcast them, and every lane below (forward) / above (backward) subtracts its L entry times the
+// broadcast values -- one shared-memory load and CB FMAs per lane and step, no barrier until the end.  (History: one
+// THREAD per right-hand side with serial dot products, ~21k cycles for m = 20, n = 40 with six of eight warps parked at
+// the barrier -- 17 % of the UKF observation-step, profiles/r02_generic_ukf_rowseg*.)  Chunks are dealt from the LAST warp
+// down so that warp 0, which evaluates the log-density first (mvn_ll_warp), gets the fewest.
+template <typename T, bool TWO>
+__device__ __forceinline__ void chol_solve_chunks(const T* L, int n, int ld, const T* B, T* X, int c, int ldb) {
+  constexpr int CB = 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int r0 = lane, r1 = lane + 32;
+  const bool v0 = r0 < n, v1 = TWO && r1 < n;
+  const T ri0 = v0 ? T(1) / L[r0 * ld + r0] : T(0);
+  const T ri1 = v1 ? T(1) / L[r1 * ld + r1] : T(0);
+  const int nchunk = (c + CB - 1) / CB;
+  for (int ch = nwarp - 1 - warp; ch < nchunk; ch += nwarp) {
+    const int col0 = ch * CB;
+    T x0[CB], x1[CB];
+#pragma unroll
+    for (int q = 0; q < CB; ++q) {
+      x0[q] = (v0 && col0 + q < c) ? B[r0 * ldb + col0 + q] : T(0);
+      x1[q] = (v1 && col0 + q < c) ? B[r1 * ldb + col0 + q] : T(0);
+    }
+    for (int i = 0; i < n; ++i) {  // L z = b
+      const int src = i & 31;
+      const bool hi = TWO && i >= 32;
+      const T l0 = (v0 && r0 > i) ? L[r0 * ld + i] : T(0);
+      const T l1 = (v1 && r1 > i) ? L[r1 * ld + i] : T(0);
+#pragma unroll
+      for (int q = 0; q < CB; ++q) {
+        const T z = __shfl_sync(0xffffffffu, hi ? x1[q] * ri1 : x0[q] * ri0, src);
+        if (lane == src) {
+          if (hi) x1[q] = z; else x0[q] = z;
+        }
+        x0[q] -= l0 * z;
+        if (TWO) x1[q] -= l1 * z;
+      }
+    }
+    for (int i = n - 1; i >= 0; --i) {  // L^T x = z
+      const int src = i & 31;
+      const bool hi = TWO && i >= 32;
+      const T l0 = r0 < i ? L[i * ld + r0] : T(0);
+      const T l1 = (TWO && r1 < i) ? L[i * ld + r1] : T(0);
+#pragma unroll
+      for (int q = 0; q < CB; ++q) {
+        const T z = __shfl_sync(0xffffffffu, hi ? x1[q] * ri1 : x0[q] * ri0, src);
+        if (lane == src) {
+          if (hi) x1[q] = z; else x0[q] = z;
+        }
+        x0[q] -= l0 * z;
+        if (TWO) x1[q] -= l1 * z;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < CB; ++q) {
+      if (col0 + q < c) {
+        if (v0) X[r0 * ldb + col0 + q] = x0[q];
+        if (v1) X[r1 * ldb + col0 + q] = x1[q];
+      }
+    }
+  }
+}
+
+template <typename T>
+__device__ void chol_solve(const T* L, int n, int ld, const T* B, T* X, int c, int ldb) {
+  if (n <= 32) {
+    chol_solve_chunks<T, false>(L, n, ld, B, X, c, ldb);
+  } else {
+    chol_solve_chunks<T, true>(L, n, ld, B, X, c, ldb);
+  }
   __syncthreads();
+}
+
+template <typename T>
+__device__ void chol_solve(const T* L, int n, int ld, T* B, int c, int ldb) {
+  chol_solve<T>(L, n, ld, B, B, c, ldb);
 }
 
 // log N(r; 0, L L^T) = -0.5 |L^-1 r|^2 - sum_i log L_ii - (m / 2) log(2 pi) for m <= 64, by WARP 0 (the MVN.log_prob of every
@@ -237,10 +362,17 @@ __device__ __forceinline__ void mvn_ll_warp(const T* __restrict__ L, int ld, con
 // C (8x8) lane -> (row lane/4, cols 2*(lane%4), +1).  Compared with one output element per thread (two shared-memory
 // operand loads per FMA) this needs 2 loads per 256 FMAs and 1/16 of the instructions.  Every thread of the CTA must
 // call it; no barrier inside (callers synchronise before the operands are read and after the epilogue writes).
+// mm_dmma_w: the tiles are dealt to `nwarp` warps, the caller being number `warp` (mm_dmma: all warps of the CTA).
 template <typename T, bool TRANSA, bool TRANSB, class Epi>
 __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
                                         int Kd, Epi epi) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  mm_dmma_w<T, TRANSA, TRANSB>(threadIdx.x >> 5, blockDim.x >> 5, A, lda, B, ldb, M, N, Kd, epi);
+}
+
+template <typename T, bool TRANSA, bool TRANSB, class Epi>
+__device__ __forceinline__ void mm_dmma_w(int warp, int nwarp, const T* __restrict__ A, int lda, const T* __restrict__ B,
+                                          int ldb, int M, int N, int Kd, Epi epi) {
+  const int lane = threadIdx.x & 31;
   const int gid = lane >> 2, tig = lane & 3;
   const int tm = (M + 7) >> 3, tn = (N + 7) >> 3;
   for (int t = warp; t < tm * tn; t += nwarp) {

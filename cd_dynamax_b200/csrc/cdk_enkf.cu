@@ -60,7 +60,7 @@ struct ELay {
     S = take(ts * m * ldm);
     SL = take(ts * m * ldm);
     KT = take(ts * m * ldn);
-    SK = take(ts * (m > n ? m : n) * ldn);
+    SK = take(ts * (m > n ? m : n) * ldp(m > n ? m : n));
     YV = take(ts * m);
     RV = take(ts * 2 * m);
     TH = take(ts * (nth > 0 ? nth : 1));
@@ -341,42 +341,24 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
     if (!ponly) {
     // ================= update (inference_enkf.py:92-148), every CTA of the cluster redundantly =================
     FOR_T(i, m) yv[i] = Y[(long long)k * m + i];
-    FOR_T(e, m * n) {  // HP = H Cxx  (= C_xy^T because h is linear)
-      const int p = e / n, j = e - p * n;
-      T s = T(0);
-      for (int q = 0; q < n; ++q) s += H[p * ldn + q] * Cxx[q * ldn + j];
-      HP[p * ldn + j] = s;
-    }
+    // HP = H Cxx (= C_xy^T because h is linear), S = H Cxx H^T + R: FP64 tensor cores
+    mm_dmma<T, false, false>(H, ldn, Cxx, ldn, m, n, n, [&](int p, int j, double v) { HP[p * ldn + j] = (T)v; });
     __syncthreads();
-    FOR_T(e, m * m) {  // S = H Cxx H^T + R
-      const int p = e / m, q2 = e - p * m;
-      T s = T(0);
-      for (int q = 0; q < n; ++q) s += HP[p * ldn + q] * H[q2 * ldn + q];
-      Sm[p * ldm + q2] = s + R[p * ldm + q2];
-    }
+    mm_dmma<T, false, true>(HP, ldn, H, ldn, m, m, n, [&](int p, int q2, double v) { Sm[p * ldm + q2] = (T)v + R[p * ldm + q2]; });
     FOR_T(p, m) {  // innovation of the ensemble mean
       T s = dv[p];
       for (int q = 0; q < n; ++q) s += H[p * ldn + q] * mean[q];
       rv[p] = yv[p] - s;
     }
     __syncthreads();
-    chol<T>(Sm, Sl, m, ldm, T(0));  // MVN(ybar, S).log_prob(y): un-boosted Cholesky (:129)
-    mvn_ll_warp<T>(Sl, ldm, rv, m, llsh);
-    // K^T = psd_solve(S, C_xy^T): chol(sym(S) + 1e-9 I)  (:141-143)
-    T* Sb = SK;
-    FOR_T(e, m * m) {
-      const int p = e / m, q2 = e - p * m;
-      Sb[p * ldm + q2] = T(0.5) * (Sm[p * ldm + q2] + Sm[q2 * ldm + p]);
-    }
+    // MVN(ybar, S).log_prob(y) factors S un-boosted (:129); K^T = psd_solve(S, C_xy^T) factors sym(S) + 1e-9 I (:141-143):
+    // one warp each, side by side (chol_warp); the un-boosted factor is parked in SK
+    chol_warp<T, false>(0, Sm, SK, m, ldm, T(0));
+    chol_warp<T, true>(blockDim.x > 32 ? 1 : 0, Sm, Sl, m, ldm, T(1e-9));
     __syncthreads();
+    mvn_ll_warp<T>(SK, ldm, rv, m, llsh);          // warp 0; the others start on the solve
+    chol_solve<T>(Sl, m, ldm, HP, Kt, n, ldn);     // ends with a barrier
     ll += *llsh;
-    chol<T>(Sb, Sl, m, ldm, T(1e-9));
-    FOR_T(e, m * n) {
-      const int p = e / n, j = e - p * n;
-      Kt[p * ldn + j] = HP[p * ldn + j];
-    }
-    __syncthreads();
-    chol_solve<T>(Sl, m, ldm, Kt, n, ldn);
     // per member: x += K ((y + chol(R) z) - (H x + d))   (:135-146)
     for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
       T x[NXA];

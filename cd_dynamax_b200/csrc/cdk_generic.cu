@@ -358,14 +358,16 @@ __device__ bool ode_solve(const Ctx<T>& c, int kind, T* y, int S, T t0, T t1, T 
 // ode_solve + ode_rhs on the same ODE.
 constexpr int STENCIL_SEG = 7;  // 6 segments x 40 rows = 240 threads for n = 40 (BASELINE config 4)
 
-__host__ __device__ inline bool stencil_fits(int n, int threads) { return n >= 4 && n * ((n + STENCIL_SEG - 1) / STENCIL_SEG) <= threads; }
+__host__ __device__ inline bool stencil_fits(int n, int threads) { return n >= 4 && n <= 255 && n * ((n + STENCIL_SEG - 1) / STENCIL_SEG) <= threads; }
 
 template <typename T>
 struct StencilRegs {
   int r, c0, cnt;              // row, first column, number of owned columns (0: idle thread)
   int rp, rm1, rm2;            // cyclic row neighbours
-  int wc[STENCIL_SEG + 3];     // cyclic column indices c0 - 2 .. c0 + SEG
+  unsigned wcp[(STENCIL_SEG + 3 + 3) / 4];  // cyclic column indices c0 - 2 .. c0 + SEG, one byte each (n <= 255): packed, so
+                                            // that the compiler neither spends 10 registers on them nor recomputes them
   T lql[STENCIL_SEG];
+  __device__ __forceinline__ int wc(int q) const { return (wcp[q >> 2] >> ((q & 3) * 8)) & 0xffu; }
 };
 
 template <typename T>
@@ -381,13 +383,17 @@ __device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R)
   R.rm1 = R.r == 0 ? n - 1 : R.r - 1;
   R.rm2 = R.rm1 == 0 ? n - 1 : R.rm1 - 1;
 #pragma unroll
+  for (int w = 0; w < (STENCIL_SEG + 3 + 3) / 4; ++w) R.wcp[w] = 0u;
+#pragma unroll
   for (int q = 0; q < STENCIL_SEG + 3; ++q) {
     int col = R.c0 - 2 + q;
     col = col < 0 ? col + n : col;
     col = col >= n ? col - n : col;
     col = col >= n ? col - n : col;  // (a short last segment can overshoot by more than one lap only for n < 4: excluded)
-    R.wc[q] = col;
+    R.wcp[q >> 2] |= (unsigned)col << ((q & 3) * 8);
   }
+#pragma unroll
+  for (int w = 0; w < (STENCIL_SEG + 3 + 3) / 4; ++w) asm volatile("" : "+r"(R.wcp[w]));  // opaque: never rematerialised
 #pragma unroll
   for (int j = 0; j < STENCIL_SEG; ++j) R.lql[j] = j < R.cnt ? lql[R.r * ld + R.c0 + j] : T(0);
 }
@@ -445,8 +451,9 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
         T xw[SEG + 3], pr[SEG + 3];
 #pragma unroll
         for (int q = 0; q < SEG + 3; ++q) {
-          xw[q] = x[R.wc[q]];
-          pr[q] = P[R.r * ld + R.wc[q]];
+          const int col = R.wc(q);
+          xw[q] = x[col];
+          pr[q] = P[R.r * ld + col];
         }
         const T ar = x[R.rm1], br = x[R.rp] - x[R.rm2];
         const T* Pu = P + R.rp * ld + R.c0;
@@ -722,19 +729,9 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
   const bool no_sym = algo == ALGO_UKF_FILTER;
   for (int it = 0; it < num_iter; ++it) {
     if (!ukf) {
-      FOR_T(e, m * n) {
-        const int a = e / n, j = e - a * n;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += H[a * ldn + q] * P[q * ldn + j];
-        HP[a * ldn + j] = s;
-      }
+      mm_dmma<T, false, false>(H, ldn, P, ldn, m, n, n, [&](int a, int j, double v) { HP[a * ldn + j] = (T)v; });
       __syncthreads();
-      FOR_T(e, m * m) {
-        const int a = e / m, b = e - a * m;
-        T s = T(0);
-        for (int q = 0; q < n; ++q) s += HP[a * ldn + q] * H[b * ldn + q];
-        Sm[a * ldm + b] = R[a * ldm + b] + s;
-      }
+      mm_dmma<T, false, true>(HP, ldn, H, ldn, m, m, n, [&](int a, int b, double v) { Sm[a * ldm + b] = R[a * ldm + b] + (T)v; });
     } else {
       // inference_ukf.py:162-203 with h(x) = H x + d:  Y_i^+- - yhat = +-c H L_i, X_i^+- - m = +-c L_i
       //   S = 2 w c^2 (H Lc)(H Lc)^T + R,  cross^T = 2 w c^2 (H Lc) Lc^T
@@ -769,39 +766,17 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
       rv[a] = yv[a] - s;  // yv already has D u subtracted (linear model)
     }
     __syncthreads();
-    if (it == 0) {
-      // MVN(.).log_prob(y): un-boosted Cholesky (TFP)
-      chol<T>(Sm, Sl, m, ldm, T(0));
-      mvn_ll_warp<T>(Sl, ldm, rv, m, &ll_sh);
-      __syncthreads();
-    }
-    // psd_solve(S, .): chol(sym(S) + 1e-9 I); symmetrise into SK (scratch, [m x ldm] fits), then factor into Sl
-    T* Sb = SK;
-    FOR_T(e, m * m) {
-      const int a = e / m, b = e - a * m;
-      Sb[a * ldm + b] = T(0.5) * (Sm[a * ldm + b] + Sm[b * ldm + a]);
-    }
+    // MVN(.).log_prob(y) factors S un-boosted (TFP); psd_solve(S, .) factors sym(S) + 1e-9 I: two independent m x m
+    // factorisations, one warp each, side by side.  The un-boosted factor is parked in SK (free until S Kt below).
+    const int w1 = blockDim.x > 32 ? 1 : 0;
+    if (it == 0) chol_warp<T, false>(0, Sm, SK, m, ldm, T(0));
+    chol_warp<T, true>(w1, Sm, Sl, m, ldm, T(1e-9));
     __syncthreads();
-    chol<T>(Sb, Sl, m, ldm, T(1e-9));
-    FOR_T(e, m * n) {
-      const int a = e / n, j = e - a * n;
-      Kt[a * ldn + j] = HP[a * ldn + j];
-    }
+    if (it == 0) mvn_ll_warp<T>(SK, ldm, rv, m, &ll_sh);  // warp 0 only; the others start on the solve
+    chol_solve<T>(Sl, m, ldm, HP, Kt, n, ldn);           // Kt = (sym(S) + 1e-9 I)^-1 H P; ends with a barrier
+    mm_dmma<T, false, false>(Sm, ldm, Kt, ldn, m, n, m, [&](int a, int j, double v) { SK[a * ldn + j] = (T)v; });
     __syncthreads();
-    chol_solve<T>(Sl, m, ldm, Kt, n, ldn);
-    FOR_T(e, m * n) {
-      const int a = e / n, j = e - a * n;
-      T s = T(0);
-      for (int b = 0; b < m; ++b) s += Sm[a * ldm + b] * Kt[b * ldn + j];
-      SK[a * ldn + j] = s;
-    }
-    __syncthreads();
-    FOR_T(e, n * n) {
-      const int i = e / n, j = e - i * n;
-      T s = T(0);
-      for (int a = 0; a < m; ++a) s += Kt[a * ldn + i] * SK[a * ldn + j];
-      P[i * ldn + j] -= s;
-    }
+    mm_dmma<T, true, false>(Kt, ldn, SK, ldn, n, n, m, [&](int i, int j, double v) { P[i * ldn + j] -= (T)v; });
     FOR_T(i, n) {
       T s = T(0);
       for (int a = 0; a < m; ++a) s += Kt[a * ldn + i] * rv[a];
