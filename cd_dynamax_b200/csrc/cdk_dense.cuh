@@ -111,7 +111,7 @@ __device__ __forceinline__ T drift_graddiv(int id, const T* th, int n, int k) {
 template <typename T, bool TRANSA, bool TRANSB, class Epi>
 __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
                                         int Kd, Epi epi);
-template <typename T, bool TRANSA, bool TRANSB, class Epi>
+template <typename T, bool TRANSA, bool TRANSB, bool LOWER = false, class Epi>
 __device__ __forceinline__ void mm_dmma_w(int warp, int nwarp, const T* __restrict__ A, int lda, const T* __restrict__ B,
                                           int ldb, int M, int N, int Kd, Epi epi);
 
@@ -178,24 +178,41 @@ __device__ void chol(const T* A, T* L, int n, int ld, T boost) {
 // trailing update on that warp's tensor-core tiles, __syncwarp instead of CTA barriers.  For the m x m innovation covariance
 // (m ~ 20) a CTA-wide trailing update buys nothing and its 2 barriers per panel park seven warps behind one; and the two
 // factorisations every measurement update needs -- chol(S) for the log-density, chol(sym(S) + 1e-9 I) for psd_solve -- are
-// independent, so two warps run them side by side (condition_on).  SYM: factor 0.5 (A + A^T) + boost I.
-// No barrier inside; the caller synchronises the CTA before other warps read L.
+// independent, so two warps run them side by side (condition_on).
+//
+// Working copy for chol_warp, written by the whole CTA (no barrier inside): the lower triangle of A, or of
+// 0.5 (A + A^T) (SYM), plus boost on the diagonal, zeros above.
 template <typename T, bool SYM>
-__device__ void chol_warp(int w, const T* A, T* L, int n, int ld, T boost) {
-  if ((threadIdx.x >> 5) != w) return;
-  const int lane = threadIdx.x & 31;
-  for (int e = lane; e < n * ld; e += 32) {
+__device__ __forceinline__ void chol_prep(const T* A, T* L, int n, int ld, T boost) {
+  FOR_T(e, n * ld) {
     const int i = e / ld, j = e - i * ld;
     T v = T(0);
     if (j < i) v = SYM ? T(0.5) * (A[e] + A[j * ld + i]) : A[e];
     if (j == i) v = A[e] + boost;
     L[e] = v;
   }
-  __syncwarp();
+}
+
+// 1 / sqrt(x): hardware seed (MUFU.RSQ64H) and two Newton steps, without the exception branches of rsqrt(); <= 2 ulp.
+// NaN for x < 0 -- the reference's behaviour for a non-PD matrix -- and for x = 0.
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+__device__ __forceinline__ float fast_rsqrt(float x) { return rsqrtf(x); }
+
+template <typename T, bool TWO>
+__device__ __forceinline__ void chol_warp_impl(T* L, int n, int ld) {
+  const int lane = threadIdx.x & 31;
   for (int j0 = 0; j0 < n; j0 += 8) {
     const int bs = n - j0 < 8 ? n - j0 : 8;
     const int r0 = j0 + lane, r1 = r0 + 32;
-    const bool v0 = r0 < n, v1 = r1 < n;
+    const bool v0 = r0 < n, v1 = TWO && r1 < n;
     T x[8], y[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -210,12 +227,12 @@ __device__ void chol_warp(int w, const T* A, T* L, int n, int ld, T boost) {
         for (int q = 0; q < jj; ++q) {
           const T pq = __shfl_sync(0xffffffffu, x[q], jj);
           a -= x[q] * pq;
-          b -= y[q] * pq;
+          if (TWO) b -= y[q] * pq;
         }
         const T sjj = __shfl_sync(0xffffffffu, a, jj);
-        const T rinv = rsqrt(sjj);
+        const T rinv = fast_rsqrt(sjj);
         x[jj] = lane == jj ? sjj * rinv : (lane > jj ? a * rinv : T(0));
-        y[jj] = b * rinv;
+        if (TWO) y[jj] = b * rinv;
       }
     }
 #pragma unroll
@@ -230,11 +247,23 @@ __device__ void chol_warp(int w, const T* A, T* L, int n, int ld, T boost) {
     if (M > 0) {
       const T* Pn = L + (j0 + bs) * ld + j0;
       T* W = L + (j0 + bs) * ld + (j0 + bs);
-      mm_dmma_w<T, false, true>(0, 1, Pn, ld, Pn, ld, M, M, bs, [&](int i, int c, double v) {
+      mm_dmma_w<T, false, true, true>(0, 1, Pn, ld, Pn, ld, M, M, bs, [&](int i, int c, double v) {
         if (c <= i) W[i * ld + c] -= (T)v;
       });
       __syncwarp();
     }
+  }
+}
+
+// In-place factorisation of a chol_prep working copy by warp `w` alone (the other warps return at once); the caller
+// synchronises the CTA before (the copy) and after (other warps reading L).
+template <typename T>
+__device__ void chol_warp(int w, T* L, int n, int ld) {
+  if ((threadIdx.x >> 5) != w) return;
+  if (n <= 32) {
+    chol_warp_impl<T, false>(L, n, ld);
+  } else {
+    chol_warp_impl<T, true>(L, n, ld);
   }
 }
 
@@ -369,7 +398,8 @@ __device__ __forceinline__ void mm_dmma(const T* __restrict__ A, int lda, const 
   mm_dmma_w<T, TRANSA, TRANSB>(threadIdx.x >> 5, blockDim.x >> 5, A, lda, B, ldb, M, N, Kd, epi);
 }
 
-template <typename T, bool TRANSA, bool TRANSB, class Epi>
+// LOWER: only the tiles that touch the lower triangle (row block >= column block).
+template <typename T, bool TRANSA, bool TRANSB, bool LOWER, class Epi>
 __device__ __forceinline__ void mm_dmma_w(int warp, int nwarp, const T* __restrict__ A, int lda, const T* __restrict__ B,
                                           int ldb, int M, int N, int Kd, Epi epi) {
   const int lane = threadIdx.x & 31;
@@ -377,6 +407,7 @@ __device__ __forceinline__ void mm_dmma_w(int warp, int nwarp, const T* __restri
   const int tm = (M + 7) >> 3, tn = (N + 7) >> 3;
   for (int t = warp; t < tm * tn; t += nwarp) {
     const int r0 = (t / tn) << 3, c0 = (t % tn) << 3;
+    if (LOWER && c0 > r0) continue;
     const int ia = r0 + gid, jb = c0 + gid;
     const bool va = ia < M, vb = jb < N;
     double d0 = 0.0, d1 = 0.0, e0 = 0.0, e1 = 0.0;

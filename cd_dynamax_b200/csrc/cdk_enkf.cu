@@ -353,8 +353,11 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
     __syncthreads();
     // MVN(ybar, S).log_prob(y) factors S un-boosted (:129); K^T = psd_solve(S, C_xy^T) factors sym(S) + 1e-9 I (:141-143):
     // one warp each, side by side (chol_warp); the un-boosted factor is parked in SK
-    chol_warp<T, false>(0, Sm, SK, m, ldm, T(0));
-    chol_warp<T, true>(blockDim.x > 32 ? 1 : 0, Sm, Sl, m, ldm, T(1e-9));
+    chol_prep<T, false>(Sm, SK, m, ldm, T(0));
+    chol_prep<T, true>(Sm, Sl, m, ldm, T(1e-9));
+    __syncthreads();
+    chol_warp<T>(0, SK, m, ldm);
+    chol_warp<T>(blockDim.x > 32 ? 1 : 0, Sl, m, ldm);
     __syncthreads();
     mvn_ll_warp<T>(SK, ldm, rv, m, llsh);          // warp 0; the others start on the solve
     chol_solve<T>(Sl, m, ldm, HP, Kt, n, ldn);     // ends with a barrier

@@ -28,19 +28,11 @@ __host__ __device__ inline bool ukf_closed(const cdk_desc& d) {
   return !(d.reserved[2] & CDK_FLAG_UKF_SIGMA_POINTS) && d.drift_id != CDK_DRIFT_USER;
 }
 
-template <typename T>
-struct GArgs {
-  KArgs<T> k;
-  RtTab tab;
-  int nslots;  // RK stage buffers kept in shared memory (1 for "chain" tableaux, S otherwise)
-  int algo;
-  int reg_ode;  // allow the register-resident Lorenz-96 moment ODE (ode_solve_stencil)
-};
-
 // shared-memory layout, computed identically on host (size) and device (offsets); units = elements of T
 struct Lay {
   int n, m, du, ldn, ldm, nn, S, nth, mpoff;
   int TH, LQL, H, R, DV, BV, BU, DU, YV, UV, MU, P, ODEY, YS, ACC, KS, J, W1, W2, W3, SM, SL, RV, MF, PF, C0, total;
+  Lay() = default;
   __host__ __device__ Lay(const cdk_desc& d, int algo, int nslots) {
     n = d.n; m = d.m; du = d.d_u; ldn = ldp(n); ldm = ldp(m); nn = n * ldn;
     const bool lin = algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH;
@@ -80,11 +72,22 @@ struct Lay {
 };
 
 template <typename T>
+struct GArgs {
+  KArgs<T> k;
+  RtTab tab;
+  int nslots;  // RK stage buffers kept in shared memory (1 for "chain" tableaux, S otherwise)
+  int algo;
+  int reg_ode;  // allow the register-resident Lorenz-96 moment ODE (ode_solve_stencil)
+  Lay lay;      // computed once on the host: the offsets are then constant-bank operands, not ~40 integer instructions
+                // the compiler re-derives from (n, m) wherever a register is short
+};
+
+template <typename T>
 struct Ctx {
   const GArgs<T>& g;
-  Lay L;
+  const Lay& L;
   T* sh;
-  __device__ Ctx(const GArgs<T>& g_, T* sh_) : g(g_), L(g_.k.d, g_.algo, g_.nslots), sh(sh_) {}
+  __device__ Ctx(const GArgs<T>& g_, T* sh_) : g(g_), L(g_.lay), sh(sh_) {}
   __device__ T* p(int off) const { return sh + off; }
 };
 
@@ -769,8 +772,11 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
     // MVN(.).log_prob(y) factors S un-boosted (TFP); psd_solve(S, .) factors sym(S) + 1e-9 I: two independent m x m
     // factorisations, one warp each, side by side.  The un-boosted factor is parked in SK (free until S Kt below).
     const int w1 = blockDim.x > 32 ? 1 : 0;
-    if (it == 0) chol_warp<T, false>(0, Sm, SK, m, ldm, T(0));
-    chol_warp<T, true>(w1, Sm, Sl, m, ldm, T(1e-9));
+    if (it == 0) chol_prep<T, false>(Sm, SK, m, ldm, T(0));
+    chol_prep<T, true>(Sm, Sl, m, ldm, T(1e-9));
+    __syncthreads();
+    if (it == 0) chol_warp<T>(0, SK, m, ldm);
+    chol_warp<T>(w1, Sl, m, ldm);
     __syncthreads();
     if (it == 0) mvn_ll_warp<T>(SK, ldm, rv, m, &ll_sh);  // warp 0 only; the others start on the solve
     chol_solve<T>(Sl, m, ldm, HP, Kt, n, ldn);           // Kt = (sym(S) + 1e-9 I)^-1 H P; ends with a barrier
@@ -1089,7 +1095,8 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
     return e && e[0] == '0' ? 0 : 1;
   }();
   g.reg_ode = reg_ode_env;
-  Lay L(g.k.d, algo, g.nslots);
+  g.lay = Lay(g.k.d, algo, g.nslots);
+  const Lay& L = g.lay;
   const size_t smem = (size_t)L.total * sizeof(T);
   int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
