@@ -351,54 +351,61 @@ __device__ bool ode_solve(const Ctx<T>& c, int kind, T* y, int S, T t0, T t1, T 
 
 // Moment ODE of the Lorenz-96 drift (EKF first / second order -- identical for this drift, SURVEY F8 -- and the closed-form
 // unscented predict) for chain tableaux, with the RK state in REGISTERS.  Thread t owns a SEGMENT of one covariance row:
-// row r = t % n, columns [c0, c0 + SEG), c0 = SEG * (t / n) (and, for the first segment of a row, mean entry r); it keeps y,
-// the running combination and its previous stage increment for those entries.  Only the STAGE INPUT lives in shared memory
-// (two buffers, YS and KS, alternating: ONE barrier per stage), because an entry's derivative reads its neighbours:
+// row r = t % n, columns [c0, c0 + SEG), c0 = min(SEG * (t / n), n - SEG) (the last segment of a row overlaps its neighbour
+// instead of being short: both owners compute and store identical values, and no entry needs a bounds predicate), and, for
+// the first segment of a row, mean entry r.  It keeps y, the running combination and the previous stage increment of its
+// entries.  Only the STAGE INPUT lives in shared memory (two buffers, YS and KS, alternating: ONE barrier per stage),
+// because an entry's derivative reads its neighbours:
 //   d/dt P_rc = (J P)_rc + (J P)_cr + (L Qc L^T)_rc,   (J P)_rc = x_{r-1} (P_{r+1,c} - P_{r-2,c}) + (x_{r+1} - x_{r-2}) P_{r-1,c} - P_rc,
-// and with P_{c',r} read as P_{r,c'} the transposed term needs only a sliding window of row r and of x.  Per stage and
-// thread: 10 + 10 window loads, 3 row coefficients, 3 column loads per entry -- ~190 instructions for 7 entries, against
-// ~500 with one entry per (thread, slot) and ~1,200 (index arithmetic of the run-time-n loops, four barriers) for
-// ode_solve + ode_rhs on the same ODE.
+// and with P_{c',r} read as P_{r,c'} the transposed term needs only a window of row r: the thread's own stage inputs
+// (already in registers) plus three halo entries.  Per stage and thread: 3 + 10 window loads, 3 row coefficients, 3 column
+// loads per entry (contiguous: immediate offsets from three row pointers) -- ~37 loads and ~150 instructions for 7
+// entries, against ~500 with one entry per (thread, slot) and ~1,200 (index arithmetic of the run-time-n loops, four
+// barriers) for ode_solve + ode_rhs on the same ODE.
 constexpr int STENCIL_SEG = 7;  // 6 segments x 40 rows = 240 threads for n = 40 (BASELINE config 4)
 
-__host__ __device__ inline bool stencil_fits(int n, int threads) { return n >= 4 && n <= 255 && n * ((n + STENCIL_SEG - 1) / STENCIL_SEG) <= threads; }
+__host__ __device__ inline bool stencil_fits(int n, int threads) {
+  return n >= STENCIL_SEG && n * ((n + STENCIL_SEG - 1) / STENCIL_SEG) <= threads;
+}
 
 template <typename T>
 struct StencilRegs {
-  int r, c0, cnt;              // row, first column, number of owned columns (0: idle thread)
-  int rp, rm1, rm2;            // cyclic row neighbours
-  unsigned wcp[(STENCIL_SEG + 3 + 3) / 4];  // cyclic column indices c0 - 2 .. c0 + SEG, one byte each (n <= 255): packed, so
-                                            // that the compiler neither spends 10 registers on them nor recomputes them
+  int act;                       // owns a segment
+  int own_m;                     // ... and mean entry r
+  int o_x, o_row;                // element offsets inside a stage buffer: x_{c0}, P_{r,c0}
+  int o_up, o_d1, o_d2;          // P_{r+1,c0}, P_{r-1,c0}, P_{r-2,c0}
+  int o_xl0, o_xl1, o_xh;        // x_{c0-2}, x_{c0-1}, x_{c0+SEG} (cyclic)
+  int o_pl0, o_pl1, o_ph;        // P_{r,c0-2}, P_{r,c0-1}, P_{r,c0+SEG} (cyclic)
+  int o_xr, o_xrp, o_xrm1, o_xrm2;  // x_r, x_{r+1}, x_{r-1}, x_{r-2}
+  int o_u0, o_u1, o_u2, o_u3;    // P_{r+1,r-1}, P_{r-1,r+1}, P_{r-2,r-1}, P_{r-1,r-2} (unscented mean term)
   T lql[STENCIL_SEG];
-  __device__ __forceinline__ int wc(int q) const { return (wcp[q >> 2] >> ((q & 3) * 8)) & 0xffu; }
 };
 
 template <typename T>
 __device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R) {
-  const int n = c.L.n, ld = c.L.ldn;
+  constexpr int SEG = STENCIL_SEG;
+  const int n = c.L.n, ld = c.L.ldn, poff = c.L.P - c.L.MU;
   const T* lql = c.p(c.L.LQL);
   const int t = threadIdx.x;
-  R.r = t % n;
-  R.c0 = STENCIL_SEG * (t / n);
-  R.cnt = R.c0 < n ? (n - R.c0 < STENCIL_SEG ? n - R.c0 : STENCIL_SEG) : 0;
-  if (R.cnt == 0) R.c0 = 0;
-  R.rp = R.r + 1 == n ? 0 : R.r + 1;
-  R.rm1 = R.r == 0 ? n - 1 : R.r - 1;
-  R.rm2 = R.rm1 == 0 ? n - 1 : R.rm1 - 1;
+  const int r = t % n, seg = t / n;
+  int c0 = SEG * seg;
+  R.act = c0 < n;
+  if (!R.act) c0 = 0;
+  if (c0 > n - SEG) c0 = n - SEG;
+  R.own_m = R.act && seg == 0;
+  auto wrap = [&](int q) { return q < 0 ? q + n : (q >= n ? q - n : q); };
+  const int rp = wrap(r + 1), rm1 = wrap(r - 1), rm2 = wrap(r - 2);
+  R.o_x = c0;
+  R.o_row = poff + r * ld + c0;
+  R.o_up = poff + rp * ld + c0;
+  R.o_d1 = poff + rm1 * ld + c0;
+  R.o_d2 = poff + rm2 * ld + c0;
+  R.o_xl0 = wrap(c0 - 2); R.o_xl1 = wrap(c0 - 1); R.o_xh = wrap(c0 + SEG);
+  R.o_pl0 = poff + r * ld + R.o_xl0; R.o_pl1 = poff + r * ld + R.o_xl1; R.o_ph = poff + r * ld + R.o_xh;
+  R.o_xr = r; R.o_xrp = rp; R.o_xrm1 = rm1; R.o_xrm2 = rm2;
+  R.o_u0 = poff + rp * ld + rm1; R.o_u1 = poff + rm1 * ld + rp; R.o_u2 = poff + rm2 * ld + rm1; R.o_u3 = poff + rm1 * ld + rm2;
 #pragma unroll
-  for (int w = 0; w < (STENCIL_SEG + 3 + 3) / 4; ++w) R.wcp[w] = 0u;
-#pragma unroll
-  for (int q = 0; q < STENCIL_SEG + 3; ++q) {
-    int col = R.c0 - 2 + q;
-    col = col < 0 ? col + n : col;
-    col = col >= n ? col - n : col;
-    col = col >= n ? col - n : col;  // (a short last segment can overshoot by more than one lap only for n < 4: excluded)
-    R.wcp[q >> 2] |= (unsigned)col << ((q & 3) * 8);
-  }
-#pragma unroll
-  for (int w = 0; w < (STENCIL_SEG + 3 + 3) / 4; ++w) asm volatile("" : "+r"(R.wcp[w]));  // opaque: never rematerialised
-#pragma unroll
-  for (int j = 0; j < STENCIL_SEG; ++j) R.lql[j] = j < R.cnt ? lql[R.r * ld + R.c0 + j] : T(0);
+  for (int j = 0; j < SEG; ++j) R.lql[j] = lql[r * ld + c0 + j];
 }
 
 // Integrate (m, P) (shared memory, [MU | P] layout of `y`) from t0 to t1.  UKFC adds the unscented second-order mean term.
@@ -406,20 +413,18 @@ template <typename T, bool UKFC>
 __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y, T t0, T t1, T dt0, int max_steps) {
   constexpr int SEG = STENCIL_SEG;
   const Lay& L = c.L;
-  const int ld = L.ldn, poff = L.P - L.MU;
   const RtTab& tab = c.g.tab;
   const T F = c.p(L.TH)[0];
-  const bool act = R.cnt > 0, own_m = act && R.c0 == 0;
-  const int rowoff = poff + R.r * ld + R.c0;
+  const bool act = R.act, own_m = R.own_m;
   T yP[SEG], aP[SEG], kP[SEG];
   T ym = T(0), am = T(0), km = T(0);
 #pragma unroll
   for (int j = 0; j < SEG; ++j) {
-    yP[j] = j < R.cnt ? y[rowoff + j] : T(0);
+    yP[j] = y[R.o_row + j];
     kP[j] = T(0);
     aP[j] = T(0);
   }
-  if (own_m) ym = y[R.r];
+  if (own_m) ym = y[R.o_xr];
   const T tol = clip_tol<T>();
   T tprev = t0, tnext = fmin(t0 + dt0, t1);
   int nsteps = 0;
@@ -436,11 +441,17 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
     for (int st = 0; st < tab.S; ++st) {
       const T a = tab.nnz[st] ? T(tab.val[st][0]) : T(0);  // chain tableau: only the previous stage
       T* B = c.sh + ((st & 1) ? L.KS : L.YS);  // an integer select keeps the pointer in the shared window (LDS / STS)
-      // stage input y + a k_{st-1} -> shared memory
+      // stage input y + a k_{st-1}: kept in registers (it is this thread's part of the row window) and published
+      T sP[SEG], sm;
 #pragma unroll
-      for (int j = 0; j < SEG; ++j)
-        if (j < R.cnt) B[rowoff + j] = st == 0 ? yP[j] : yP[j] + a * kP[j];
-      if (own_m) B[R.r] = st == 0 ? ym : ym + a * km;
+      for (int j = 0; j < SEG; ++j) sP[j] = st == 0 ? yP[j] : yP[j] + a * kP[j];
+      sm = st == 0 ? ym : ym + a * km;
+      if (act) {
+        T* row = B + R.o_row;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) row[j] = sP[j];
+        if (own_m) B[R.o_xr] = sm;
+      }
       if (st == 0) {
 #pragma unroll
         for (int j = 0; j < SEG; ++j) aP[j] = yP[j];
@@ -448,34 +459,33 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
       }
       __syncthreads();
       if (act) {
-        const T* x = B;
-        const T* P = B + poff;
         const T b = T(tab.b[st]);
+        // windows: index q <-> column c0 - 2 + q
         T xw[SEG + 3], pr[SEG + 3];
-#pragma unroll
-        for (int q = 0; q < SEG + 3; ++q) {
-          const int col = R.wc(q);
-          xw[q] = x[col];
-          pr[q] = P[R.r * ld + col];
-        }
-        const T ar = x[R.rm1], br = x[R.rp] - x[R.rm2];
-        const T* Pu = P + R.rp * ld + R.c0;
-        const T* Pd1 = P + R.rm1 * ld + R.c0;
-        const T* Pd2 = P + R.rm2 * ld + R.c0;
+        xw[0] = B[R.o_xl0]; xw[1] = B[R.o_xl1]; xw[SEG + 2] = B[R.o_xh];
+        pr[0] = B[R.o_pl0]; pr[1] = B[R.o_pl1]; pr[SEG + 2] = B[R.o_ph];
+        const T* xs = B + R.o_x;
 #pragma unroll
         for (int j = 0; j < SEG; ++j) {
-          if (j < R.cnt) {
-            const int q = j + 2;
-            const T jp_rc = ar * (Pu[j] - Pd2[j]) + br * Pd1[j] - pr[q];
-            const T jp_cr = xw[q - 1] * (pr[q + 1] - pr[q - 2]) + (xw[q + 1] - xw[q - 2]) * pr[q - 1] - pr[q];
-            kP[j] = dt * ((jp_rc + jp_cr) + R.lql[j]);
-            aP[j] += b * kP[j];
-          }
+          xw[j + 2] = xs[j];
+          pr[j + 2] = sP[j];
+        }
+        const T ar = B[R.o_xrm1], br = B[R.o_xrp] - B[R.o_xrm2];
+        const T* Pu = B + R.o_up;
+        const T* Pd1 = B + R.o_d1;
+        const T* Pd2 = B + R.o_d2;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+          const int q = j + 2;
+          const T jp_rc = ar * (Pu[j] - Pd2[j]) + br * Pd1[j] - pr[q];
+          const T jp_cr = xw[q - 1] * (pr[q + 1] - pr[q - 2]) + (xw[q + 1] - xw[q - 2]) * pr[q - 1] - pr[q];
+          kP[j] = dt * ((jp_rc + jp_cr) + R.lql[j]);
+          aP[j] += b * kP[j];
         }
         if (own_m) {
-          T f = br * ar - x[R.r] + F;
+          T f = br * ar - sm + F;
           if (UKFC)  // 0.5 tr(Hess f_r P) = sym(P)_{r+1,r-1} - sym(P)_{r-2,r-1}
-            f += T(0.5) * (P[R.rp * ld + R.rm1] + P[R.rm1 * ld + R.rp]) - T(0.5) * (P[R.rm2 * ld + R.rm1] + P[R.rm1 * ld + R.rm2]);
+            f += T(0.5) * (B[R.o_u0] + B[R.o_u1]) - T(0.5) * (B[R.o_u2] + B[R.o_u3]);
           km = dt * f;
           am += b * km;
         }
@@ -490,10 +500,11 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
     tnext = cand > t1 - tol ? t1 : cand;
   }
   __syncthreads();  // the last stage's readers are done before the state block is rewritten
+  if (act) {
 #pragma unroll
-  for (int j = 0; j < SEG; ++j)
-    if (j < R.cnt) y[rowoff + j] = yP[j];
-  if (own_m) y[R.r] = ym;
+    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = yP[j];
+    if (own_m) y[R.o_xr] = ym;
+  }
   __syncthreads();
   return hit;
 }
