@@ -416,46 +416,46 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
   const RtTab& tab = c.g.tab;
   const T F = c.p(L.TH)[0];
   const bool act = R.act, own_m = R.own_m;
-  T yP[SEG], aP[SEG], kP[SEG];
-  T ym = T(0), am = T(0), km = T(0);
+  // aP is the running combination y + sum_s b_s k_s: it equals y at the start of every step, so y itself needs no copy
+  T aP[SEG], kP[SEG], yP[SEG];
+  T am = T(0), km = T(0), ym = T(0);
 #pragma unroll
   for (int j = 0; j < SEG; ++j) {
-    yP[j] = y[R.o_row + j];
+    aP[j] = y[R.o_row + j];
     kP[j] = T(0);
-    aP[j] = T(0);
   }
-  if (own_m) ym = y[R.o_xr];
+  if (own_m) am = y[R.o_xr];
   const T tol = clip_tol<T>();
   T tprev = t0, tnext = fmin(t0 + dt0, t1);
   int nsteps = 0;
   bool hit = false;
+  const int boff0 = L.YS, boff1 = L.KS;
   while (tprev < t1) {
     if (nsteps >= max_steps) {
       hit = true;
 #pragma unroll
-      for (int j = 0; j < SEG; ++j) yP[j] = T(NAN);
-      ym = T(NAN);
+      for (int j = 0; j < SEG; ++j) aP[j] = T(NAN);
+      am = T(NAN);
       break;
     }
     const T dt = tnext - tprev;
-    for (int st = 0; st < tab.S; ++st) {
-      const T a = tab.nnz[st] ? T(tab.val[st][0]) : T(0);  // chain tableau: only the previous stage
-      T* B = c.sh + ((st & 1) ? L.KS : L.YS);  // an integer select keeps the pointer in the shared window (LDS / STS)
-      // stage input y + a k_{st-1}: kept in registers (it is this thread's part of the row window) and published
-      T sP[SEG], sm;
 #pragma unroll
-      for (int j = 0; j < SEG; ++j) sP[j] = st == 0 ? yP[j] : yP[j] + a * kP[j];
-      sm = st == 0 ? ym : ym + a * km;
+    for (int j = 0; j < SEG; ++j) yP[j] = aP[j];
+    ym = am;
+    for (int st = 0; st < tab.S; ++st) {
+      // chain tableau: only the previous stage; a = 0 at stage 0, where k still holds the previous step's (finite) value
+      const T a = (st > 0 && tab.nnz[st]) ? T(tab.val[st][0]) : T(0);
+      T* B = c.sh + ((st & 1) ? boff1 : boff0);  // an integer select keeps the pointer in the shared window (LDS / STS)
+      // stage input y + a k_{st-1}: kept in registers (it is this thread's part of the row window) and published
+      T sP[SEG];
+#pragma unroll
+      for (int j = 0; j < SEG; ++j) sP[j] = fma(a, kP[j], yP[j]);
+      const T sm = fma(a, km, ym);
       if (act) {
         T* row = B + R.o_row;
 #pragma unroll
         for (int j = 0; j < SEG; ++j) row[j] = sP[j];
         if (own_m) B[R.o_xr] = sm;
-      }
-      if (st == 0) {
-#pragma unroll
-        for (int j = 0; j < SEG; ++j) aP[j] = yP[j];
-        am = ym;
       }
       __syncthreads();
       if (act) {
@@ -477,23 +477,24 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
 #pragma unroll
         for (int j = 0; j < SEG; ++j) {
           const int q = j + 2;
-          const T jp_rc = ar * (Pu[j] - Pd2[j]) + br * Pd1[j] - pr[q];
-          const T jp_cr = xw[q - 1] * (pr[q + 1] - pr[q - 2]) + (xw[q + 1] - xw[q - 2]) * pr[q - 1] - pr[q];
-          kP[j] = dt * ((jp_rc + jp_cr) + R.lql[j]);
-          aP[j] += b * kP[j];
+          // (J P)_rc + (J P)_cr + LQL_rc as one fma chain: 3 differences, 5 fma
+          T v = fma(T(-2), pr[q], R.lql[j]);
+          v = fma(ar, Pu[j] - Pd2[j], v);
+          v = fma(br, Pd1[j], v);
+          v = fma(xw[q - 1], pr[q + 1] - pr[q - 2], v);
+          v = fma(xw[q + 1] - xw[q - 2], pr[q - 1], v);
+          kP[j] = dt * v;
+          aP[j] = fma(b, kP[j], aP[j]);
         }
         if (own_m) {
-          T f = br * ar - sm + F;
+          T f = fma(br, ar, F - sm);
           if (UKFC)  // 0.5 tr(Hess f_r P) = sym(P)_{r+1,r-1} - sym(P)_{r-2,r-1}
-            f += T(0.5) * (B[R.o_u0] + B[R.o_u1]) - T(0.5) * (B[R.o_u2] + B[R.o_u3]);
+            f += T(0.5) * ((B[R.o_u0] + B[R.o_u1]) - (B[R.o_u2] + B[R.o_u3]));
           km = dt * f;
-          am += b * km;
+          am = fma(b, km, am);
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < SEG; ++j) yP[j] = aP[j];
-    ym = am;
     ++nsteps;
     tprev = tnext;
     const T cand = tprev + dt0;
@@ -502,8 +503,8 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
   __syncthreads();  // the last stage's readers are done before the state block is rewritten
   if (act) {
 #pragma unroll
-    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = yP[j];
-    if (own_m) y[R.o_xr] = ym;
+    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = aP[j];
+    if (own_m) y[R.o_xr] = am;
   }
   __syncthreads();
   return hit;
