@@ -6,6 +6,7 @@
 #include <atomic>
 
 #include "cdk_common.cuh"
+#include "cdk_rng.cuh"
 
 namespace cdk {
 
@@ -246,6 +247,17 @@ static int fma_probe(int blocks, int iters, T* sink, cdk_stream_t stream) {
   return check_launch("fma_probe_kernel");
 }
 
+// ---- normal-deviate probe (tests: bit equality with the oracle's stream) ------------------------------------------
+__global__ void __launch_bounds__(256) rng_probe_kernel(long long count, uint32_t traj, uint32_t step, uint32_t c3_base,
+                                                        uint64_t seed, double* out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= count) return;
+  double z[4];
+  normal_quad((uint32_t)i, traj, step, c3_base + ((uint32_t)i & 0xffu), seed, z);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) out[4 * i + u] = z[u];
+}
+
 // ---- FP64 tensor-core (DMMA m8n8k4) probe -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dmma_probe_kernel(int iters, double* sink) {
   double c[8][2];
@@ -420,6 +432,15 @@ int cdk_fma3_probe_f64(int blocks, int iters, double* sink, const double* seed, 
   fma3_probe_kernel<<<blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(iters, sink, seed);
   note_launch();
   return check_launch("fma3_probe_kernel");
+}
+
+int cdk_rng_probe_f64(int64_t count, uint32_t traj, uint32_t step, uint32_t c3_base, uint64_t seed, double* out,
+                      cdk_stream_t stream) {
+  if (!out || count < 1) return fail(CDK_E_NULL, "rng_probe: bad arguments");
+  rng_probe_kernel<<<(unsigned)((count + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(count, traj, step, c3_base,
+                                                                                                   seed, out);
+  note_launch();
+  return check_launch("rng_probe_kernel");
 }
 
 int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream) {

@@ -430,8 +430,15 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
           if (i < n) x[i] = X[(size_t)i * ldE + el];
         if (diagG) {
 #pragma unroll UFP
-          for (int j = 0; j < NXA; j += 4) {
-            if (j < n) {
+          for (int j = 0; j < NXA; j += 8) {
+            if (j + 4 < n) {  // two quads at once (normal_oct: same values, interleaved chains)
+              double z8[8];
+              normal_oct((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 2),
+                         rng_c3(RNG_DYN, nsteps, (j >> 2) + 1), seed, z8);
+#pragma unroll
+              for (int u = 0; u < 8; ++u)
+                if (j + u < NXA && j + u < n) xe[j + u] = G[(j + u) * ldn + j + u] * (sqdt * (T)z8[u]);
+            } else if (j < n) {
               double z4[4];
               normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, j >> 2), seed, z4);
 #pragma unroll

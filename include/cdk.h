@@ -252,6 +252,12 @@ int cdk_fma3_probe_f64(int blocks, int iters, double* sink, const double* seed, 
  * accumulator tiles per warp; flops = 2 * 8*8*4 * 8 * iters * blocks * 8 warps. */
 int cdk_dmma_probe_f64(int blocks, int iters, double* sink, cdk_stream_t stream);
 
+/* The library's normal deviates (the counter-based stream of the EnKF and the path sampler, csrc/cdk_rng.cuh): writes the
+ * four deviates of counter (member = i, traj, step, c3 = c3_base + (i & 0xff)) for i < count to out[4 i .. 4 i + 3].
+ * Test hook: the CPU oracle reproduces the stream bit for bit (oracle/cd_oracle.py:philox_normal_quad). */
+int cdk_rng_probe_f64(int64_t count, uint32_t traj, uint32_t step, uint32_t c3_base, uint64_t seed, double* out,
+                      cdk_stream_t stream);
+
 /* Diagnostics: register (or clear, with NULL) a device buffer of 4 x uint64 per warp of 32 trajectories; the Lorenz-63
  * EKF kernel then records {globaltimer at entry, at exit, %smid, %warpid} per warp (scripts/trace_lw.py). */
 int cdk_debug_set_trace(void* devbuf);

@@ -727,15 +727,59 @@ def philox4x32(c0, c1, c2, c3, k0, k1):
     return c0, c1, c2, c3
 
 
+def box_muller_f32(ra, rb):
+    """One Box-Muller pair from two uint32 arrays in float32 arithmetic made of correctly rounded add / mul / div / sqrt only
+    (no FMA, no libm), operation for operation csrc/cdk_rng.cuh:box_muller_f32 -- so the GPU deviates are reproduced bit for
+    bit.  Returns two float32 arrays."""
+    f32 = np.float32
+    ra, rb = np.asarray(ra, np.uint32), np.asarray(rb, np.uint32)
+    uf = ra.astype(f32) + f32(0.5)
+    bits = uf.view(np.uint32)
+    e = (bits >> np.uint32(23)).astype(np.int32) - np.int32(127)
+    m = ((bits & np.uint32(0x007FFFFF)) | np.uint32(0x3F800000)).view(f32)
+    big = m > f32(1.41421354)
+    m = np.where(big, m * f32(0.5), m)
+    e = np.where(big, e + np.int32(1), e)
+    s = (m + f32(-1.0)) / (m + f32(1.0))
+    s2 = s * s
+    p = np.full(s2.shape, f32(0.111111112), f32)
+    for c in (0.142857149, 0.2, 0.333333343, 1.0):
+        p = p * s2 + f32(c)
+    lnm = (f32(2.0) * s) * p
+    lnu = lnm + (e - np.int32(32)).astype(f32) * f32(0.693147182)
+    radh = np.sqrt(f32(-2.0) * lnu) * f32(0.707106769)
+    q = rb >> np.uint32(30)
+    g = (((rb >> np.uint32(7)) & np.uint32(0x7FFFFF)).astype(f32) + f32(0.5)) * f32(1.1920929e-07) + f32(-0.5)
+    y = g * f32(1.57079637)
+    y2 = y * y
+    ps = np.full(y2.shape, f32(2.75573188e-06), f32)
+    for c in (-1.98412701e-04, 8.33333377e-03, -0.166666672, 1.0):
+        ps = ps * y2 + f32(c)
+    sy = y * ps
+    pc = np.full(y2.shape, f32(2.48015876e-05), f32)
+    for c in (-1.38888892e-03, 4.16666679e-02, -0.5):
+        pc = pc * y2 + f32(c)
+    cy = pc * y2 + f32(1.0)
+    c45, s45 = cy + (-sy), cy + sy
+    odd = (q & np.uint32(1)) != 0
+    cq = np.where(odd, -s45, c45)
+    sq = np.where(odd, c45, s45)
+    neg = (q & np.uint32(2)) != 0
+    cq = np.where(neg, -cq, cq)
+    sq = np.where(neg, -sq, sq)
+    z0, z1 = radh * cq, radh * sq
+    assert z0.dtype == f32 and z1.dtype == f32 and p.dtype == f32 and lnu.dtype == f32 and y.dtype == f32
+    return z0, z1
+
+
 def philox_normal_quad(c0, c1, c2, c3, seed):
-    """Four standard normals per counter: four 32-bit uniforms (r + 0.5) 2^-32, two Box-Muller pairs in fp64
+    """Four standard normals per counter: two float32 Box-Muller pairs from words (r0, r1) and (r2, r3), widened to fp64
     (csrc/cdk_rng.cuh:normal_quad)."""
     k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
     r = philox4x32(c0, c1, c2, c3, k0, k1)
-    u = [(ri.astype(np.float64) + 0.5) * (1.0 / 4294967296.0) for ri in r]
-    rad0, rad1 = np.sqrt(-2.0 * np.log(u[0])), np.sqrt(-2.0 * np.log(u[2]))
-    a0, a1 = 2.0 * math.pi * u[1], 2.0 * math.pi * u[3]
-    return rad0 * np.cos(a0), rad0 * np.sin(a0), rad1 * np.cos(a1), rad1 * np.sin(a1)
+    z0, z1 = box_muller_f32(r[0], r[1])
+    z2, z3 = box_muller_f32(r[2], r[3])
+    return tuple(z.astype(np.float64) for z in (z0, z1, z2, z3))
 
 
 # stream ids (counter word c3 high byte)

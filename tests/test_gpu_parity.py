@@ -345,6 +345,24 @@ def test_enkf_vs_oracle(kind, N, K, E, solver, cluster, monkeypatch):
         assert scaled_err(getattr(f, fld), r[fld]) < 1e-8, fld
 
 
+def test_normal_deviates_bit_identical_to_oracle():
+    """The library's deviate stream (Philox4x32-10 + fp32 Box-Muller out of correctly rounded operations only) against the
+    oracle's restatement: every bit of 4 x 200,000 deviates."""
+    import ctypes
+    import torch
+    from cd_dynamax_b200 import _lib as L
+    lib = L.lib()
+    count, traj, step, c3b, seed = 200_000, 77, 5, (2 << 28) | (3 << 8), 0x1234567887654321
+    out = torch.empty(4 * count, dtype=torch.float64, device="cuda")
+    L.check(lib.cdk_rng_probe_f64(count, traj, step, c3b, seed, ctypes.c_void_p(out.data_ptr()), None), "rng_probe")
+    torch.cuda.synchronize()
+    z = out.cpu().numpy().reshape(count, 4)
+    i = np.arange(count, dtype=np.uint32)
+    ref = np.stack(o.philox_normal_quad(i, np.uint32(traj), np.uint32(step), np.uint32(c3b) + (i & np.uint32(0xFF)), seed), axis=1)
+    assert np.array_equal(z.view(np.uint64), ref.view(np.uint64))
+    assert abs(z.mean()) < 5e-3 and abs(z.var() - 1.0) < 5e-3 and np.abs(z).max() < 6.77
+
+
 def test_enkf_matches_kalman_filter_in_distribution():
     """The reference's own EnKF check (cdnlgssm_test_filter_linear_TRegular.py:434-470): on a linear model the EnKF
     moments approach the CD-KF's as E grows.  E = 4096 members: Monte-Carlo error ~ 1/sqrt(E)."""
