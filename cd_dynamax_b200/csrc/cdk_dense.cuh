@@ -439,4 +439,47 @@ __device__ __forceinline__ void mm_dmma_w(int warp, int nwarp, const T* __restri
   }
 }
 
+// C(i, j) = sum_k opA(i, k) * B[k * ldb + j] for a WIDE result (N >> M: a small matrix applied to every member of an
+// ensemble): each warp takes strips of 8 columns and keeps the accumulators of ALL row tiles (M <= 64) in registers, so a
+// B fragment is loaded once per k-step and reused by every row tile, and the per-tile bookkeeping of mm_dmma (index
+// arithmetic, bounds, accumulator setup: ~130 instructions around the 5-10 DMMAs of a short k loop) is paid once per strip.
+template <typename T, bool TRANSA, class Epi>
+__device__ __forceinline__ void mm_dmma_strip(const T* __restrict__ A, int lda, const T* __restrict__ B, int ldb, int M, int N,
+                                              int Kd, Epi epi) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int gid = lane >> 2, tig = lane & 3;
+  const int tm = (M + 7) >> 3, ts = (N + 7) >> 3;
+  for (int sidx = warp; sidx < ts; sidx += nwarp) {
+    const int jb = (sidx << 3) + gid;
+    const bool vb = jb < N;
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int k0 = 0; k0 < Kd; k0 += 4) {
+      const int k = k0 + tig;
+      const bool vk = k < Kd;
+      const double bv = (vb && vk) ? (double)B[(size_t)k * ldb + jb] : 0.0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        if (t < tm) {
+          const int ia = (t << 3) + gid;
+          const double av = (ia < M && vk) ? (double)(TRANSA ? A[k * lda + ia] : A[ia * lda + k]) : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[t][0]), "+d"(acc[t][1])
+                       : "d"(av), "d"(bv));
+        }
+      }
+    }
+    const int j = (sidx << 3) + 2 * tig;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int i = (t << 3) + gid;
+      if (t < tm && i < M) {
+        if (j < N) epi(i, j, acc[t][0]);
+        if (j + 1 < N) epi(i, j + 1, acc[t][1]);
+      }
+    }
+  }
+}
+
 }  // namespace cdk

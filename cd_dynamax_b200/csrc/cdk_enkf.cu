@@ -39,8 +39,9 @@ constexpr int ENKF_TPB = 256;
 struct ELay {
   int n, m, ldn, ldm, ldE, nth;
   // byte offsets
-  size_t X, PSUM, CPART, CXX, MEAN, H, R, CHR, DV, G, HP, S, SL, KT, SK, YV, RV, TH, MISC, total;
-  __host__ __device__ ELay(int n_, int m_, int nth_, int Eloc, size_t ts) {
+  size_t X, PSUM, CPART, CXX, MEAN, H, R, CHR, DV, G, HP, S, SL, KT, SK, YV, RV, TH, MISC, DB, total;
+  // dg: room for the [m x ldE] innovation block of the tensor-core gain application (EArgs::dg)
+  __host__ __device__ ELay(int n_, int m_, int nth_, int Eloc, size_t ts, int dg) {
     n = n_; m = m_; nth = nth_;
     ldn = ldp(n); ldm = ldp(m);
     ldE = ((Eloc + 31) / 32) * 32 + 4;  // = 4 (mod 32): DMMA fragment loads X[i0 + gid][e0 + tig] are conflict-free
@@ -65,6 +66,7 @@ struct ELay {
     RV = take(ts * 2 * m);
     TH = take(ts * (nth > 0 ? nth : 1));
     MISC = take(64);
+    DB = take(dg ? ts * m * ldE : 0);
     total = o;
   }
 };
@@ -73,6 +75,7 @@ template <typename T>
 struct EArgs {
   KArgs<T> k;
   int C;     // cluster size (CTAs per trajectory)
+  int dg;    // 1: gain application X += K (Y~ - H X - d) as two tensor-core products over the CTA's members (needs ELay::DB)
   int Eloc;  // members per CTA (the last CTA may own fewer)
 };
 
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
   const int n = NX > 0 ? NX : d.n, m = d.m, K = d.K, E = d.E, C = g.C;
   const int rank = (int)cluster.block_rank();
   const long long traj = blockIdx.x / C;
-  const ELay L(n, m, d.n_theta, g.Eloc, sizeof(T));
+  const ELay L(n, m, d.n_theta, g.Eloc, sizeof(T), g.dg);
   const int ldn = L.ldn, ldm = L.ldm, ldE = L.ldE;
   const int e_base = rank * g.Eloc;
   const int nmem = max(0, min(g.Eloc, E - e_base));
@@ -274,6 +277,12 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
     if (i != j && G[i * ldn + j] != T(0)) offdiag = 1;
   }
   const bool diagG = __syncthreads_or(offdiag) == 0;
+  offdiag = 0;
+  FOR_T(e, m * m) {
+    const int i = e / m, j = e - i * m;
+    if (i != j && chR[i * ldm + j] != T(0)) offdiag = 1;
+  }
+  const bool diagR = __syncthreads_or(offdiag) == 0;  // diagonal chol(R): the measurement noise is chR_pp z_p
 
   // ---- initial ensemble: m0 + chol(P0) z (inference_enkf.py:260-262) ----
   {
@@ -363,6 +372,38 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
     chol_solve<T>(Sl, m, ldm, HP, Kt, n, ldn);     // ends with a barrier
     ll += *llsh;
     // per member: x += K ((y + chol(R) z) - (H x + d))   (:135-146)
+    if (g.dg) {
+      // Over the CTA's members at once: D = (y - d) 1^T + chol(R) Z - H X  [m x nmem],  X += K D, the two products on the FP64
+      // tensor cores (per member this is 2 m n FMAs with one shared-memory operand load each: 11 % of the instruction stream).
+      T* Db = reinterpret_cast<T*>(sh + L.DB);
+      for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
+        if (d.perturb_measurements) {
+          T r[CDK_MAX_M];
+          for (int p = 0; p < m; p += 4) {
+            double z4[4];
+            normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_OBS, 0, p >> 2), seed, z4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (p + u < m) r[p + u] = (T)z4[u];
+          }
+          if (diagR) {
+            for (int p = 0; p < m; ++p) Db[(size_t)p * ldE + el] = (yv[p] + chR[p * ldm + p] * r[p]) - dv[p];
+          } else {
+            for (int p = m - 1; p >= 0; --p) {  // chol(R) z from the bottom row up
+              T s = T(0);
+              for (int q = 0; q <= p; ++q) s += chR[p * ldm + q] * r[q];
+              Db[(size_t)p * ldE + el] = (yv[p] + s) - dv[p];
+            }
+          }
+        } else {
+          for (int p = 0; p < m; ++p) Db[(size_t)p * ldE + el] = yv[p] - dv[p];
+        }
+      }
+      __syncthreads();
+      mm_dmma_strip<T, false>(H, ldn, X, ldE, m, nmem, n, [&](int p, int e, double v) { Db[(size_t)p * ldE + e] -= (T)v; });
+      __syncthreads();
+      mm_dmma_strip<T, true>(Kt, ldn, Db, ldE, n, nmem, m, [&](int i, int e, double v) { X[(size_t)i * ldE + e] += (T)v; });
+    } else
     for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
       T x[NXA];
 #pragma unroll UF
@@ -528,20 +569,29 @@ int launch_enkf(const KArgs<T>& a, cudaStream_t s) {
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   int forced = 0;
   if (const char* e = getenv("CDK_ENKF_CLUSTER")) forced = atoi(e);
+  static const int dmma_gain_env = []() {
+    const char* e = getenv("CDK_ENKF_DMMA_GAIN");
+    return e && e[0] == '0' ? 0 : 1;
+  }();
   EArgs<T> g;
   g.k = a;
   g.C = 0;
+  g.dg = 0;
   size_t smem = 0;
   for (int C = 1; C <= 8; C *= 2) {
     if (forced && C != forced) continue;
     const int Eloc = (((d.E + C - 1) / C) + 3) & ~3;
-    const ELay L(d.n, d.m, d.n_theta, Eloc, sizeof(T));
-    if (L.total <= (size_t)max_optin && (forced || Eloc <= 2 * ENKF_TPB || C == 8)) {
-      g.C = C;
-      g.Eloc = Eloc;
-      smem = L.total;
-      break;
+    if (!(forced || Eloc <= 2 * ENKF_TPB || C == 8)) continue;
+    for (int dg = dmma_gain_env; dg >= 0 && g.C == 0; --dg) {  // prefer the tensor-core gain application if its block fits
+      const ELay L(d.n, d.m, d.n_theta, Eloc, sizeof(T), dg);
+      if (L.total <= (size_t)max_optin) {
+        g.C = C;
+        g.Eloc = Eloc;
+        g.dg = dg;
+        smem = L.total;
+      }
     }
+    if (g.C) break;
   }
   if (g.C == 0) return CDK_E_SIZE;  // ensemble too large for 8 CTAs x 227 KB
   if (d.n == 40 && d.drift_id == CDK_DRIFT_LORENZ96) return launch_nx<T, 40>(g, smem, s);
