@@ -163,7 +163,12 @@ static int run(int algo, const cdk_desc* d, const void* const* in, void* const* 
     rc = launch_kf_warp<T>(algo, a, s);
     if (rc != CDK_E_UNSUPPORTED) return rc;
   }
-  if (algo == ALGO_ENKF_FILTER) return launch_enkf<T>(a, s);
+  if (algo == ALGO_ENKF_FILTER) {
+    rc = launch_enkf<T>(a, s);
+    return rc == CDK_E_SIZE ? fail(rc, "enkf: the ensemble and its model do not fit the shared memory of an 8-CTA cluster "
+                                       "(8 x 227 KB; roughly n * E * sizeof(T) / 8 + 12 n^2 sizeof(T) per CTA)")
+                            : rc;
+  }
   if (algo == ALGO_SAMPLE) {
     rc = launch_sample_path<T>(a, s);
     return rc == CDK_E_UNSUPPORTED ? fail(rc, "cdk_sample_path: model parameters must not be batched; solver euler or heun") : rc;
@@ -172,7 +177,16 @@ static int run(int algo, const cdk_desc* d, const void* const* in, void* const* 
     rc = launch_emission_moments<T>(a, s);
     return rc == CDK_E_UNSUPPORTED ? fail(rc, "cdk_emission_moments: H, d, R must not be batched") : rc;
   }
-  return launch_generic<T>(algo, a, s);
+  rc = launch_generic<T>(algo, a, s);
+  if (rc == CDK_E_SIZE) {
+    static thread_local char msg[256];
+    snprintf(msg, sizeof(msg),
+             "n = %d, m = %d: the per-trajectory working set of the shared-memory kernels exceeds the 227 KB of one CTA "
+             "(fp64, m = n: KF n <= 38 / 30, EKF 45 / 37, UKF 50-55 with a chain tableau (euler, heun, rk4) / dopri5; see cdk.h)",
+             d->n, d->m);
+    return fail(rc, msg);
+  }
+  return rc;
 }
 
 // ---- deterministic ll reduction ------------------------------------------------------------------------------------

@@ -159,6 +159,10 @@ typedef struct cdk_desc {
  * (the point-estimate branch of cdnlgssm_forecast, cd_nonlinear/models.py:840-936). */
 #define CDK_FLAG_FIXED_INIT 16
 
+/* Upper bounds of the ABI.  The real limit of the shared-memory kernels (any n > 3 EKF / UKF, KF with n > 16 or m > 8,
+ * smoothers) is the 227 KB of one CTA, which holds the whole per-trajectory working set: in fp64 with m = n, KF n <= 38
+ * (30 with dopri5, whose seven stages are all kept), EKF n <= 45 (37), UKF n <= 50-55; more with m << n (KF n <= 43 at
+ * m = 4), about 1.4x in fp32.  Larger requests return CDK_E_SIZE with a message, never a wrong answer. */
 #define CDK_MAX_N 64
 #define CDK_MAX_M 64
 

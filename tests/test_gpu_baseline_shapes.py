@@ -163,6 +163,66 @@ def test_c2_kf_n16_k500_vs_oracle(solver, dt0):
             assert scaled_err(getattr(s, fld), rs[fld]) < 1e-8, (stype, fld)
 
 
+@pytest.mark.parametrize("n,m", [(36, 36), (32, 40), (12, 33)])
+def test_kf_maximum_sizes_vs_oracle(n, m):
+    """The largest KF the 227 KB of a CTA hold (n = m = 36; cdk.h) and emission dimensions above 32 (two rows per lane in the single-warp Cholesky, the
+    chunked triangular solves and the warp log-density; m > n exercises the scratch sizing) -- generic kernel, filter and
+    type-1 smoother against the NumPy oracle."""
+    cd = api()
+    N, K = 3, 12
+    rng = np.random.default_rng(n * 100 + m)
+    g, _, t, _ = _c2_case(N, K, seed=n + m, n=n, m=min(m, n))
+    H = rng.standard_normal((m, n)) / np.sqrt(n)
+    A = rng.standard_normal((m, m)) / np.sqrt(m)
+    g.update(H=H, d=0.1 * rng.standard_normal(m), R=0.2 * np.eye(m) + 0.1 * A @ A.T)
+    y = rng.standard_normal((N, K, m))
+    po = o.LinearParams(m0=g["m0"], P0=g["P0"], F=g["F"], L=g["L"], Qc=g["Qc"], H=g["H"], R=g["R"], b=g["b"], d=g["d"])
+    hp = cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
+    f = cd.cdlgssm_filter(linear_params_api(g), y, t[..., None], hp)
+    r = o.cdlgssm_filter(po, y, t, settings=o.SolverSettings("rk4", 0.01))
+    e = max_rel_err(f.marginal_loglik, r["marginal_loglik"])
+    record(f"kf_max_n{n}_m{m}:marginal_loglik", e)
+    assert e < TOL
+    check_moments(f, r, f"kf_max_n{n}_m{m}")
+    s = cd.cdlgssm_smoother(linear_params_api(g), y, t[..., None], hp, smoother_type="cd_smoother_1")
+    rs = o.cdlgssm_smoother(po, y, t, settings=o.SolverSettings("rk4", 0.01), smoother_type=1)
+    for fld in ("smoothed_means", "smoothed_covariances"):
+        assert scaled_err(getattr(s, fld), rs[fld]) < 1e-8, fld
+
+
+def test_oversized_request_fails_loudly():
+    """n = m = 64 is inside the ABI bounds but its working set exceeds one CTA's shared memory: CDK_E_SIZE with a message."""
+    from cd_dynamax_b200._lib import CdkError
+    cd = api()
+    g, _, t, y = _c2_case(2, 4, n=64, m=64)
+    with pytest.raises(CdkError, match="227 KB"):
+        cd.cdlgssm_filter(linear_params_api(g), y, t[..., None], cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01}))
+
+
+def test_ukf_and_enkf_wide_emission_vs_oracle():
+    """m = 36 > 32 on the nonlinear kernels: closed-form UKF (Lorenz-96 n = 40) and EnKF (cluster path, tensor-core gain)."""
+    cd = api()
+    n, m, N, K = 40, 36, 2, 8
+    g, po, t, y = _l96_case(N, K, seed=21, n=n, m=20)
+    rng = np.random.default_rng(7)
+    H = rng.standard_normal((m, n)) / np.sqrt(n)
+    g.update(H=H, d=np.zeros(m), R=0.5 * np.eye(m))
+    po = o.NonlinearParams(m0=g["m0"], P0=g["P0"], drift=o.Lorenz96Drift(g["theta"][0]), L=g["L"], Qc=g["Qc"], H=H, R=g["R"], d=g["d"])
+    y = (H @ g["m0"])[None, None, :] + rng.standard_normal((N, K, m))
+    p = nonlinear_params_api(g)
+    f = cd.cdnlgssm_filter(p, y, t[..., None], cd.UKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.005}))
+    r = o.unscented_kalman_filter(po, y, t, settings=o.SolverSettings("rk4", 0.005))
+    assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < TOL
+    check_moments(f, r, "ukf_wide_m36")
+    E = 128
+    hp = cd.EnKFHyperParams(N_particles=E, key=99, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
+    fe = cd.cdnlgssm_filter(p, y, t[..., None], hp)
+    re = o.ensemble_kalman_filter(po, y, t, E=E, seed=99, settings=o.SolverSettings("euler", 0.005))
+    assert max_rel_err(fe.marginal_loglik, re["marginal_loglik"]) < 1e-8
+    for fld in ("filtered_means", "filtered_covariances", "predicted_means", "predicted_covariances"):
+        assert scaled_err(getattr(fe, fld), re[fld]) < 1e-8, fld
+
+
 # ---- fp32 entry points: one stated bound each (oracle in fp64 on the fp32-rounded inputs, so the comparison isolates the
 # ---- arithmetic precision).  The reference's own fp32 "match" ladder is 1e-5 .. 1e-4 on well-conditioned linear models
 # ---- (test_utils.py:160-180); chaotic drifts amplify rounding by e^{lambda t}.
