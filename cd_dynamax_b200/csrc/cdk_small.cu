@@ -1668,7 +1668,19 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   // full wave (148 SMs x 14 warps x 32 = 66,304 trajectories) is that its ceil(N / 32) warps spread over ALL SMs and all
   // four sub-partitions of each -- N / 8 = 8,192 trajectories (the 8-GPU shard of BASELINE config 3) are 256 warps, i.e.
   // 128 CTAs of 2 warps instead of 19 CTAs of 14.  Warps never synchronise with each other, so the kernel is the same.
-  const int warps = lw_warps_per_cta(a.d.N, wpc, wpc == 7 ? 2 : 1);
+  int warps = lw_warps_per_cta(a.d.N, wpc, wpc == 7 ? 2 : 1);
+  {
+    // Nearly two waves of 8 warps instead of one wave of 14 when all four moment arrays are written: measured at
+    // N = 65,536 (profiles/r02_c3_outputs_probe.jsonl) 6.93 ms against 7.30 ms.  With 14 warps an SM's sub-partitions hold
+    // (4, 4, 3, 3) warps and the scattered 48 / 144-byte output rows of 14 x 32 trajectories per SM cap the pass at
+    // ~1.75 TB/s of DRAM writes; two warps per sub-partition are balanced and 15 % more productive per SM, which outweighs
+    // the 27 % idle tail of the second wave.  With two arrays or fewer the single wave is faster (6.15 vs 6.50 ms).
+    int nout = 0;
+    for (int slot : {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP}) nout += a.out[slot] != nullptr;
+    static const bool forced = getenv("CDK_LW_WARPS") != nullptr;
+    const long long nwarps = (a.d.N + 31) / 32;
+    if (!forced && wpc == 14 && warps > 8 && nout >= 3 && nwarps > 1761 && nwarps <= 2368) warps = 8;
+  }
   const size_t smw = (size_t)warp_bytes * warps;
   const long long wblocks = (a.d.N + 32 * warps - 1) / (32 * warps);
   if (wblocks > 2147483647LL) return CDK_E_SIZE;
