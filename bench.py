@@ -49,7 +49,7 @@ CFG = dict(N=65536, K=1000, n=3, m=1, mean_gap=0.01, dt0=0.0025, solver="rk4", s
 FLOP_SUBSTEP_SURVEY, FLOP_UPDATE_SURVEY = 496.0, 107.0
 FLOP_SUBSTEP_EXEC, FLOP_UPDATE_EXEC = 338.0, 60.0
 BYTES_PER_OBS_STEP = 16 + 192  # y,t in (16 B) + filtered/predicted mean+cov out (24 doubles)
-TRAFFIC_NCU_BYTES = 16.44e9  # dram read 2.64 GB + write 13.80 GB: profiles/r01_ekf_small_lw14_inplace_rk.txt
+TRAFFIC_NCU_BYTES = 14.79e9  # dram read 1.72 GB + write 13.07 GB: profiles/r02_ekf_small_lw_8warp_ctas_N65536.txt
 
 
 def parse():

@@ -1670,11 +1670,12 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   // 128 CTAs of 2 warps instead of 19 CTAs of 14.  Warps never synchronise with each other, so the kernel is the same.
   int warps = lw_warps_per_cta(a.d.N, wpc, wpc == 7 ? 2 : 1);
   {
-    // Nearly two waves of 8 warps instead of one wave of 14 when all four moment arrays are written: measured at
-    // N = 65,536 (profiles/r02_c3_outputs_probe.jsonl) 6.93 ms against 7.30 ms.  With 14 warps an SM's sub-partitions hold
-    // (4, 4, 3, 3) warps and the scattered 48 / 144-byte output rows of 14 x 32 trajectories per SM cap the pass at
-    // ~1.75 TB/s of DRAM writes; two warps per sub-partition are balanced and 15 % more productive per SM, which outweighs
-    // the 27 % idle tail of the second wave.  With two arrays or fewer the single wave is faster (6.15 vs 6.50 ms).
+    // CTAs of 8 warps instead of 14 when all four moment arrays are written and the batch is about one full wave: measured at
+    // N = 65,536 (profiles/r02_c3_outputs_probe.jsonl) 6.93 ms against 7.30 ms.  Two such CTAs share an SM (128 registers,
+    // 104 KB each), so 108 SMs carry 16 warps -- four per sub-partition, balanced -- and 40 carry 8, where 14 warps per SM put
+    // (4, 4, 3, 3) warps on the sub-partitions of every SM; and the scattered 48 / 144-byte output rows merge better in L2
+    // (ncu: 14.8 GB of DRAM traffic instead of 16.4 GB for 13.6 GB algorithmic).  With two arrays or fewer the single wave of
+    // 14 is faster (6.15 vs 6.50 ms).
     int nout = 0;
     for (int slot : {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP}) nout += a.out[slot] != nullptr;
     static const bool forced = getenv("CDK_LW_WARPS") != nullptr;
