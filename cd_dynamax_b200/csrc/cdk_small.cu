@@ -402,6 +402,15 @@ struct alignas(128) LWSmem {
   // followed by the model constants: NPAR values (shared) or 32 * NPAR (one block per lane when batched)
 };
 
+// Time-sliced mode (see ekf_small_lw): the filter state of a group of 32 trajectories between two K-segments.
+template <typename T, int NX>
+struct alignas(128) LWGroup {
+  T m[NX][32];
+  T P[NX * (NX + 1) / 2][32];
+  T ll[32], sprod[32];
+  int esum[32], flags[32];  // flags: bit 0 sbad, bits 8.. status
+};
+
 // Write one staging row (LEN elements of step parity ROW) of this lane's [2][LEN] block.  fp64: the block starts 16-byte
 // aligned (lane stride 16 LEN bytes), so all but at most one element go out as 128-bit stores (conflict-free per quarter
 // warp) -- 14 shared-memory stores per step instead of 24.
@@ -425,7 +434,8 @@ __device__ __forceinline__ void stage_row(T* lane_block, const T (&v)[LEN]) {
 // trajectories are one wave of 2,048 warps over 148 SMs.  CDK_LW_WPC selects.
 template <typename T, class Drift, int NY, int SOLVER, int WPC>
 __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
-    ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps, const int warp_bytes, const int use_token) {
+    ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps, const int warp_bytes, const int use_token, const int G,
+                 const int segk) {
   constexpr int NX = Drift::NX;
   constexpr int NP = St<T, NX>::NP;
   constexpr int NTH = Drift::NTHETA;
@@ -441,8 +451,23 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   const int lane = threadIdx.x & 31;
   // the CTA may be launched with FEWER warps than WPC (launch_one picks the count from N so that a small batch still
   // spreads over every SM and sub-partition): the trajectory map only depends on the run-time block size
-  const long long cta0 = (long long)blockIdx.x * blockDim.x;
-  const long long traj0 = cta0 + warp * 32;
+  //
+  // TIME SLICING (G groups of 32 trajectories per CTA, K cut into segments of `segk` steps; the launcher enables it when the
+  // batch is more than one balanced wave): the CTA's W resident warps work through the items (segment, group) in rounds of W,
+  // item i = segment i / G, group i % G, with a CTA barrier between rounds -- item i - G (the same group's previous segment)
+  // always lies in an earlier round because W <= G.  A group's state crosses segments through an LWGroup block in shared
+  // memory.  Why: 2,048 warps on 148 SMs are 13.84 per SM, i.e. (4, 4, 3, 3) per sub-partition, and the pass takes as long
+  // as the sub-partitions with four; with W = 12 (or 8) resident warps every sub-partition carries three (two) at any time
+  // and the 14 groups of an SM take 14 / 12 passes of a balanced SM instead of 4 / 3 (measured balanced rates:
+  // profiles/r02_c3_outputs_probe.jsonl).  Without slicing G = W, one segment: warp w keeps group w for the whole kernel.
+  const int W = blockDim.x >> 5;
+  const long long ngroups = (N + 31) >> 5;
+  const long long gfirst = (long long)blockIdx.x * G;
+  const int Gc = (int)(ngroups - gfirst < (long long)G ? ngroups - gfirst : (long long)G);  // groups of this CTA
+  const int nseg = (K + segk - 1) / segk;
+  const int Wr = W < Gc ? W : Gc;  // items per round
+  const int nitems = Gc * nseg;
+  long long traj0 = (gfirst + warp) * 32;  // first item (the only one without slicing); reset per item below
   // Optional FP64-pipe semaphore (CDK_LW_TOKEN = permits, default off): at most `permits` warps of an SM sub-partition are
   // inside the RK substep loop at a time (FIFO tickets), the others update / stage / store.  Built to break the convoy
   // that forms because warps sharing a pipe equally re-synchronise their phases; measured no gain (7.2-7.5 ms with 2-3
@@ -452,17 +477,17 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   __shared__ unsigned lw_token[4][2];  // [sub-partition][next ticket, tenures completed]
   if (threadIdx.x < 8) (&lw_token[0][0])[threadIdx.x] = 0u;
   __syncthreads();
-  if (traj0 >= N) return;  // whole warp out of range (nobody ever waits for it)
+  if (nseg == 1 && warp >= Gc) return;  // whole warp out of range (without slicing nobody ever waits for it)
   unsigned hw_warp;
   asm volatile("mov.u32 %0, %warpid;" : "=r"(hw_warp));
   volatile unsigned* const tok = &lw_token[hw_warp & 3][0];
-  const long long traj = traj0 + lane;
-  const bool live = traj < N;
+  long long traj = traj0 + lane;
+  bool live = traj < N;
   // A lane past the end of the batch (ragged last warp) shadows the last trajectory: it computes, never stores (its
   // staging rows fall outside the tensor map and TMA clips them; the cooperative flush copies `nlive` rows).  The step
   // body therefore has no per-lane `live` branch at all.
-  const long long trc = live ? traj : N - 1;
-  const int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
+  long long trc = live ? traj : N - 1;
+  int nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
   const uint32_t par_mask = (1u << CDK_IN_F) | (1u << CDK_IN_L) | (1u << CDK_IN_QC) | (1u << CDK_IN_H) |
                             (1u << CDK_IN_D) | (1u << CDK_IN_R);
   const bool par_batched = (a.d.batched_mask & par_mask) != 0;
@@ -495,13 +520,14 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     for (int i = 0; i < NY; ++i) par[NTH + NP + NY * NX + i] = dv[i];
     for (int i = 0; i < NY * NY; ++i) par[NTH + NP + NY * NX + NY + i] = R[i];
   }
-  const T* __restrict__ Yg = a.in[CDK_IN_Y] ? a.in[CDK_IN_Y] + trc * a.in_stride[CDK_IN_Y] : nullptr;
-  const T* __restrict__ Tg = a.in[CDK_IN_T] + trc * a.in_stride[CDK_IN_T];
+  const T* Yg = a.in[CDK_IN_Y] ? a.in[CDK_IN_Y] + trc * a.in_stride[CDK_IN_Y] : nullptr;
+  const T* Tg = a.in[CDK_IN_T] + trc * a.in_stride[CDK_IN_T];
   // forecast (CDK_FLAG_PREDICT_ONLY): no updates, no observations; Tg holds K + 1 stamps per trajectory, t_init first
   const bool ponly = (a.d.reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
   const int KT = ponly ? K + 1 : K;
+  int kb = 0, ke = K, kpre = KT;  // the item's step range [kb, ke) and the end of its input prefetches
   auto prefetch = [&](int kk) {
-    if (kk < KT) {
+    if (kk < kpre) {
       if (!ponly) {
 #pragma unroll
         for (int c = 0; c < NY; ++c) cp_async_elem(&sm.inY[kk & (LW_RING - 1)][c][lane], Yg + (long long)kk * NY + c);
@@ -510,20 +536,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     }
     cp_async_commit();
   };
-  prefetch(0);
-  prefetch(1);
-  prefetch(2);
   St<T, NX> s;
-  {
-    const T* m0 = a.in[CDK_IN_M0] + trc * a.in_stride[CDK_IN_M0];
-    const T* P0 = a.in[CDK_IN_P0] + trc * a.in_stride[CDK_IN_P0];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) s.m[i] = m0[i];
-#pragma unroll
-    for (int i = 0; i < NX; ++i)
-#pragma unroll
-      for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = P0[i * NX + j];
-  }
   __syncwarp();
   const T* par = par_batched ? parbase + lane * NPAR : parbase;
   // WPC == 14: theta and L Qc L^T stay in registers for the whole kernel; WPC == 7: re-read from shared memory
@@ -668,7 +681,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
       if (LLC && live) LLC[traj * (long long)K + k] = ll;
     }
     prefetch(k + 3);
-    if (use_tma && row == 0 && k > 0) {  // the FM/FP store of the previous block was issued ~6 substeps ago
+    if (use_tma && row == 0 && k > kb) {  // the FM/FP store of the previous block was issued ~6 substeps ago
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
       __syncwarp();
     }
@@ -697,12 +710,12 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
       __syncwarp();
       if (lane == 0) atomicAdd(const_cast<unsigned*>(tok + 1), 1u);
     }
-    if (use_tma && row == 0 && k > 0) {  // the PM/PP store of the previous block was issued one whole step ago
+    if (use_tma && row == 0 && k > kb) {  // the PM/PP store of the previous block was issued one whole step ago
       if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       __syncwarp();
     }
     if (any_out) stage(rowc, &sm.pm[lane][0][0], &sm.pp[lane][0][0]);
-    if (any_out && (row == 1 || k == K - 1)) {
+    if (any_out && (row == 1 || k == ke - 1)) {
       __syncwarp();
       if (use_tma) {
         if (lane == 0) tma_pair(2, k - 1);
@@ -726,9 +739,83 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     }
   };
 
-  for (int k = 0; k < K; k += 2) {
-    step(std::integral_constant<int, 0>{}, k);
-    if (k + 1 < K) step(std::integral_constant<int, 1>{}, k + 1);
+  LWGroup<T, NX>* const groups = reinterpret_cast<LWGroup<T, NX>*>(smem_raw + (size_t)W * warp_bytes);  // nseg > 1 only
+  for (int base = 0; base < nitems; base += Wr) {
+    const int item = base + warp;
+    if (warp < Wr && item < nitems) {
+      const int seg = item / Gc, g = item - seg * Gc;
+      traj0 = (gfirst + g) * 32;
+      traj = traj0 + lane;
+      live = traj < N;
+      trc = live ? traj : N - 1;
+      nlive = (int)((N - traj0) < 32 ? (N - traj0) : 32);
+      Yg = a.in[CDK_IN_Y] ? a.in[CDK_IN_Y] + trc * a.in_stride[CDK_IN_Y] : nullptr;
+      Tg = a.in[CDK_IN_T] + trc * a.in_stride[CDK_IN_T];
+      kb = seg * segk;
+      ke = kb + segk < K ? kb + segk : K;
+      kpre = ke + 1 < KT ? ke + 1 : KT;  // step ke - 1 reads the stamp of step ke
+      if (use_tma && base > 0) {  // this warp's staging rows may still be read by the stores of its previous item
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+      }
+      prefetch(kb);
+      prefetch(kb + 1);
+      prefetch(kb + 2);
+      if (seg == 0) {
+        const T* m0 = a.in[CDK_IN_M0] + trc * a.in_stride[CDK_IN_M0];
+        const T* P0 = a.in[CDK_IN_P0] + trc * a.in_stride[CDK_IN_P0];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s.m[i] = m0[i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+#pragma unroll
+          for (int j = i; j < NX; ++j) s.P[pidx<NX>(i, j)] = P0[i * NX + j];
+        ll = T(0);
+        sprod = T(1);
+        esum = 0;
+        sbad = false;
+        status = 0;
+      } else {
+        const LWGroup<T, NX>& gs = groups[g];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) s.m[i] = gs.m[i][lane];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) s.P[i] = gs.P[i][lane];
+        ll = gs.ll[lane];
+        sprod = gs.sprod[lane];
+        esum = gs.esum[lane];
+        sbad = (gs.flags[lane] & 1) != 0;
+        status = gs.flags[lane] >> 8;
+      }
+      for (int k = kb; k < ke; k += 2) {
+        step(std::integral_constant<int, 0>{}, k);
+        if (k + 1 < ke) step(std::integral_constant<int, 1>{}, k + 1);
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");  // the input ring is refilled from the next item's range
+      if (seg + 1 < nseg) {
+        LWGroup<T, NX>& gs = groups[g];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) gs.m[i][lane] = s.m[i];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) gs.P[i][lane] = s.P[i];
+        gs.ll[lane] = ll;
+        gs.sprod[lane] = sprod;
+        gs.esum[lane] = esum;
+        gs.flags[lane] = (sbad ? 1 : 0) | (status << 8);
+      } else if (live) {
+        T llf = ll;
+        int st = status;
+        if (lean) {
+          // sum_k log S_k = esum log 2 + log(sprod); the -log(2 pi)/2 of every step
+          llf -= T(0.5) * (T(esum) * T(0.69314718055994530942) + log(sprod)) + T(K) * half_log_2pi<T>();
+          if (sbad) llf = T(NAN);
+        }
+        if (st == 0 && !isfinite(llf)) st = 1;
+        if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = llf;
+        if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = st;
+      }
+    }
+    if (nseg > 1) __syncthreads();
   }
   if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (trace && lane == 0) {
@@ -740,16 +827,6 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
     r[1] = globaltimer();
     r[2] = smid;
     r[3] = wid;
-  }
-  if (live) {
-    if (lean) {
-      // sum_k log S_k = esum log 2 + log(sprod); the -log(2 pi)/2 of every step
-      ll -= T(0.5) * (T(esum) * T(0.69314718055994530942) + log(sprod)) + T(K) * half_log_2pi<T>();
-      if (sbad) ll = T(NAN);
-    }
-    if (status == 0 && !isfinite(ll)) status = 1;
-    if (a.out[CDK_OUT_LL]) static_cast<T*>(a.out[CDK_OUT_LL])[traj] = ll;
-    if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = status;
   }
 }
 
@@ -1598,6 +1675,16 @@ encode_tiled_fn get_encode_tiled() {
 // Warps per CTA for a batch of N trajectories: the smallest count that still fits the batch into one wave of
 // `ctas_per_sm` CTAs per SM (so the warps spread over every SM and sub-partition), at most `max_warps`.
 // CDK_LW_WARPS=k forces k (experiments).
+int lw_num_sms() {
+  static const int num_sms = []() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
+      n = 148;
+    return n;
+  }();
+  return num_sms;
+}
+
 int lw_warps_per_cta(long long N, int max_warps, int ctas_per_sm) {
   static const int forced = []() {
     const char* e = getenv("CDK_LW_WARPS");
@@ -1669,27 +1756,75 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   // four sub-partitions of each -- N / 8 = 8,192 trajectories (the 8-GPU shard of BASELINE config 3) are 256 warps, i.e.
   // 128 CTAs of 2 warps instead of 19 CTAs of 14.  Warps never synchronise with each other, so the kernel is the same.
   int warps = lw_warps_per_cta(a.d.N, wpc, wpc == 7 ? 2 : 1);
-  {
-    // CTAs of 8 warps instead of 14 when all four moment arrays are written and the batch is about one full wave: measured at
-    // N = 65,536 (profiles/r02_c3_outputs_probe.jsonl) 6.93 ms against 7.30 ms.  Two such CTAs share an SM (128 registers,
-    // 104 KB each), so 108 SMs carry 16 warps -- four per sub-partition, balanced -- and 40 carry 8, where 14 warps per SM put
-    // (4, 4, 3, 3) warps on the sub-partitions of every SM; and the scattered 48 / 144-byte output rows merge better in L2
-    // (ncu: 14.8 GB of DRAM traffic instead of 16.4 GB for 13.6 GB algorithmic).  With two arrays or fewer the single wave of
-    // 14 is faster (6.15 vs 6.50 ms).
-    int nout = 0;
-    for (int slot : {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP}) nout += a.out[slot] != nullptr;
-    static const bool forced = getenv("CDK_LW_WARPS") != nullptr;
-    const long long nwarps = (a.d.N + 31) / 32;
-    if (!forced && wpc == 14 && warps > 8 && nout >= 3 && nwarps > 1761 && nwarps <= 2368) warps = 8;
+  int nout = 0;
+  for (int slot : {CDK_OUT_FM, CDK_OUT_FP, CDK_OUT_PM, CDK_OUT_PP}) nout += a.out[slot] != nullptr;
+  static const bool forced = getenv("CDK_LW_WARPS") != nullptr;
+  const long long nwarps = (a.d.N + 31) / 32;
+  // Time slicing (see the kernel): when the batch is more than one BALANCED wave -- 12 resident warps per SM, three per
+  // sub-partition, or 8 when all four moment arrays are written (the scattered 48 / 144-byte output rows of more warps cap
+  // the pass at ~1.8 TB/s of DRAM writes; measured balanced rates in profiles/r02_c3_outputs_probe.jsonl: 12.0 / 9.5
+  // trajectories per us with 12 warps, 11.3 / 10.6 with 8, log-likelihood only / all outputs) -- every SM gets
+  // G = ceil(groups / SMs) groups of 32 trajectories and works through them in K-segments of 50 steps.  CDK_LW_SLICE=0
+  // disables, CDK_LW_SLICE=w forces w resident warps.
+  // (read at every launch, not cached: the tests switch them; CDK_LW_SLICE_SMS pretends a smaller GPU so that a small batch
+  // takes the sliced path)
+  const char* slice_e = getenv("CDK_LW_SLICE");
+  const int slice_env = slice_e ? atoi(slice_e) : -1;
+  const char* sms_e = getenv("CDK_LW_SLICE_SMS");
+  const char* segk_e = getenv("CDK_LW_SEGK");  // segment length (even); default: chosen below
+  const int segk_env = segk_e && atoi(segk_e) >= 2 ? (atoi(segk_e) & ~1) : 50;
+  int G = warps, segk = a.d.K > 0 ? a.d.K : 1;
+  size_t smw = (size_t)warp_bytes * warps;
+  long long wblocks = (a.d.N + 32 * warps - 1) / (32 * warps);
+  const bool ponly_l = (a.d.reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
+  bool sliced = false;
+  if (!forced && slice_env != 0 && wpc == 14 && !par_batched && !ponly_l && a.d.K >= 200 && (a.d.K & 1) == 0) {
+    const int sms = sms_e && atoi(sms_e) > 0 ? atoi(sms_e) : lw_num_sms();
+    for (int wres : {slice_env > 0 ? slice_env : (nout >= 3 ? 8 : 12), 8}) {
+      if (wres < 1 || wres > 14 || nwarps <= (long long)sms * wres) continue;
+      const long long Gs = (nwarps + sms - 1) / sms;
+      const size_t need = (size_t)warp_bytes * wres + (size_t)Gs * sizeof(LWGroup<T, NX>);
+      if (Gs < wres || need > 227 * 1024) continue;
+      warps = wres;
+      G = (int)Gs;
+      // segment length: the pass costs ceil(G nseg / W) rounds of segk steps; fewest total steps, then fewest segments
+      // (every item pays a barrier and a refill of its input ring: 250-step segments measured 3 % faster than 50-step ones)
+      segk = segk_env;
+      if (!segk_e) {
+        long long best = -1;
+        for (int ns = 2; ns <= 24; ++ns) {
+          const int sk = (((a.d.K + ns - 1) / ns) + 1) & ~1;
+          const int nsr = (a.d.K + sk - 1) / sk;  // segments this length really gives
+          const long long cost = ((Gs * nsr + wres - 1) / wres) * sk;
+          if (best < 0 || cost < best) {
+            best = cost;
+            segk = sk;
+          }
+        }
+      }
+      smw = need;
+      wblocks = (nwarps + Gs - 1) / Gs;
+      sliced = true;
+      break;
+    }
   }
-  const size_t smw = (size_t)warp_bytes * warps;
-  const long long wblocks = (a.d.N + 32 * warps - 1) / (32 * warps);
+  if (!sliced) {
+    // CTAs of 8 warps instead of 14 when all four moment arrays are written and the batch is about one full wave (only
+    // reached when slicing is off): 6.93 ms against 7.30 ms at N = 65,536.  Two such CTAs share an SM, so 108 SMs carry
+    // 16 warps -- four per sub-partition, balanced -- and 40 carry 8, where 14 warps per SM put (4, 4, 3, 3) warps on the
+    // sub-partitions of every SM.
+    if (!forced && wpc == 14 && warps > 8 && nout >= 3 && nwarps > 1761 && nwarps <= 2368) warps = 8;
+    G = warps;
+    smw = (size_t)warp_bytes * warps;
+    wblocks = (a.d.N + 32 * warps - 1) / (32 * warps);
+  }
   if (wblocks > 2147483647LL) return CDK_E_SIZE;
   V5Maps maps;
   make_maps<T>(a, NX, 32, maps);
   auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7> : ekf_small_lw<T, Drift, NY, SOLVER, 14>;
-  if ((size_t)warp_bytes * wpc > 48 * 1024) {
-    if (cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)warp_bytes * wpc)) != cudaSuccess)
+  {
+    const size_t cap = (size_t)warp_bytes * wpc > smw ? (size_t)warp_bytes * wpc : smw;
+    if (cap > 48 * 1024 && cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap) != cudaSuccess)
       return check_launch("cudaFuncSetAttribute(ekf_small_lw)");
   }
   static const int token_env = []() {  // experiment, default off (see the kernel)
@@ -1697,7 +1832,7 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
     return e ? atoi(e) : 0;
   }();
   const int use_token = wpc == 14 ? token_env : 0;  // with two CTAs per SM the lock would have to span CTAs
-  kw<<<(unsigned)wblocks, 32 * warps, smw, s>>>(a, maps, warp_bytes, use_token);
+  kw<<<(unsigned)wblocks, 32 * warps, smw, s>>>(a, maps, warp_bytes, use_token, G, segk);
   note_launch();
   return check_launch("ekf_small_lw");
 }
