@@ -573,9 +573,11 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "allreduce": allreduce_kind,
         "roofline": {
-            "bound": "fp64", "kernel": f"ekf_small_lw<double, DriftL63, 1, RK4> on rank 0: {warps} independent warps "
-                                        "(32 trajectories each, state and drift parameters in registers, TMA tensor stores), "
-                                        "warps per CTA chosen from N so that they spread over all SMs",
+            "bound": "fp64", "kernel": f"ekf_small_lw<double, DriftL63, 1, RK4> on rank 0: {warps} groups of 32 trajectories "
+                                        "(state and drift parameters in registers, TMA tensor stores); up to one balanced "
+                                        "wave each group keeps one warp, warps per CTA chosen from N so that they spread over "
+                                        "all SMs and sub-partitions; above it (this config at 1 GPU) the groups of an SM are "
+                                        "time-sliced over 8 resident warps in K-segments through shared memory",
             "achieved": ach_survey, "peak": fp64_peak, "unit": "TFLOP/s",
             "frac": ach_survey / fp64_peak if fp64_peak else None,
             "peak_source": "DFMA probe (cdk_fma_probe_f64) measured in this run, burst; MEASURED_PEAKS.json has no FP64 "
