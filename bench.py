@@ -44,10 +44,10 @@ CFG = dict(N=65536, K=1000, n=3, m=1, mean_gap=0.01, dt0=0.0025, solver="rk4", s
 # 3x3 products, loop-invariant L Qc L^T hoisted) -- this is the figure `roofline.achieved` is computed from.
 # The kernel stores P symmetric (6 entries), uses the sparsity of the Lorenz-63 Jacobian and folds dt into the RK
 # coefficients, so it EXECUTES fewer: per RK4 substep 4 stages * (f 8 + J.P 33 + dP 12 + stage/accumulate FMAs 36) - 18
-# = 338 (SASS: 127 DFMA + 51 DADD + 25 DMUL per substep); scalar-emission update 60.  Both are reported (`achieved` /
+# = 324 (SASS: 143 DFMA + 25 DADD + 13 DMUL per substep; 338 = 127 + 51 + 25 before the leaner covariance RHS); scalar-emission update 60.  Both are reported (`achieved` /
 # `achieved_executed`).
 FLOP_SUBSTEP_SURVEY, FLOP_UPDATE_SURVEY = 496.0, 107.0
-FLOP_SUBSTEP_EXEC, FLOP_UPDATE_EXEC = 338.0, 60.0
+FLOP_SUBSTEP_EXEC, FLOP_UPDATE_EXEC = 324.0, 60.0
 BYTES_PER_OBS_STEP = 16 + 192  # y,t in (16 B) + filtered/predicted mean+cov out (24 doubles)
 TRAFFIC_NCU_BYTES = 14.79e9  # dram read 1.72 GB + write 13.07 GB: profiles/r02_ekf_small_lw_8warp_ctas_N65536.txt
 
@@ -587,10 +587,10 @@ def run_ours(args):
             "peak_3_register_operands": fp64_peak3,
             "peak_3_register_operands_note": "cdk_fma3_probe_f64, measured in this run: a DFMA whose three operands are "
                                              "distinct vector registers issues every 3 cycles per SM sub-partition on "
-                                             "B200, not 2 (register-file bandwidth); 127 of the kernel's 203 FP64 "
+                                             "B200, not 2 (register-file bandwidth); most of the 143 DFMAs among the kernel's 181 FP64 "
                                              "instructions per substep are such DFMAs",
             "frac_of_3_register_peak": ach_survey / fp64_peak3 if fp64_peak3 else None,
-            "flop_model_executed": "338*sum_q + 60*N*K (symmetric P, sparse Lorenz-63 Jacobian, dt folded into RK weights)",
+            "flop_model_executed": "324*sum_q + 60*N*K (symmetric P, sparse Lorenz-63 Jacobian, dt folded into RK weights)",
             "kernel_ms": kernel_ms,
             "kernel_ms_how": "CUDA events between back-to-back launches of the pre-marshalled C-ABI call on the launching "
                              "stream (mean of 7), GPU kept busy by the previous launch: kernel duration only",
