@@ -174,6 +174,22 @@ __device__ void moments(cg::cluster_group& cluster, const ELay& L, unsigned char
   cluster.sync();  // nobody may overwrite psum / Cp (next moments call) or read a stale Cxx before everyone is done
 }
 
+// Lorenz-96 drift entry and Euler-Maruyama update with the oracle's operation order and NO fused multiply-adds
+// (((x_{i+1} - x_{i-2}) x_{i-1} - x_i) + F;  (x + dt f) + noise): both member mappings and the NumPy oracle then agree bit for
+// bit given the same deviates (the compiler is otherwise free to contract differently in differently shaped code).
+__device__ __forceinline__ double l96_entry(double xp, double xm2, double xm1, double xi, double F) {
+  return __dadd_rn(__dsub_rn(__dmul_rn(__dsub_rn(xp, xm2), xm1), xi), F);
+}
+__device__ __forceinline__ float l96_entry(float xp, float xm2, float xm1, float xi, float F) {
+  return __fadd_rn(__fsub_rn(__fmul_rn(__fsub_rn(xp, xm2), xm1), xi), F);
+}
+__device__ __forceinline__ double em_update(double x, double dt, double f, double noise) {
+  return __dadd_rn(__dadd_rn(x, __dmul_rn(dt, f)), noise);
+}
+__device__ __forceinline__ float em_update(float x, float dt, float f, float noise) {
+  return __fadd_rn(__fadd_rn(x, __fmul_rn(dt, f)), noise);
+}
+
 // ---- per-member drift on a thread-private state ---------------------------------------------------------------------
 // NX > 0 fixes the drift at compile time (NX = 40: Lorenz-96, NX = 3: Lorenz-63) so that fully unrolled code stays small.
 template <typename T, int NX>
@@ -185,15 +201,23 @@ __device__ __forceinline__ T member_f(int drift_id, const T* th, int n, int i, c
   }
   if (NX > 3) {
     const int ip = i + 1 == n ? 0 : i + 1, im1 = i == 0 ? n - 1 : i - 1, im2 = im1 == 0 ? n - 1 : im1 - 1;
-    return (x[ip] - x[im2]) * x[im1] - x[i] + th[0];
+    return l96_entry(x[ip], x[im2], x[im1], x[i], th[0]);
   }
   return drift_f<T>(drift_id, th, n, i, [&](int j) { return x[j]; });
 }
 
 // NX > 0: compile-time state dimension (member state in registers, loops unrolled); NX == 0: runtime n <= CDK_MAX_N
 // (thread-private arrays in local memory).
-template <typename T, int NX>
-__global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
+//
+// LIGHT (Lorenz-96 n = 40, Euler-Maruyama, diagonal diffusion -- BASELINE config 5): 512 threads per CTA, <= 128 registers.
+// The per-member state of the legacy mapping (x and x_e in registers: 160 of 255 registers, 8 warps per SM, every phase of
+// the kernel latency-bound at two warps per scheduler) is replaced by the ensemble's own shared-memory columns: lanes l and
+// l + 16 of a warp share member 16 warp + l and sweep dimensions [0, 20) and [20, 40) IN PLACE with a three-value rolling
+// window of old entries in registers (the stencil reads x_{i-2}, x_{i-1}, x_{i+1}); the three old values a sweep needs from the
+// partner's half are read before anyone writes (one __syncwarp).  Same counters, same operation order: bit-identical to the
+// legacy mapping.  Sixteen warps then also share the cooperative phases (moments, gain products, update algebra).
+template <typename T, int NX, bool LIGHT>
+__global__ void __launch_bounds__(LIGHT ? 2 * ENKF_TPB : ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
   constexpr int NXA = NX > 0 ? NX : CDK_MAX_N;
   constexpr int UF = NX > 0 ? NX : 1;             // unroll factor of loops over the state dimension
   constexpr int UFP = NX > 0 ? (NX + 3) / 4 : 1;  // ... over normal quads (four normals per Philox call)
@@ -444,8 +468,10 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
         if (i < n) X[(size_t)i * ldE + el] = x[i];
     }
     __syncthreads();
-    moments<T>(cluster, L, sh, nmem, E, C);  // filtered moments (:225-228)
-    write_moments(FM, FP, row0 + k);
+    if (FM || FP) {  // filtered moments (:225-228): an output only -- the next update reads the PREDICTED moments
+      moments<T>(cluster, L, sh, nmem, E, C);
+      write_moments(FM, FP, row0 + k);
+    }
     if (LLC && rank == 0 && threadIdx.x == 0) LLC[row0 + k] = ll;
     }
 
@@ -464,6 +490,56 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
       }
       const T dt = tnext - tprev;
       const T sqdt = sqrt(dt);
+      bool light_done = false;
+      if constexpr (LIGHT && NX == 40) {
+        if (diagG && d.solver == CDK_EULER) {
+          light_done = true;
+          constexpr int HN = NX / 2;
+          const int lane = threadIdx.x & 31, half = lane >> 4;
+          const int el = (threadIdx.x >> 5) * 16 + (lane & 15);
+          const bool act = el < nmem;
+          const int i0 = half * HN;
+          T* xc = X + el;
+          const T th0 = th[0];
+          T xm2 = T(0), xm1 = T(0), cur = T(0), halo = T(0);
+          if (act) {
+            xm2 = xc[(size_t)(i0 == 0 ? NX - 2 : i0 - 2) * ldE];
+            xm1 = xc[(size_t)(i0 == 0 ? NX - 1 : i0 - 1) * ldE];
+            halo = xc[(size_t)(i0 + HN == NX ? 0 : i0 + HN) * ldE];
+            cur = xc[(size_t)i0 * ldE];
+          }
+          __syncwarp();  // both halves hold their old halo values before either writes
+          if (act) {
+#pragma unroll
+            for (int q0 = 0; q0 < HN; q0 += 8) {
+              double z8[8];
+              if (q0 + 4 < HN) {
+                normal_oct((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, (i0 + q0) >> 2),
+                           rng_c3(RNG_DYN, nsteps, ((i0 + q0) >> 2) + 1), seed, z8);
+              } else {
+                double z4[4];
+                normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_DYN, nsteps, (i0 + q0) >> 2), seed, z4);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) z8[u] = z4[u];
+              }
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                if (q0 + u < HN) {
+                  const int i = i0 + q0 + u;
+                  const T nxt = (q0 + u + 1 < HN) ? xc[(size_t)(i + 1) * ldE] : halo;
+                  const T noise = G[i * ldn + i] * (sqdt * (T)z8[u]);
+                  xc[(size_t)i * ldE] = em_update(cur, dt, l96_entry(nxt, xm2, xm1, cur, th0), noise);
+                  xm2 = xm1;
+                  xm1 = cur;
+                  cur = nxt;
+                }
+              }
+            }
+          }
+          __syncwarp();  // the partner's new entries are this half's halo of the next substep
+        }
+      }
+      if (!light_done)
       for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
         T x[NXA], xe[NXA];  // xe first holds the noise G dW, then the Euler-Maruyama state
 #pragma unroll UF
@@ -503,7 +579,7 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
         }
 #pragma unroll UF
         for (int i = 0; i < NXA; ++i)
-          if (i < n) xe[i] = fma(dt, member_f<T, NX>(d.drift_id, th, n, i, x), x[i]) + xe[i];
+          if (i < n) xe[i] = em_update(x[i], dt, member_f<T, NX>(d.drift_id, th, n, i, x), xe[i]);
         if (d.solver == CDK_HEUN) {
           // x + dt/2 (f(x) + f(xe)) + noise, written as xe + dt/2 (f(xe) - f(x)) so the noise is not kept (oracle: same form)
           const T hdt = T(0.5) * dt;
@@ -535,14 +611,14 @@ __global__ void __launch_bounds__(ENKF_TPB, 1) enkf_kernel(const EArgs<T> g) {
   (void)misc;
 }
 
-template <typename T, int NX>
+template <typename T, int NX, bool LIGHT = false>
 int launch_nx(const EArgs<T>& g, size_t smem, cudaStream_t s) {
-  auto kern = enkf_kernel<T, NX>;
+  auto kern = enkf_kernel<T, NX, LIGHT>;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("cudaFuncSetAttribute(enkf_kernel)");
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(g.k.d.N * g.C), 1, 1);
-  cfg.blockDim = dim3(ENKF_TPB, 1, 1);
+  cfg.blockDim = dim3(LIGHT ? 2 * ENKF_TPB : ENKF_TPB, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -594,7 +670,12 @@ int launch_enkf(const KArgs<T>& a, cudaStream_t s) {
     if (g.C) break;
   }
   if (g.C == 0) return CDK_E_SIZE;  // ensemble too large for 8 CTAs x 227 KB
-  if (d.n == 40 && d.drift_id == CDK_DRIFT_LORENZ96) return launch_nx<T, 40>(g, smem, s);
+  if (d.n == 40 && d.drift_id == CDK_DRIFT_LORENZ96) {
+    // two threads per member, state swept in shared memory (see the kernel); CDK_ENKF_LIGHT=0: the register mapping
+    const char* le = getenv("CDK_ENKF_LIGHT");
+    const bool light = !(le && le[0] == '0') && d.solver == CDK_EULER && g.dg && g.Eloc <= ENKF_TPB;
+    return light ? launch_nx<T, 40, true>(g, smem, s) : launch_nx<T, 40>(g, smem, s);
+  }
   if (d.n == 3 && d.drift_id == CDK_DRIFT_LORENZ63) return launch_nx<T, 3>(g, smem, s);
   return launch_nx<T, 0>(g, smem, s);
 }

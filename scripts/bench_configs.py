@@ -155,8 +155,9 @@ def c5(scale):
     y = 8 + 2 * torch.randn(N, K, m, **f64)
     hp = cd.EnKFHyperParams(N_particles=E, key=1234, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
     ms = timeit(lambda: cd.cdnlgssm_filter(p, y, t[..., None], hp), reps=2)
+    ms_ll = timeit(lambda: cd.cdnlgssm_filter(p, y, t[..., None], hp, output_fields=[]), reps=2)
     return dict(config=f"C5 EnKF Lorenz-96 n=40 m=20 E=1024 N={N} (of 1,024) K=500", ms=ms, obs_steps_per_s=N * K / ms * 1e3,
-                tflops_survey=(0.4e6 * 4.5 + 13.2e6) * N * K / ms / 1e9)
+                tflops_survey=(0.4e6 * 4.5 + 13.2e6) * N * K / ms / 1e9, ll_only_ms=ms_ll, ll_only_obs_steps_per_s=N * K / ms_ll * 1e3)
 
 
 if __name__ == "__main__":

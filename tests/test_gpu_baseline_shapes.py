@@ -163,6 +163,23 @@ def test_c2_kf_n16_k500_vs_oracle(solver, dt0):
             assert scaled_err(getattr(s, fld), rs[fld]) < 1e-8, (stype, fld)
 
 
+@pytest.mark.parametrize("E", [1024, 600])
+def test_c5_enkf_light_mapping_is_bit_identical(E, monkeypatch):
+    """The two-threads-per-member mapping (ensemble swept in place in shared memory, 512 threads) against the
+    one-thread-per-member register mapping: same counters, same operation order -> identical bits (ragged last CTA at E = 600)."""
+    cd = api()
+    g, po, t, y = _l96_case(N=2, K=12, seed=51)
+    hp = cd.EnKFHyperParams(N_particles=E, key=77, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
+    monkeypatch.setenv("CDK_ENKF_CLUSTER", "4")
+    monkeypatch.setenv("CDK_ENKF_LIGHT", "0")
+    f0 = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], hp)
+    monkeypatch.setenv("CDK_ENKF_LIGHT", "1")
+    f1 = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], hp)
+    assert np.array_equal(np.asarray(f0.marginal_loglik), np.asarray(f1.marginal_loglik))
+    for fld in FIELDS:
+        assert np.array_equal(np.asarray(getattr(f0, fld)), np.asarray(getattr(f1, fld))), fld
+
+
 @pytest.mark.parametrize("n,m", [(36, 36), (32, 40), (12, 33)])
 def test_kf_maximum_sizes_vs_oracle(n, m):
     """The largest KF the 227 KB of a CTA hold (n = m = 36; cdk.h) and emission dimensions above 32 (two rows per lane in the single-warp Cholesky, the
