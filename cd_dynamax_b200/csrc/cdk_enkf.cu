@@ -400,6 +400,22 @@ __global__ void __launch_bounds__(LIGHT ? 2 * ENKF_TPB : ENKF_TPB, 1) enkf_kerne
       // Over the CTA's members at once: D = (y - d) 1^T + chol(R) Z - H X  [m x nmem],  X += K D, the two products on the FP64
       // tensor cores (per member this is 2 m n FMAs with one shared-memory operand load each: 11 % of the instruction stream).
       T* Db = reinterpret_cast<T*>(sh + L.DB);
+      const bool pair_fill = (int)blockDim.x >= 2 * g.Eloc && diagR && d.perturb_measurements;
+      if (pair_fill) {
+        // twice as many threads as members (LIGHT): lanes l and l + 16 share a member and take alternate quads of the
+        // observation noise, so all sixteen warps generate deviates instead of eight waiting at the barrier below
+        const int lane = threadIdx.x & 31, half = lane >> 4;
+        const int el = (threadIdx.x >> 5) * 16 + (lane & 15);
+        if (el < nmem) {
+          for (int p = 4 * half; p < m; p += 8) {
+            double z4[4];
+            normal_quad((uint32_t)(e_base + el), ctr_traj, (uint32_t)k, rng_c3(RNG_OBS, 0, p >> 2), seed, z4);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (p + u < m) Db[(size_t)(p + u) * ldE + el] = (yv[p + u] + chR[(p + u) * ldm + p + u] * (T)z4[u]) - dv[p + u];
+          }
+        }
+      } else
       for (int el = threadIdx.x; el < nmem; el += blockDim.x) {
         if (d.perturb_measurements) {
           T r[CDK_MAX_M];
