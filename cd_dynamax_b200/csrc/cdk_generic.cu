@@ -33,13 +33,16 @@ struct Lay {
   int n, m, du, ldn, ldm, nn, S, nth, mpoff;
   int TH, LQL, H, R, DV, BV, BU, DU, YV, UV, MU, P, ODEY, YS, ACC, KS, J, W1, W2, W3, SM, SL, RV, MF, PF, C0, total;
   Lay() = default;
-  __host__ __device__ Lay(const cdk_desc& d, int algo, int nslots) {
+  // reg_ode: the launcher has chosen the register-resident stencil ODE (ode_solve_stencil), so the shared-memory RHS and its
+  // Jacobian buffer are never used by this launch
+  __host__ __device__ Lay(const cdk_desc& d, int algo, int nslots, bool reg_ode = false) {
     n = d.n; m = d.m; du = d.d_u; ldn = ldp(n); ldm = ldp(m); nn = n * ldn;
     const bool lin = algo == ALGO_KF_FILTER || algo == ALGO_KF_SMOOTH;
     const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
     const bool ukf = algo == ALGO_UKF_FILTER;
     const bool ukfc = ukf && ukf_closed(d);
-    nth = lin ? nn : (ukf ? d.n_theta : (d.n_theta > nn ? d.n_theta : nn));
+    const bool ekf_reg = algo == ALGO_EKF_FILTER && reg_ode;
+    nth = lin ? nn : ((ukf || ekf_reg) ? d.n_theta : (d.n_theta > nn ? d.n_theta : nn));
     const int mx = n > m ? n : m;
     const int wsz = mx * ldp(mx);
     mpoff = (n + 1) & ~1;           // offset of P behind MU inside the (m, P) ODE state
@@ -52,10 +55,10 @@ struct Lay {
     MU = take(n); P = take(nn);  // contiguous: [MU | P] is the (m, P) ODE state (n is padded to even by take())
     ODEY = take(lin ? 2 * nn : 0);
     YS = take(S); ACC = take(S); KS = take(nslots * S);
-    if (ukfc && nslots == 1 && m <= n && stencil_drift(d.drift_id)) {
-      // closed-form UKF, stencil Jacobian, chain tableau: the RHS needs no scratch at all (J P is formed in the output
-      // block and symmetrised in place) and the update's three [m x n] scratch matrices are only live while the ODE stage
-      // buffers are not -- 84 KB for n = 40, m = 20.
+    if ((ukfc || ekf_reg) && nslots == 1 && m <= n && stencil_drift(d.drift_id)) {
+      // closed-form UKF (or the EKF on the register-resident stencil ODE), stencil Jacobian, chain tableau: the RHS needs
+      // no scratch at all (J P is formed in the output block and symmetrised in place) and the update's three [m x n]
+      // scratch matrices are only live while the ODE stage buffers are not -- 84 KB for n = 40, m = 20: two CTAs per SM.
       J = KS; W1 = YS; W2 = KS; W3 = ACC;
     } else if (ukf && !ukfc && nslots == 1 && m <= n) {
       // sigma-point UKF with a chain tableau: 110 KB instead of 164 KB for n = 40, m = 20, so that TWO trajectories share
@@ -1107,20 +1110,20 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
     return e && e[0] == '0' ? 0 : 1;
   }();
   g.reg_ode = reg_ode_env;
-  g.lay = Lay(g.k.d, algo, g.nslots);
+  const int nmax = a.d.n > a.d.m ? a.d.n : a.d.m;
+  const int threads = nmax <= 4 ? 32 : (nmax <= 8 ? 64 : (nmax <= 16 ? 128 : 256));
+  const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
+  // Lorenz-96 moment ODE with a chain tableau: RK state in registers (ode_solve_stencil); CDK_GENERIC_REG_ODE=0 disables
+  const cdk_desc& dd = g.k.d;
+  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && g.nslots == 1 && stencil_fits(dd.n, threads) &&
+                       ((algo == ALGO_EKF_FILTER && dd.state_order != CDK_ORDER_ZEROTH) || (algo == ALGO_UKF_FILTER && ukf_closed(dd)));
+  g.lay = Lay(g.k.d, algo, g.nslots, reg_ode);
   const Lay& L = g.lay;
   const size_t smem = (size_t)L.total * sizeof(T);
   int dev = 0, max_optin = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem > (size_t)max_optin) return CDK_E_SIZE;
-  const int n = a.d.n > a.d.m ? a.d.n : a.d.m;
-  const int threads = n <= 4 ? 32 : (n <= 8 ? 64 : (n <= 16 ? 128 : 256));
-  const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
-  // Lorenz-96 moment ODE with a chain tableau: RK state in registers (ode_solve_stencil); CDK_GENERIC_REG_ODE=0 disables
-  const cdk_desc& dd = g.k.d;
-  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && g.nslots == 1 && stencil_fits(dd.n, threads) &&
-                       ((algo == ALGO_EKF_FILTER && dd.state_order != CDK_ORDER_ZEROTH) || (algo == ALGO_UKF_FILTER && ukf_closed(dd)));
   auto kern = smooth ? generic_smooth_kernel<T> : (reg_ode ? generic_filter_kernel<T, true> : generic_filter_kernel<T, false>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
