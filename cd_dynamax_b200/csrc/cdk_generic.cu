@@ -433,6 +433,7 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
   int nsteps = 0;
   bool hit = false;
   const int boff0 = L.YS, boff1 = L.KS;
+  int flip = 0;
   while (tprev < t1) {
     if (nsteps >= max_steps) {
       hit = true;
@@ -448,7 +449,11 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
     for (int st = 0; st < tab.S; ++st) {
       // chain tableau: only the previous stage; a = 0 at stage 0, where k still holds the previous step's (finite) value
       const T a = (st > 0 && tab.nnz[st]) ? T(tab.val[st][0]) : T(0);
-      T* B = c.sh + ((st & 1) ? boff1 : boff0);  // an integer select keeps the pointer in the shared window (LDS / STS)
+      // the two stage buffers alternate over ALL stages of the solve (not per step: with an odd stage count -- euler, bosh3 --
+      // the last stage of a step and the first of the next would otherwise share a buffer with no barrier between the reads of
+      // the one and the writes of the other); an integer select keeps the pointer in the shared window (LDS / STS)
+      T* B = c.sh + (flip ? boff1 : boff0);
+      flip ^= 1;
       // stage input y + a k_{st-1}: kept in registers (it is this thread's part of the row window) and published
       T sP[SEG];
 #pragma unroll
@@ -508,6 +513,123 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
 #pragma unroll
     for (int j = 0; j < SEG; ++j) y[R.o_row + j] = aP[j];
     if (own_m) y[R.o_xr] = am;
+  }
+  __syncthreads();
+  return hit;
+}
+
+// The same register-resident moment ODE for the reference's DEFAULT solver, Dormand-Prince 5 with a constant step
+// (diffrax_utils.py:121-127): six stages with a full tableau, so the increments k_1 .. k_5 of the thread's entries stay in
+// registers as well (5 x 7 doubles; ~170 registers: one CTA per SM, its own kernel instantiation) and the stage loop is
+// unrolled over the compile-time tableau.  (Through the shared-memory solver with six stage buffers the default solver ran
+// at a quarter of the RK4 rate on BASELINE config 4's model.)
+template <typename T, bool UKFC>
+__device__ bool ode_solve_stencil_dopri5(const Ctx<T>& c, const StencilRegs<T>& R, T* y, T t0, T t1, T dt0, int max_steps) {
+  constexpr int SEG = STENCIL_SEG;
+  using TB = Tab<CDK_DOPRI5>;
+  constexpr int S = TB::S;
+  const Lay& L = c.L;
+  const T F = c.p(L.TH)[0];
+  const bool act = R.act, own_m = R.own_m;
+  T yP[SEG], kk[S - 1][SEG];
+  T ym = T(0), kkm[S - 1];
+#pragma unroll
+  for (int j = 0; j < SEG; ++j) yP[j] = y[R.o_row + j];
+  if (own_m) ym = y[R.o_xr];
+#pragma unroll
+  for (int q = 0; q < S - 1; ++q) {
+    kkm[q] = T(0);
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) kk[q][j] = T(0);
+  }
+  const T tol = clip_tol<T>();
+  T tprev = t0, tnext = fmin(t0 + dt0, t1);
+  int nsteps = 0;
+  bool hit = false;
+  const int boff0 = L.YS, boff1 = L.KS;
+  while (tprev < t1) {
+    if (nsteps >= max_steps) {
+      hit = true;
+#pragma unroll
+      for (int j = 0; j < SEG; ++j) yP[j] = T(NAN);
+      ym = T(NAN);
+      break;
+    }
+    const T dt = tnext - tprev;
+    T aP[SEG], am = ym;
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) aP[j] = yP[j];
+#pragma unroll
+    for (int st = 0; st < S; ++st) {
+      T* B = c.sh + ((st & 1) ? boff1 : boff0);
+      T sP[SEG], sm = ym;
+#pragma unroll
+      for (int j = 0; j < SEG; ++j) sP[j] = yP[j];
+#pragma unroll
+      for (int q = 0; q < st; ++q) {
+        if (TB::a(st, q) != 0.0) {
+          const T aq = T(TB::a(st, q));
+#pragma unroll
+          for (int j = 0; j < SEG; ++j) sP[j] = fma(aq, kk[q][j], sP[j]);
+          sm = fma(aq, kkm[q], sm);
+        }
+      }
+      if (act) {
+        T* row = B + R.o_row;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) row[j] = sP[j];
+        if (own_m) B[R.o_xr] = sm;
+      }
+      __syncthreads();
+      if (act) {
+        T xw[SEG + 3], pr[SEG + 3];
+        xw[0] = B[R.o_xl0]; xw[1] = B[R.o_xl1]; xw[SEG + 2] = B[R.o_xh];
+        pr[0] = B[R.o_pl0]; pr[1] = B[R.o_pl1]; pr[SEG + 2] = B[R.o_ph];
+        const T* xs = B + R.o_x;
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+          xw[j + 2] = xs[j];
+          pr[j + 2] = sP[j];
+        }
+        const T ar = B[R.o_xrm1], br = B[R.o_xrp] - B[R.o_xrm2];
+        const T* Pu = B + R.o_up;
+        const T* Pd1 = B + R.o_d1;
+        const T* Pd2 = B + R.o_d2;
+        const T b = T(TB::b(st));
+#pragma unroll
+        for (int j = 0; j < SEG; ++j) {
+          const int q = j + 2;
+          T v = fma(T(-2), pr[q], R.lql[j]);
+          v = fma(ar, Pu[j] - Pd2[j], v);
+          v = fma(br, Pd1[j], v);
+          v = fma(xw[q - 1], pr[q + 1] - pr[q - 2], v);
+          v = fma(xw[q + 1] - xw[q - 2], pr[q - 1], v);
+          const T kv = dt * v;
+          if (st < S - 1) kk[st < S - 1 ? st : 0][j] = kv;
+          if (TB::b(st) != 0.0) aP[j] = fma(b, kv, aP[j]);
+        }
+        if (own_m) {
+          T f = fma(br, ar, F - sm);
+          if (UKFC) f += T(0.5) * ((B[R.o_u0] + B[R.o_u1]) - (B[R.o_u2] + B[R.o_u3]));
+          const T kv = dt * f;
+          if (st < S - 1) kkm[st < S - 1 ? st : 0] = kv;
+          if (TB::b(st) != 0.0) am = fma(b, kv, am);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) yP[j] = aP[j];
+    ym = am;
+    ++nsteps;
+    tprev = tnext;
+    const T cand = tprev + dt0;
+    tnext = cand > t1 - tol ? t1 : cand;
+  }
+  __syncthreads();
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = yP[j];
+    if (own_m) y[R.o_xr] = ym;
   }
   __syncthreads();
   return hit;
@@ -823,8 +945,8 @@ __device__ T condition_on(const Ctx<T>& c, int algo, int num_iter) {
 // REGODE: the launcher has established that the predict step is the Lorenz-96 moment ODE with a chain tableau
 // (ode_solve_stencil, RK state in registers); that instantiation contains no other ODE code, so its register allocation is
 // not burdened by the shared-memory solver and vice versa.
-template <typename T, bool REGODE>
-__global__ void __launch_bounds__(256, 2) generic_filter_kernel(const GArgs<T> g) {
+template <typename T, int REGODE>
+__global__ void __launch_bounds__(256, REGODE == 2 ? 1 : 2) generic_filter_kernel(const GArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Ctx<T> c(g, reinterpret_cast<T*>(smem_raw));
   const Lay& L = c.L;
@@ -859,7 +981,7 @@ __global__ void __launch_bounds__(256, 2) generic_filter_kernel(const GArgs<T> g
   // forecast (CDK_FLAG_PREDICT_ONLY): no updates; Tm holds K + 1 stamps, t_init first
   const bool ponly = (d.reserved[2] & CDK_FLAG_PREDICT_ONLY) != 0;
   StencilRegs<T> sreg;
-  if constexpr (REGODE) stencil_init<T>(c, sreg);
+  if constexpr (REGODE != 0) stencil_init<T>(c, sreg);
   for (int k = 0; k < K; ++k) {
     FOR_T(i, du) uv[i] = U[(long long)k * du + i];
     __syncthreads();
@@ -885,11 +1007,17 @@ __global__ void __launch_bounds__(256, 2) generic_filter_kernel(const GArgs<T> g
     const T t0 = Tm[k];
     const T t1 = (ponly || k + 1 < K) ? Tm[k + 1] : t0 + T(d.dt_final);
     bool hit = false;
-    if constexpr (REGODE) {
+    if constexpr (REGODE == 1) {
       if (algo == ALGO_UKF_FILTER) {
         hit = ode_solve_stencil<T, true>(c, sreg, mu, t0, t1, dt0, d.max_steps);
       } else {
         hit = ode_solve_stencil<T, false>(c, sreg, mu, t0, t1, dt0, d.max_steps);
+      }
+    } else if constexpr (REGODE == 2) {
+      if (algo == ALGO_UKF_FILTER) {
+        hit = ode_solve_stencil_dopri5<T, true>(c, sreg, mu, t0, t1, dt0, d.max_steps);
+      } else {
+        hit = ode_solve_stencil_dopri5<T, false>(c, sreg, mu, t0, t1, dt0, d.max_steps);
       }
     } else if (linear) {
       // pushforward from (I, 0), then m = A m + B u + b, P = A P A^T + Q (cd_linear/inference.py:619-620)
@@ -1115,8 +1243,12 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
   const bool smooth = algo == ALGO_KF_SMOOTH || algo == ALGO_EKF_SMOOTH;
   // Lorenz-96 moment ODE with a chain tableau: RK state in registers (ode_solve_stencil); CDK_GENERIC_REG_ODE=0 disables
   const cdk_desc& dd = g.k.d;
-  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && g.nslots == 1 && stencil_fits(dd.n, threads) &&
+  const bool dopri = dd.solver == CDK_DOPRI5;
+  const bool reg_ode = g.reg_ode && !smooth && dd.drift_id == CDK_DRIFT_LORENZ96 && (g.nslots == 1 || dopri) &&
+                       stencil_fits(dd.n, threads) &&
                        ((algo == ALGO_EKF_FILTER && dd.state_order != CDK_ORDER_ZEROTH) || (algo == ALGO_UKF_FILTER && ukf_closed(dd)));
+  // on the register path Dopri5 keeps its stage increments in registers: the shared-memory layout is the one-slot one
+  if (reg_ode && dopri) g.nslots = 1;
   g.lay = Lay(g.k.d, algo, g.nslots, reg_ode);
   const Lay& L = g.lay;
   const size_t smem = (size_t)L.total * sizeof(T);
@@ -1124,7 +1256,8 @@ int launch_generic(int algo, const KArgs<T>& a, cudaStream_t s) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   if (smem > (size_t)max_optin) return CDK_E_SIZE;
-  auto kern = smooth ? generic_smooth_kernel<T> : (reg_ode ? generic_filter_kernel<T, true> : generic_filter_kernel<T, false>);
+  auto kern = smooth ? generic_smooth_kernel<T>
+                     : (reg_ode ? (dopri ? generic_filter_kernel<T, 2> : generic_filter_kernel<T, 1>) : generic_filter_kernel<T, 0>);
   if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return check_launch("cudaFuncSetAttribute(generic)");

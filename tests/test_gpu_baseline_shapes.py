@@ -108,6 +108,29 @@ def test_c4_ukf_l96_n40_m20_vs_oracle(solver, dt0, sigma_points, monkeypatch):
     check_moments(f, r, f"c4_ukf_n40_{solver_tag}")
 
 
+@pytest.mark.parametrize("algo", ["ekf", "ukf"])
+@pytest.mark.parametrize("solver,dt0", [("euler", 0.004), ("heun", 0.005), ("midpoint", 0.005), ("bosh3", 0.006), ("dopri5", 0.01)])
+def test_l96_register_ode_every_solver_vs_oracle(algo, solver, dt0):
+    """The register-resident Lorenz-96 moment ODE at n = 40 for every tableau: odd stage counts (euler 1, bosh3 3: the stage
+    buffers alternate over all stages of a solve), b_1 = 0 (midpoint) and the six-stage Dopri5 variant (stage increments in
+    registers), EKF (compact two-CTA layout) and closed-form UKF."""
+    cd = api()
+    g, po, t, y = _l96_case(N=4, K=25, seed=60 + len(solver))
+    p = nonlinear_params_api(g)
+    st = {"solver": solver, "dt0": dt0}
+    if algo == "ekf":
+        f = cd.cdnlgssm_filter(p, y, t[..., None], cd.EKFHyperParams(diffeqsolve_settings=st))
+        r = o.extended_kalman_filter(po, y, t, settings=o.SolverSettings(solver, dt0))
+    else:
+        f = cd.cdnlgssm_filter(p, y, t[..., None], cd.UKFHyperParams(diffeqsolve_settings=st))
+        r = o.unscented_kalman_filter(po, y, t, settings=o.SolverSettings(solver, dt0))
+    assert np.isfinite(r["marginal_loglik"]).all()
+    e = max_rel_err(f.marginal_loglik, r["marginal_loglik"])
+    record(f"l96_reg_{algo}_{solver}:marginal_loglik", e)
+    assert e < TOL
+    check_moments(f, r, f"l96_reg_{algo}_{solver}")
+
+
 @pytest.mark.parametrize("solver", ["euler", "heun"])
 def test_c5_enkf_l96_e1024_cluster4_vs_oracle(solver):
     """BASELINE config 5 shape: 1,024 members = a cluster of 4 CTAs x 256 members (the launcher's own choice for E = 1,024,
