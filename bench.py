@@ -49,7 +49,7 @@ CFG = dict(N=65536, K=1000, n=3, m=1, mean_gap=0.01, dt0=0.0025, solver="rk4", s
 FLOP_SUBSTEP_SURVEY, FLOP_UPDATE_SURVEY = 496.0, 107.0
 FLOP_SUBSTEP_EXEC, FLOP_UPDATE_EXEC = 324.0, 60.0
 BYTES_PER_OBS_STEP = 16 + 192  # y,t in (16 B) + filtered/predicted mean+cov out (24 doubles)
-TRAFFIC_NCU_BYTES = 14.79e9  # dram read 1.72 GB + write 13.07 GB: profiles/r02_ekf_small_lw_8warp_ctas_N65536.txt
+TRAFFIC_NCU_BYTES = 15.15e9  # dram read 1.95 GB + write 13.19 GB: profiles/r02_ekf_small_lw_time_sliced_N65536.txt
 
 
 def parse():
