@@ -432,8 +432,8 @@ __device__ __forceinline__ void stage_row(T* lane_block, const T (&v)[LEN]) {
 // Warps per CTA: 7 (two CTAs per SM, <= 128 registers) or 14 (ONE CTA per SM, <= 144 registers: the drift parameters and
 // L Qc L^T then live in registers instead of being re-read from shared memory every substep).  Either way 65,536
 // trajectories are one wave of 2,048 warps over 148 SMs.  CDK_LW_WPC selects.
-template <typename T, class Drift, int NY, int SOLVER, int WPC>
-__global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
+template <typename T, class Drift, int NY, int SOLVER, int WPC, bool SLICED = false>
+__global__ void __launch_bounds__(SLICED ? 32 * 12 : 32 * WPC, WPC == 7 ? 2 : 1)
     ekf_small_lw(const KArgs<T> a, const __grid_constant__ V5Maps maps, const int warp_bytes, const int use_token, const int G,
                  const int segk) {
   constexpr int NX = Drift::NX;
@@ -460,13 +460,16 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   // as the sub-partitions with four; with W = 12 (or 8) resident warps every sub-partition carries three (two) at any time
   // and the 14 groups of an SM take 14 / 12 passes of a balanced SM instead of 4 / 3 (measured balanced rates:
   // profiles/r02_c3_outputs_probe.jsonl).  Without slicing G = W, one segment: warp w keeps group w for the whole kernel.
+  // (SLICED is its own instantiation with at most 12 resident warps and 170 registers: the bookkeeping that stays live
+  // across the step loop costs the 128-register 14-warp kernel spills inside the loop.)
   const int W = blockDim.x >> 5;
   const long long ngroups = (N + 31) >> 5;
-  const long long gfirst = (long long)blockIdx.x * G;
-  const int Gc = (int)(ngroups - gfirst < (long long)G ? ngroups - gfirst : (long long)G);  // groups of this CTA
-  const int nseg = (K + segk - 1) / segk;
+  const int Gq = SLICED ? G : W;
+  const long long gfirst = (long long)blockIdx.x * Gq;
+  const int Gc = (int)(ngroups - gfirst < (long long)Gq ? ngroups - gfirst : (long long)Gq);  // groups of this CTA
+  const int nseg = SLICED ? (K + segk - 1) / segk : 1;
   const int Wr = W < Gc ? W : Gc;  // items per round
-  const int nitems = Gc * nseg;
+  const int nitems = SLICED ? Gc * nseg : 1;
   long long traj0 = (gfirst + warp) * 32;  // first item (the only one without slicing); reset per item below
   // Optional FP64-pipe semaphore (CDK_LW_TOKEN = permits, default off): at most `permits` warps of an SM sub-partition are
   // inside the RK substep loop at a time (FIFO tickets), the others update / stage / store.  Built to break the convoy
@@ -477,7 +480,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   __shared__ unsigned lw_token[4][2];  // [sub-partition][next ticket, tenures completed]
   if (threadIdx.x < 8) (&lw_token[0][0])[threadIdx.x] = 0u;
   __syncthreads();
-  if (nseg == 1 && warp >= Gc) return;  // whole warp out of range (without slicing nobody ever waits for it)
+  if (!SLICED && warp >= Gc) return;  // whole warp out of range (without slicing nobody ever waits for it)
   unsigned hw_warp;
   asm volatile("mov.u32 %0, %warpid;" : "=r"(hw_warp));
   volatile unsigned* const tok = &lw_token[hw_warp & 3][0];
@@ -740,10 +743,10 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
   };
 
   LWGroup<T, NX>* const groups = reinterpret_cast<LWGroup<T, NX>*>(smem_raw + (size_t)W * warp_bytes);  // nseg > 1 only
-  for (int base = 0; base < nitems; base += Wr) {
-    const int item = base + warp;
-    if (warp < Wr && item < nitems) {
-      const int seg = item / Gc, g = item - seg * Gc;
+  for (int base = 0; base < nitems; base += SLICED ? Wr : 1) {
+    const int item = SLICED ? base + warp : warp;
+    if (!SLICED || (warp < Wr && item < nitems)) {  // (!SLICED: out-of-range warps have returned above)
+      const int seg = SLICED ? item / Gc : 0, g = SLICED ? item - seg * Gc : warp;
       traj0 = (gfirst + g) * 32;
       traj = traj0 + lane;
       live = traj < N;
@@ -754,7 +757,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
       kb = seg * segk;
       ke = kb + segk < K ? kb + segk : K;
       kpre = ke + 1 < KT ? ke + 1 : KT;  // step ke - 1 reads the stamp of step ke
-      if (use_tma && base > 0) {  // this warp's staging rows may still be read by the stores of its previous item
+      if (SLICED && use_tma && base > 0) {  // this warp's staging rows may still be read by the stores of its previous item
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
       }
@@ -815,7 +818,7 @@ __global__ void __launch_bounds__(32 * WPC, WPC == 7 ? 2 : 1)
         if (a.out[CDK_OUT_STATUS]) static_cast<int*>(a.out[CDK_OUT_STATUS])[traj] = st;
       }
     }
-    if (nseg > 1) __syncthreads();
+    if (SLICED) __syncthreads();
   }
   if (use_tma && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (trace && lane == 0) {
@@ -1781,7 +1784,7 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   if (!forced && slice_env != 0 && wpc == 14 && !par_batched && !ponly_l && a.d.K >= 200 && (a.d.K & 1) == 0) {
     const int sms = sms_e && atoi(sms_e) > 0 ? atoi(sms_e) : lw_num_sms();
     for (int wres : {slice_env > 0 ? slice_env : (nout >= 3 ? 8 : 12), 8}) {
-      if (wres < 1 || wres > 14 || nwarps <= (long long)sms * wres) continue;
+      if (wres < 1 || wres > 12 || nwarps <= (long long)sms * wres) continue;
       const long long Gs = (nwarps + sms - 1) / sms;
       const size_t need = (size_t)warp_bytes * wres + (size_t)Gs * sizeof(LWGroup<T, NX>);
       if (Gs < wres || need > 227 * 1024) continue;
@@ -1821,7 +1824,8 @@ int launch_one(const KArgs<T>& a, cudaStream_t s) {
   if (wblocks > 2147483647LL) return CDK_E_SIZE;
   V5Maps maps;
   make_maps<T>(a, NX, 32, maps);
-  auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7> : ekf_small_lw<T, Drift, NY, SOLVER, 14>;
+  auto kw = wpc == 7 ? ekf_small_lw<T, Drift, NY, SOLVER, 7>
+                     : (sliced ? ekf_small_lw<T, Drift, NY, SOLVER, 14, true> : ekf_small_lw<T, Drift, NY, SOLVER, 14>);
   {
     const size_t cap = (size_t)warp_bytes * wpc > smw ? (size_t)warp_bytes * wpc : smw;
     if (cap > 48 * 1024 && cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap) != cudaSuccess)
