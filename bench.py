@@ -588,7 +588,8 @@ def run_ours(args):
             "peak_3_register_operands_note": "cdk_fma3_probe_f64, measured in this run: a DFMA whose three operands are "
                                              "distinct vector registers issues every 3 cycles per SM sub-partition on "
                                              "B200, not 2 (register-file bandwidth); most of the 143 DFMAs among the kernel's 181 FP64 "
-                                             "instructions per substep are such DFMAs",
+                                             "instructions per substep are such DFMAs; frac_of_3_register_peak divides the ALGORITHMIC rate by it and can exceed 1 "
+                                             "(the kernel executes fewer flops than the survey counts: see achieved_executed)",
             "frac_of_3_register_peak": ach_survey / fp64_peak3 if fp64_peak3 else None,
             "flop_model_executed": "324*sum_q + 60*N*K (symmetric P, sparse Lorenz-63 Jacobian, dt folded into RK weights)",
             "kernel_ms": kernel_ms,
