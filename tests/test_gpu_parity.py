@@ -200,6 +200,24 @@ def test_ekf_l63_time_sliced_launch_is_bit_identical(wres, sms, N, K, dtype, fie
         assert max_rel_err(f1.marginal_loglik[:64], r["marginal_loglik"]) < TOL
 
 
+def test_ekf_l63_default_launch_slices_large_batches_identically(monkeypatch):
+    """N = 40,007 x K = 200 is more than one balanced wave of a B200 (1,251 groups > 148 SMs x 8 warps), so the DEFAULT launch
+    is the time-sliced one on the real SM count; it must equal the unsliced launch bit for bit (all four moment arrays)."""
+    cd = api()
+    N, K = 40007, 200
+    t, y = c3_problem(N, K, seed=5)
+    g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]),
+             L=np.eye(3), Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))
+    p = nonlinear_params_api(g)
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    f1 = cd.cdnlgssm_filter(p, y, t[..., None], hp)
+    monkeypatch.setenv("CDK_LW_SLICE", "0")
+    f0 = cd.cdnlgssm_filter(p, y, t[..., None], hp)
+    assert np.isfinite(np.asarray(f1.marginal_loglik)).all()
+    for fld in ("marginal_loglik",) + tuple(FIELDS):
+        assert np.array_equal(np.asarray(getattr(f0, fld)), np.asarray(getattr(f1, fld))), fld
+
+
 @pytest.mark.parametrize("N,K", [(1, 1), (3, 7), (225, 33), (500, 64)])
 def test_ekf_l63_fast_path_ragged_shapes(N, K):
     """Odd / tiny K and N around the 224-slot CTA size: the TMA store path needs even K, the cooperative flush covers
