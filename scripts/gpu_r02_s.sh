@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -x -q -m gpu -k "default_launch_slices" 2>&1 | tail -3
+timeout 300 python scripts/c3_eks_probe.py
+for w in 7 8 12; do CDK_LW_WARPS=$w timeout 300 python scripts/c3_eks_probe.py; done
