@@ -1693,14 +1693,8 @@ int lw_warps_per_cta(long long N, int max_warps, int ctas_per_sm) {
     const char* e = getenv("CDK_LW_WARPS");
     return e ? atoi(e) : 0;
   }();
-  static const int num_sms = []() {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1)
-      n = 148;
-    return n;
-  }();
   if (forced >= 1) return forced < max_warps ? forced : max_warps;
-  const long long nwarps = (N + 31) / 32, slots = (long long)num_sms * ctas_per_sm;
+  const long long nwarps = (N + 31) / 32, slots = (long long)lw_num_sms() * ctas_per_sm;
   const long long w = (nwarps + slots - 1) / slots;
   return (int)(w < 1 ? 1 : (w > max_warps ? max_warps : w));
 }

@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python scripts/c3_eks_probe.py
-for w in 7 8 12; do CDK_LW_WARPS=$w timeout 300 python scripts/c3_eks_probe.py; done
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
