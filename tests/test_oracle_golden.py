@@ -131,3 +131,26 @@ def test_c_oracle_matches_numpy_oracle():
         assert max_rel_err(c["marginal_loglik"], r["marginal_loglik"]) < 1e-12
         for fld, core in (("filtered_means", 1), ("filtered_covariances", 2), ("predicted_means", 1), ("predicted_covariances", 2)):
             assert gate_err(c[fld], r[fld]) < 1e-10 and moment_norm_err(c[fld], r[fld], core) < 1e-11, (solver, fld)
+
+
+def test_normal_deviate_stream_is_pinned():
+    """Known-answer pins of the counter-based deviate stream (Philox4x32-10 + the float32 Box-Muller made of correctly
+    rounded operations only, oracle/cd_oracle.py:box_muller_f32): exact bit patterns, so a change of the stream -- which the
+    GPU must mirror bit for bit (tests/test_gpu_parity.py::test_normal_deviates_bit_identical_to_oracle) -- cannot pass
+    silently; plus the edge words (radius word 0 and 2^32 - 1, all quadrants) and the first two moments."""
+    i = np.arange(6, dtype=np.uint32)
+    z = np.stack(o.philox_normal_quad(i, np.uint32(77), np.uint32(5), np.uint32((2 << 28) | (3 << 8)) + i, 0x1234567887654321), axis=1)
+    want = np.array([[1053230178, 1029320931, 3206743056, 1058688914], [1067050446, 1060128608, 1068043539, 1066804496],
+                     [3211958930, 1055106219, 1076386205, 3211180195], [1065972825, 3208228336, 1059546727, 1065486141],
+                     [3214596317, 3208984820, 1039668577, 1048666161], [1063250250, 3192822815, 3209181155, 1028190270]], np.uint32)
+    assert z.dtype == np.float64 and np.array_equal(z.astype(np.float32).astype(np.float64), z)  # exactly fp32-representable
+    assert np.array_equal(z.astype(np.float32).view(np.uint32), want)
+    ra = np.array([0, 1, 2**32 - 1, 2**31, 123456789], np.uint32)
+    rb = np.array([0, 2**32 - 1, 2**30, 2**31, 987654321], np.uint32)
+    a, b = o.box_muller_f32(ra, rb)
+    assert np.array_equal(a.view(np.uint32), np.array([1087926343, 1087581517, 0, 3214325087, 1051416574], np.uint32))
+    assert np.array_equal(b.view(np.uint32), np.array([895848794, 3042966698, 2147483648, 3021986233, 1076439692], np.uint32))
+    rng = np.random.default_rng(0)
+    w = rng.integers(0, 2**32, size=(2, 400_000), dtype=np.uint64).astype(np.uint32)
+    zz = np.concatenate(o.box_muller_f32(w[0], w[1])).astype(np.float64)
+    assert abs(zz.mean()) < 4e-3 and abs(zz.var() - 1.0) < 4e-3 and abs((zz**4).mean() - 3.0) < 3e-2 and np.abs(zz).max() < 6.77
