@@ -345,6 +345,28 @@ def test_fp32_enkf_bound():
         assert e < 2e-3, (fld, e)
 
 
+def test_fp32_enkf_l96_light_mapping(monkeypatch):
+    """cdk_enkf_filter_f32 on Lorenz-96 n = 40 (the fp32 instantiation of the two-threads-per-member mapping): against the fp32
+    register mapping to fp32 rounding (separate template instantiations may contract a * b + c differently in fp32), and, over
+    a short horizon (K = 6: chaos amplifies fp32 rounding by e^{lambda t}), against the fp64 oracle."""
+    cd = api()
+    g, po, t, y = _l96_case(N=2, K=6, seed=52)
+    y32, t32 = _f32(y, t)
+    hp = cd.EnKFHyperParams(N_particles=512, key=5, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
+    monkeypatch.setenv("CDK_ENKF_CLUSTER", "2")
+    monkeypatch.setenv("CDK_ENKF_LIGHT", "0")
+    f0 = cd.cdnlgssm_filter(nonlinear_params_api(g), y32, t32[..., None], hp)
+    monkeypatch.setenv("CDK_ENKF_LIGHT", "1")
+    f1 = cd.cdnlgssm_filter(nonlinear_params_api(g), y32, t32[..., None], hp)
+    assert f1.filtered_means.dtype == np.float32
+    for fld in FIELDS:
+        assert scaled_err(getattr(f1, fld), np.asarray(getattr(f0, fld), np.float64)) < 2e-4, fld
+    r = o.ensemble_kalman_filter(po, _as64(y32), _as64(t32), E=512, seed=5, settings=o.SolverSettings("euler", float(np.float32(0.005))))
+    assert max_rel_err(f1.marginal_loglik, r["marginal_loglik"]) < 5e-3
+    for fld in FIELDS:
+        assert scaled_err(getattr(f1, fld), r[fld]) < 5e-3, fld
+
+
 def test_fp32_eks_bound():
     """cdk_ekf_smooth_f32 (register kernel, Lorenz-63), K = 100.  Bound: 5e-3 scaled on the smoothed moments."""
     cd = api()
