@@ -322,6 +322,28 @@ def test_fp32_ukf_bound():
         assert e < 5e-3, (fld, e)
 
 
+@pytest.mark.parametrize("algo", ["ekf", "ukf"])
+@pytest.mark.parametrize("solver,dt0", [("rk4", 0.005), ("dopri5", 0.01)])
+def test_fp32_l96_register_ode_bound(algo, solver, dt0):
+    """The fp32 instantiations of the register-resident Lorenz-96 moment ODE (chain tableau and Dopri5) at n = 40, short
+    horizon (K = 8).  Bound: 2e-3 relative on the log-likelihood, 5e-3 scaled on the moments."""
+    cd = api()
+    g, po, t, y = _l96_case(N=3, K=8, seed=71)
+    y32, t32 = _f32(y, t)
+    st = {"solver": solver, "dt0": dt0}
+    so = o.SolverSettings(solver, float(np.float32(dt0)))
+    if algo == "ekf":
+        f = cd.cdnlgssm_filter(nonlinear_params_api(g), y32, t32[..., None], cd.EKFHyperParams(diffeqsolve_settings=st))
+        r = o.extended_kalman_filter(po, _as64(y32), _as64(t32), settings=so)
+    else:
+        f = cd.cdnlgssm_filter(nonlinear_params_api(g), y32, t32[..., None], cd.UKFHyperParams(diffeqsolve_settings=st))
+        r = o.unscented_kalman_filter(po, _as64(y32), _as64(t32), settings=so)
+    assert f.filtered_means.dtype == np.float32
+    assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < 2e-3
+    for fld in FIELDS:
+        assert scaled_err(getattr(f, fld), r[fld]) < 5e-3, fld
+
+
 def test_fp32_enkf_bound():
     """cdk_enkf_filter_f32: linear drift (no chaotic amplification of the fp32 normal deviates), E = 256, K = 40, same
     Philox counters as the fp64 oracle.  Bound: 1e-3 relative on the log-likelihood, 2e-3 scaled on the moments."""
