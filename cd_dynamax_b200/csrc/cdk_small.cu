@@ -810,7 +810,9 @@ __global__ void __launch_bounds__(SLICED ? 32 * 12 : 32 * WPC, WPC == 7 ? 2 : 1)
         int st = status;
         if (lean) {
           // sum_k log S_k = esum log 2 + log(sprod); the -log(2 pi)/2 of every step
-          llf -= T(0.5) * (T(esum) * T(0.69314718055994530942) + log(sprod)) + T(K) * half_log_2pi<T>();
+          // (explicit fma / single operations: the sliced and the plain instantiation must round identically)
+          const T lsum = fma(T(esum), T(0.69314718055994530942), log(sprod));
+          llf = llf - fma(T(0.5), lsum, T(K) * half_log_2pi<T>());
           if (sbad) llf = T(NAN);
         }
         if (st == 0 && !isfinite(llf)) st = 1;

@@ -17,7 +17,7 @@ import numpy as np
 import pytest
 
 from oracle import cd_oracle as o
-from tests.helpers import max_rel_err, moment_err, record, scaled_err
+from tests.helpers import gate_err, max_rel_err, moment_err, record, scaled_err
 from tests.test_gpu_parity import FIELDS, TOL, api, c3_problem, check_moments, linear_params_api, nonlinear_params_api
 
 pytestmark = pytest.mark.gpu
@@ -52,6 +52,39 @@ def test_c3_ekf_l63_k1000_multi_cta_vs_c_oracle():
     assert max_rel_err(f0.marginal_loglik, r["marginal_loglik"]) < TOL
     fc = cd.cdnlgssm_filter(nonlinear_params_api(L63), y[:300], t[:300, :, None], hp, output_fields=["marginal_loglik"])
     assert max_rel_err(fc.marginal_loglik[:, -1], r["marginal_loglik"][:300]) < TOL
+
+
+def test_c3_full_size_sharding_invariance_and_oracle_sample():
+    """BASELINE config 3 at FULL size (N = 65,536, K = 1,000; the time-sliced launch) through size-independent properties:
+    the full batch equals its eight 8,192-trajectory shards bit for bit (what trajectory sharding over 8 GPUs relies on: a
+    trajectory's arithmetic does not depend on the batch it travels in, nor on the launch geometry), a permuted batch gives the
+    permuted result, and a sample of trajectories matches the C oracle."""
+    import torch
+    cd = api()
+    N, K = 65536, 1000
+    t, y = c3_problem(N, K, seed=3)
+    dev = torch.device("cuda", 0)
+    td, yd = torch.as_tensor(t, device=dev), torch.as_tensor(y, device=dev)
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    p = nonlinear_params_api(L63)
+    full = cd.cdnlgssm_filter(p, yd, td[..., None], hp, output_fields=["filtered_means", "predicted_covariances"])
+    assert bool(torch.isfinite(full.marginal_loglik).all())
+    for sh in range(8):
+        lo, hi = sh * 8192, (sh + 1) * 8192
+        part = cd.cdnlgssm_filter(p, yd[lo:hi], td[lo:hi, :, None], hp, output_fields=["filtered_means", "predicted_covariances"])
+        assert torch.equal(part.marginal_loglik, full.marginal_loglik[lo:hi]), sh
+        assert torch.equal(part.filtered_means, full.filtered_means[lo:hi]), sh
+        assert torch.equal(part.predicted_covariances, full.predicted_covariances[lo:hi]), sh
+    perm = torch.randperm(N, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    pf = cd.cdnlgssm_filter(p, yd[perm].contiguous(), td[perm].contiguous()[..., None], hp, output_fields=["filtered_means"])
+    assert torch.equal(pf.marginal_loglik, full.marginal_loglik[perm])
+    assert torch.equal(pf.filtered_means, full.filtered_means[perm])
+    sel = np.r_[0:96, 30000:30096, N - 64:N]
+    r = _c_oracle_ekf(y[sel], t[sel])
+    e = max_rel_err(full.marginal_loglik[sel].cpu().numpy(), r["marginal_loglik"])
+    record("c3_full_size_sample:marginal_loglik", e)
+    assert e < TOL
+    assert gate_err(full.filtered_means[sel].cpu().numpy(), r["filtered_means"]) < TOL
 
 
 @pytest.mark.parametrize("N", [4736, 4737, 8192, 16384, 20000, 41000])
