@@ -376,6 +376,7 @@ struct StencilRegs {
   int act;                       // owns a segment
   int own_m;                     // ... and mean entry r
   int o_x, o_row;                // element offsets inside a stage buffer: x_{c0}, P_{r,c0}
+  int o_colT;                    // P_{c0,r} (the transposed entries follow with stride ld)
   int o_up, o_d1, o_d2;          // P_{r+1,c0}, P_{r-1,c0}, P_{r-2,c0}
   int o_xl0, o_xl1, o_xh;        // x_{c0-2}, x_{c0-1}, x_{c0+SEG} (cyclic)
   int o_pl0, o_pl1, o_ph;        // P_{r,c0-2}, P_{r,c0-1}, P_{r,c0+SEG} (cyclic)
@@ -400,6 +401,7 @@ __device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R)
   const int rp = wrap(r + 1), rm1 = wrap(r - 1), rm2 = wrap(r - 2);
   R.o_x = c0;
   R.o_row = poff + r * ld + c0;
+  R.o_colT = poff + c0 * ld + r;
   R.o_up = poff + rp * ld + c0;
   R.o_d1 = poff + rm1 * ld + c0;
   R.o_d2 = poff + rm2 * ld + c0;
@@ -409,6 +411,25 @@ __device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R)
   R.o_u0 = poff + rp * ld + rm1; R.o_u1 = poff + rm1 * ld + rp; R.o_u2 = poff + rm2 * ld + rm1; R.o_u3 = poff + rm1 * ld + rm2;
 #pragma unroll
   for (int j = 0; j < SEG; ++j) R.lql[j] = lql[r * ld + c0 + j];
+}
+
+// The row-segment right-hand side reads P_{c',r} as P_{r,c'}: it integrates dP = J P + P J^T, whose ANTISYMMETRIC part obeys the
+// same (chaotic, unstable) dynamics as the symmetric one.  The EKF symmetrises P in every update, so its covariance enters a
+// gap exactly symmetric; the UKF never does (inference_ukf.py:202), and the rounding-level asymmetry of its update then
+// doubles every few steps (1e-16 -> O(1) in ~240 steps of BASELINE config 4, found by the full-size test).  The reference's
+// unscented right-hand side factors chol of the SYMMETRISED covariance (jnp.linalg.cholesky) and returns a symmetric
+// derivative: the symmetric part evolves from sym(P) and the antisymmetric part is carried along unchanged.  UKFC does exactly
+// that: integrate S = sym(P), then add the old antisymmetric part back.
+template <typename T, bool UKFC>
+__device__ __forceinline__ T stencil_load_entry(const T* y, const StencilRegs<T>& R, int j, int ld) {
+  const T prc = y[R.o_row + j];
+  return UKFC ? T(0.5) * (prc + y[R.o_colT + j * ld]) : prc;
+}
+template <typename T, bool UKFC>
+__device__ __forceinline__ T stencil_antisym(const T* y, const StencilRegs<T>& R, int j, int ld) {
+  if (!UKFC) return T(0);
+  const T prc = y[R.o_row + j];
+  return prc - T(0.5) * (prc + y[R.o_colT + j * ld]);
 }
 
 // Integrate (m, P) (shared memory, [MU | P] layout of `y`) from t0 to t1.  UKFC adds the unscented second-order mean term.
@@ -424,7 +445,7 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
   T am = T(0), km = T(0), ym = T(0);
 #pragma unroll
   for (int j = 0; j < SEG; ++j) {
-    aP[j] = y[R.o_row + j];
+    aP[j] = stencil_load_entry<T, UKFC>(y, R, j, c.L.ldn);
     kP[j] = T(0);
   }
   if (own_m) am = y[R.o_xr];
@@ -508,10 +529,13 @@ __device__ bool ode_solve_stencil(const Ctx<T>& c, const StencilRegs<T>& R, T* y
     const T cand = tprev + dt0;
     tnext = cand > t1 - tol ? t1 : cand;
   }
-  __syncthreads();  // the last stage's readers are done before the state block is rewritten
+  T a0[SEG];
+#pragma unroll
+  for (int j = 0; j < SEG; ++j) a0[j] = stencil_antisym<T, UKFC>(y, R, j, c.L.ldn);
+  __syncthreads();  // the last stage's readers and the readers of the old state are done before the state block is rewritten
   if (act) {
 #pragma unroll
-    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = aP[j];
+    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = UKFC ? aP[j] + a0[j] : aP[j];
     if (own_m) y[R.o_xr] = am;
   }
   __syncthreads();
@@ -534,7 +558,7 @@ __device__ bool ode_solve_stencil_dopri5(const Ctx<T>& c, const StencilRegs<T>& 
   T yP[SEG], kk[S - 1][SEG];
   T ym = T(0), kkm[S - 1];
 #pragma unroll
-  for (int j = 0; j < SEG; ++j) yP[j] = y[R.o_row + j];
+  for (int j = 0; j < SEG; ++j) yP[j] = stencil_load_entry<T, UKFC>(y, R, j, c.L.ldn);
   if (own_m) ym = y[R.o_xr];
 #pragma unroll
   for (int q = 0; q < S - 1; ++q) {
@@ -625,10 +649,13 @@ __device__ bool ode_solve_stencil_dopri5(const Ctx<T>& c, const StencilRegs<T>& 
     const T cand = tprev + dt0;
     tnext = cand > t1 - tol ? t1 : cand;
   }
+  T a0[SEG];
+#pragma unroll
+  for (int j = 0; j < SEG; ++j) a0[j] = stencil_antisym<T, UKFC>(y, R, j, c.L.ldn);
   __syncthreads();
   if (act) {
 #pragma unroll
-    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = yP[j];
+    for (int j = 0; j < SEG; ++j) y[R.o_row + j] = UKFC ? yP[j] + a0[j] : yP[j];
     if (own_m) y[R.o_xr] = ym;
   }
   __syncthreads();

@@ -296,6 +296,96 @@ def test_ukf_and_enkf_wide_emission_vs_oracle():
         assert scaled_err(getattr(fe, fld), re[fld]) < 1e-8, fld
 
 
+def test_c4_full_size_sharding_invariance_and_oracle_sample():
+    """BASELINE config 4 at FULL size (UKF, Lorenz-96 n = 40, m = 20, N = 8,192, K = 500; log-likelihood + filtered means --
+    all four moment arrays would be 105 GB): shards reproduce the batch bit for bit; three trajectories against the NumPy
+    oracle's literal sigma points over all 500 steps (t = 10, ~17 Lyapunov times of the unobserved system: the filter's
+    contraction keeps the two roundings together)."""
+    import torch
+    cd = api()
+    N, K = 8192, 500
+    g, po, t, y = _l96_case(N=N, K=K, seed=4)
+    dev = torch.device("cuda", 0)
+    td, yd = torch.as_tensor(t, device=dev), torch.as_tensor(y, device=dev)
+    hp = cd.UKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.005})
+    p = nonlinear_params_api(g)
+    full = cd.cdnlgssm_filter(p, yd, td[..., None], hp, output_fields=["filtered_means", "marginal_loglik"])  # cumulative ll
+    assert bool(torch.isfinite(full.marginal_loglik).all()) and bool(torch.isfinite(full.filtered_means).all())
+    for lo, hi in ((0, 1000), (5000, 8192)):
+        part = cd.cdnlgssm_filter(p, yd[lo:hi], td[lo:hi, :, None], hp, output_fields=["filtered_means", "marginal_loglik"])
+        assert torch.equal(part.marginal_loglik, full.marginal_loglik[lo:hi])
+        assert torch.equal(part.filtered_means, full.filtered_means[lo:hi])
+    sel = np.array([0, 4097, N - 1])
+    r = o.unscented_kalman_filter(po, y[sel], t[sel], settings=o.SolverSettings("rk4", 0.005))
+    llc = full.marginal_loglik[sel].cpu().numpy()
+    fm = full.filtered_means[sel].cpu().numpy()
+    # the first 100 steps at the parity gate; the whole chaotic run (two roundings of the same algorithm drift apart at the
+    # system's Lyapunov rate between the corrections of the filter) at 1e-6 of the log-likelihood / 1e-3 of the mean scale
+    k0 = 100
+    ref_cum = r["marginal_loglik_cumulative"]
+    e100 = scaled_err(fm[:, :k0], r["filtered_means"][:, :k0])
+    eall = scaled_err(fm, r["filtered_means"])
+    ell = max_rel_err(llc[:, -1], r["marginal_loglik"])
+    record("c4_full_size_sample:filtered_means_first100:scaled", e100)
+    record("c4_full_size_sample:filtered_means_all500:scaled", eall)
+    record("c4_full_size_sample:marginal_loglik_all500", ell)
+    assert e100 < 1e-8 and eall < 1e-3 and ell < 1e-6, (e100, eall, ell)
+    assert max_rel_err(llc[:, k0 - 1], ref_cum[:, k0 - 1]) < TOL
+
+
+def test_c5_full_size_subset_invariance_and_oracle_sample():
+    """BASELINE config 5 at FULL size (EnKF, n = 40, m = 20, E = 1,024, N = 1,024, K = 500): a subset of the batch reproduces
+    its rows bit for bit (the Philox counters are per trajectory index); the first 60 steps of two trajectories against the
+    oracle on the shared stream (the filter is causal)."""
+    import torch
+    cd = api()
+    N, K = 1024, 500
+    g, po, t, y = _l96_case(N=N, K=K, seed=5)
+    dev = torch.device("cuda", 0)
+    td, yd = torch.as_tensor(t, device=dev), torch.as_tensor(y, device=dev)
+    hp = cd.EnKFHyperParams(N_particles=1024, key=1234, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
+    p = nonlinear_params_api(g)
+    full = cd.cdnlgssm_filter(p, yd, td[..., None], hp, output_fields=["filtered_means"])
+    assert bool(torch.isfinite(full.marginal_loglik).all())
+    part = cd.cdnlgssm_filter(p, yd[:96], td[:96, :, None], hp, output_fields=["filtered_means"])
+    assert torch.equal(part.marginal_loglik, full.marginal_loglik[:96])
+    assert torch.equal(part.filtered_means, full.filtered_means[:96])
+    Ks = 60
+    r = o.ensemble_kalman_filter(po, y[:2, :Ks], t[:2, :Ks], E=1024, seed=1234, settings=o.SolverSettings("euler", 0.005))
+    em = scaled_err(full.filtered_means[:2, :Ks].cpu().numpy(), r["filtered_means"])
+    record("c5_full_size_sample:filtered_means:scaled", em)
+    assert em < 1e-8, em
+
+
+def test_c2_full_size_sharding_invariance_and_oracle_sample():
+    """BASELINE config 2 at FULL size (KF n = 16, m = 4, N = 262,144, K = 500, log-likelihood only: 5 GB of inputs resident):
+    a slice of the batch reproduces its rows bit for bit; 64 trajectories against the C oracle."""
+    import torch
+    from oracle import cpu_baseline as cb
+    cd = api()
+    N, K = 262144, 500
+    g, _, t, y = _c2_case(N, K, seed=22)
+    dev = torch.device("cuda", 0)
+    td, yd = torch.as_tensor(t, device=dev), torch.as_tensor(y, device=dev)
+    from cd_dynamax_b200 import _lib as L
+    from cd_dynamax_b200.continuous_discrete_linear_gaussian_ssm.inference import _filter_device
+    hp = cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
+    p = linear_params_api(g)
+    # the reference's linear filter has no output_fields: the moments of this batch would be 570 GB, so the test asks the
+    # shim's device-level driver for the log-likelihoods only (what marginal_log_prob does)
+    ll = lambda yy, tt: _filter_device(p, yy, tt[..., None], hp, None, (L.OUT_LL,))[0][L.OUT_LL]
+    full = ll(yd, td)
+    assert bool(torch.isfinite(full).all())
+    lo, hi = 100000, 108192
+    assert torch.equal(ll(yd[lo:hi], td[lo:hi]), full[lo:hi])
+    sel = np.r_[0:32, N - 32:N]
+    r = cb.filter_c("kf", y[sel], t[sel], g["m0"], g["P0"], g["F"], g["L"], g["Qc"], g["H"], g["d"], g["R"], bias=g["b"],
+                    solver="rk4", dt0=0.01)
+    e = max_rel_err(full[sel].cpu().numpy(), r["marginal_loglik"])
+    record("c2_full_size_sample:marginal_loglik", e)
+    assert e < TOL
+
+
 # ---- fp32 entry points: one stated bound each (oracle in fp64 on the fp32-rounded inputs, so the comparison isolates the
 # ---- arithmetic precision).  The reference's own fp32 "match" ladder is 1e-5 .. 1e-4 on well-conditioned linear models
 # ---- (test_utils.py:160-180); chaotic drifts amplify rounding by e^{lambda t}.
