@@ -420,10 +420,12 @@ __device__ __forceinline__ void stencil_init(const Ctx<T>& c, StencilRegs<T>& R)
 // unscented right-hand side factors chol of the SYMMETRISED covariance (jnp.linalg.cholesky) and returns a symmetric
 // derivative: the symmetric part evolves from sym(P) and the antisymmetric part is carried along unchanged.  UKFC does exactly
 // that: integrate S = sym(P), then add the old antisymmetric part back.
+// (The EKF's covariance is exactly symmetric after an update, but not between the gaps of a FORECAST -- no updates --, where the
+// rounding asymmetry of one gap would be amplified by the next: it integrates sym(P) as well; the reference's own
+// F P + P F^T keeps an exactly symmetric P exactly symmetric, so there is no antisymmetric part to carry.)
 template <typename T, bool UKFC>
 __device__ __forceinline__ T stencil_load_entry(const T* y, const StencilRegs<T>& R, int j, int ld) {
-  const T prc = y[R.o_row + j];
-  return UKFC ? T(0.5) * (prc + y[R.o_colT + j * ld]) : prc;
+  return T(0.5) * (y[R.o_row + j] + y[R.o_colT + j * ld]);
 }
 template <typename T, bool UKFC>
 __device__ __forceinline__ T stencil_antisym(const T* y, const StencilRegs<T>& R, int j, int ld) {

@@ -165,3 +165,33 @@ def test_emission_moments_vs_oracle():
     em2, ec2 = cd.cdnlgssm_emissions(p, np.zeros((K, 1)), sm[0])  # point estimates: the model's own (H m + d, R)
     rm2, rc2 = o.emission_moments(_oracle_params(g), sm[0])
     assert em2.shape == (K, m) and scaled_err(em2, rm2) < 1e-13 and scaled_err(ec2, rc2) < 1e-13
+
+
+@pytest.mark.parametrize("algo", ["ekf", "ukf"])
+def test_long_forecast_l96_n40_stays_symmetric(algo):
+    """150 gaps with no update on Lorenz-96 n = 40 (t = 3, ~5 Lyapunov times): the register-resident moment ODE reads P_{c,r} as
+    P_{r,c}, i.e. it integrates dP = J P + P J^T, whose antisymmetric part is as unstable as the symmetric one -- every gap
+    therefore starts from sym(P).  The forecast covariance must stay symmetric to rounding and follow the oracle's (EKF: gate
+    relaxed to 1e-7 -- the unobserved chaotic covariance grows by e^{2 lambda t} and so does the distance between two roundings)."""
+    from tests.test_gpu_baseline_shapes import _l96_case
+    cd = api()
+    N, K = 2, 150
+    g, po, t, y = _l96_case(N=N, K=K, seed=8)
+    g = dict(g, P0=0.01 * np.eye(40))
+    po = o.NonlinearParams(m0=g["m0"], P0=g["P0"], drift=o.Lorenz96Drift(8.0), L=g["L"], Qc=g["Qc"], H=g["H"], R=g["R"], d=g["d"])
+    tf = 0.3 + t + 0.02
+    st = {"solver": "rk4", "dt0": 0.005}
+    hp = cd.EKFHyperParams(diffeqsolve_settings=st) if algo == "ekf" else cd.UKFHyperParams(diffeqsolve_settings=st)
+    m0 = np.repeat(g["m0"][None], N, axis=0)
+    fc = cd.cdnlgssm_forecast(nonlinear_params_api(g), cd.MultivariateNormalFullCovariance(m0, g["P0"]), 0.3, tf[..., None], hp)
+    P = np.asarray(fc.forecasted_state_covariances)
+    assert np.isfinite(P).all()
+    asym = np.abs(P - np.swapaxes(P, -1, -2)).max(axis=(-1, -2)) / np.abs(P).max(axis=(-1, -2))
+    record(f"long_forecast_{algo}:asymmetry", asym.max())
+    assert asym.max() < 1e-12, asym.max()
+    if algo == "ekf":
+        T = np.concatenate([np.full((N, 1), 0.3), tf], axis=1)
+        r = o.extended_kalman_filter(po, np.zeros((N, K, 20)), T, settings=o.SolverSettings("rk4", 0.005), forecast=True)
+        e = scaled_err(P, r["predicted_covariances"])
+        record("long_forecast_ekf:covariances:scaled", e)
+        assert e < 1e-7, e
