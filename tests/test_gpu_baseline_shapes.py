@@ -607,3 +607,27 @@ def test_ll_allreduce_with_a_raw_nccl_communicator():
     torch.cuda.synchronize()
     assert s.item() == before == float(np.sum(np.arange(1000) * -0.37)) or abs(s.item() - before) == 0.0
     comm.destroy()
+
+
+@pytest.mark.parametrize("sigma_points", [False, True])
+def test_ukf_l63_k1000_long_run_vs_oracle(sigma_points, monkeypatch):
+    """A LONG unscented run (K = 1,000, config 3's data) through the shared-memory UKF kernels: the UKF never symmetrises its
+    covariance, so anything that amplified the rounding asymmetry of the update would show here (it did, on the Lorenz-96
+    register path, after ~240 steps: DESIGN 4.2)."""
+    cd = api()
+    monkeypatch.setenv("CDK_UKF_SIGMA_POINTS", "1" if sigma_points else "0")
+    N, K = 6, 1000
+    t, y = c3_problem(N, K, seed=12)
+    hp = cd.UKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    f = cd.cdnlgssm_filter(nonlinear_params_api(L63), y, t[..., None], hp)
+    po = o.NonlinearParams(m0=L63["m0"], P0=L63["P0"], drift=o.Lorenz63Drift(*L63["theta"]), L=L63["L"], Qc=L63["Qc"],
+                           H=L63["H"], R=L63["R"], d=L63["d"])
+    r = o.unscented_kalman_filter(po, y, t, settings=o.SolverSettings("rk4", 0.0025))
+    assert np.isfinite(r["marginal_loglik"]).all()
+    P = np.asarray(f.filtered_covariances)
+    assert np.abs(P - np.swapaxes(P, -1, -2)).max() < 1e-12 * np.abs(P).max()
+    e = max_rel_err(f.marginal_loglik, r["marginal_loglik"])
+    record(f"ukf_l63_k1000_{'sigma' if sigma_points else 'closed'}:marginal_loglik", e)
+    assert e < 1e-8
+    for fld in FIELDS:
+        assert scaled_err(getattr(f, fld), r[fld]) < 1e-6, fld
