@@ -631,3 +631,28 @@ def test_ukf_l63_k1000_long_run_vs_oracle(sigma_points, monkeypatch):
     assert e < 1e-8
     for fld in FIELDS:
         assert scaled_err(getattr(f, fld), r[fld]) < 1e-6, fld
+
+
+@pytest.mark.parametrize("algo,solver,dt0", [("ekf", "rk4", 0.005), ("ekf", "dopri5", 0.01), ("ukf", "dopri5", 0.01), ("ukf", "heun", 0.005)])
+def test_l96_n40_long_runs_vs_oracle(algo, solver, dt0):
+    """K = 300 observation steps on Lorenz-96 n = 40 through the register-resident ODE variants (chain tableau, Dopri5; EKF,
+    UKF): finite and symmetric to the end, the first 100 steps at the parity gate, the whole run at 1e-3 of the scale (two
+    roundings of a chaotic filter separate at the Lyapunov rate between corrections)."""
+    cd = api()
+    g, po, t, y = _l96_case(N=2, K=300, seed=31)
+    st = {"solver": solver, "dt0": dt0}
+    if algo == "ekf":
+        f = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], cd.EKFHyperParams(diffeqsolve_settings=st))
+        r = o.extended_kalman_filter(po, y, t, settings=o.SolverSettings(solver, dt0))
+    else:
+        f = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], cd.UKFHyperParams(diffeqsolve_settings=st))
+        r = o.unscented_kalman_filter(po, y, t, settings=o.SolverSettings(solver, dt0))
+    P = np.asarray(f.filtered_covariances)
+    assert np.isfinite(P).all() and np.isfinite(np.asarray(f.marginal_loglik)).all()
+    assert np.abs(P - np.swapaxes(P, -1, -2)).max() < 1e-12 * np.abs(P).max()
+    e100 = scaled_err(np.asarray(f.filtered_means)[:, :100], r["filtered_means"][:, :100])
+    eall = scaled_err(f.filtered_means, r["filtered_means"])
+    record(f"l96_long_{algo}_{solver}:filtered_means_first100", e100)
+    record(f"l96_long_{algo}_{solver}:filtered_means_all300", eall)
+    assert e100 < 1e-8 and eall < 1e-3, (e100, eall)
+    assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < 1e-6
