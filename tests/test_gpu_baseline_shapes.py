@@ -656,3 +656,34 @@ def test_l96_n40_long_runs_vs_oracle(algo, solver, dt0):
     record(f"l96_long_{algo}_{solver}:filtered_means_all300", eall)
     assert e100 < 1e-8 and eall < 1e-3, (e100, eall)
     assert max_rel_err(f.marginal_loglik, r["marginal_loglik"]) < 1e-6
+
+
+def test_c3_eks_k1000_long_run_vs_oracle():
+    """Config 3's smoother at full K: filter + EKS backward pass over 1,000 steps (register kernels) against the NumPy oracle."""
+    cd = api()
+    N, K = 5, 1000
+    t, y = c3_problem(N, K, seed=14)
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    s = cd.cdnlgssm_smoother(nonlinear_params_api(L63), y, t[..., None], hp)
+    po = o.NonlinearParams(m0=L63["m0"], P0=L63["P0"], drift=o.Lorenz63Drift(*L63["theta"]), L=L63["L"], Qc=L63["Qc"],
+                           H=L63["H"], R=L63["R"], d=L63["d"])
+    rs = o.extended_kalman_smoother(po, y, t, settings=o.SolverSettings("rk4", 0.0025))
+    assert np.isfinite(np.asarray(s.smoothed_covariances)).all()
+    assert max_rel_err(s.marginal_loglik, rs["marginal_loglik"]) < TOL
+    for fld in ("smoothed_means", "smoothed_covariances"):
+        e = scaled_err(getattr(s, fld), rs[fld])
+        record(f"c3_eks_k1000:{fld}", e)
+        assert e < 1e-8, (fld, e)
+
+
+def test_c5_enkf_heun_full_length_finite_and_causal_sample():
+    """EnKF with the reference's default SDE solver (Heun) over config 5's full K = 500 on a few trajectories: finite to the
+    end; the first 40 steps against the oracle on the shared stream."""
+    cd = api()
+    g, po, t, y = _l96_case(N=3, K=500, seed=53)
+    hp = cd.EnKFHyperParams(N_particles=1024, key=9, diffeqsolve_settings={"solver": "heun", "dt0": 0.005})
+    f = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], hp)
+    assert np.isfinite(np.asarray(f.filtered_covariances)).all() and np.isfinite(np.asarray(f.marginal_loglik)).all()
+    Ks = 40
+    r = o.ensemble_kalman_filter(po, y[:2, :Ks], t[:2, :Ks], E=1024, seed=9, settings=o.SolverSettings("heun", 0.005))
+    assert scaled_err(np.asarray(f.filtered_means)[:2, :Ks], r["filtered_means"]) < 1e-8
