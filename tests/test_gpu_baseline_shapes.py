@@ -687,3 +687,39 @@ def test_c5_enkf_heun_full_length_finite_and_causal_sample():
     Ks = 40
     r = o.ensemble_kalman_filter(po, y[:2, :Ks], t[:2, :Ks], E=1024, seed=9, settings=o.SolverSettings("heun", 0.005))
     assert scaled_err(np.asarray(f.filtered_means)[:2, :Ks], r["filtered_means"]) < 1e-8
+
+
+def test_eks_l96_n40_generic_smoother_vs_oracle():
+    """Filter (register ODE, compact layout) + EKS backward pass (generic_smooth_kernel) at n = 40, m = 20."""
+    cd = api()
+    g, po, t, y = _l96_case(N=2, K=30, seed=33)
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.005})
+    s = cd.cdnlgssm_smoother(nonlinear_params_api(g), y, t[..., None], hp)
+    rs = o.extended_kalman_smoother(po, y, t, settings=o.SolverSettings("rk4", 0.005))
+    assert max_rel_err(s.marginal_loglik, rs["marginal_loglik"]) < TOL
+    for fld in ("smoothed_means", "smoothed_covariances"):
+        e = scaled_err(getattr(s, fld), rs[fld])
+        record(f"eks_l96_n40:{fld}", e)
+        assert e < 1e-8, (fld, e)
+
+
+def test_kf_generic_n32_long_run_vs_oracle():
+    """The shared-memory linear kernel beyond the warp kernel's n <= 16: n = 32, m = 8, K = 300 against the C oracle, both
+    smoother types against the NumPy oracle on a shorter slice."""
+    from oracle import cpu_baseline as cb
+    cd = api()
+    N, K = 6, 300
+    g, po, t, y = _c2_case(N, K, seed=41, n=32, m=8)
+    hp = cd.KFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.01})
+    f = cd.cdlgssm_filter(linear_params_api(g), y, t[..., None], hp)
+    r = cb.filter_c("kf", y, t, g["m0"], g["P0"], g["F"], g["L"], g["Qc"], g["H"], g["d"], g["R"], bias=g["b"], solver="rk4", dt0=0.01)
+    e = max_rel_err(f.marginal_loglik, r["marginal_loglik"])
+    record("kf_generic_n32_k300:marginal_loglik", e)
+    assert e < TOL
+    check_moments(f, r, "kf_generic_n32_k300")
+    Ks = 40
+    for stype in ("cd_smoother_1", "cd_smoother_2"):
+        s = cd.cdlgssm_smoother(linear_params_api(g), y[:2, :Ks], t[:2, :Ks, None], hp, smoother_type=stype)
+        rs = o.cdlgssm_smoother(po, y[:2, :Ks], t[:2, :Ks], settings=o.SolverSettings("rk4", 0.01), smoother_type=int(stype[-1]))
+        for fld in ("smoothed_means", "smoothed_covariances"):
+            assert scaled_err(getattr(s, fld), rs[fld]) < 1e-8, (stype, fld)
