@@ -715,6 +715,30 @@ def test_ekf_loglik_gradient_reverse_mode_matches_forward_mode(solver, dt0, monk
         assert np.max(np.abs(ga[name] - gb[name])) < 1e-9 * np.max(np.abs(gb[name])), name
 
 
+def test_ekf_loglik_gradient_long_run_reverse_vs_forward(monkeypatch):
+    """The two independent derivative kernels over config 3's full K = 1,000 (the reverse pass walks 1,000 stored steps and
+    ~4,500 re-integrated substeps backwards): they must still agree to rounding relative to each gradient's scale, and the
+    reverse-mode log-likelihood must be the filter's."""
+    cd = api()
+    N, K = 40, 1000
+    t, y = c3_problem(N, K, seed=35)
+    g = dict(m0=np.zeros(3), P0=5 * np.eye(3), drift="lorenz63", theta=np.array([10.0, 28.0, 8.0 / 3.0]),
+             L=np.eye(3), Qc=np.eye(3), H=np.array([[1.0, 0.0, 0.0]]), R=np.eye(1), d=np.zeros(1))
+    hp = cd.EKFHyperParams(diffeqsolve_settings={"solver": "rk4", "dt0": 0.0025})
+    p = nonlinear_params_api(g)
+    monkeypatch.setenv("CDK_GRAD_MODE", "forward")
+    ll_f, gf = cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp, wrt=("drift", "emission_cov", "initial_mean"))
+    monkeypatch.setenv("CDK_GRAD_MODE", "reverse")
+    ll_r, gr = cd.ekf_marginal_log_prob_and_grad(p, y, t[..., None], hp, wrt=("drift", "emission_cov", "initial_mean"))
+    f = cd.cdnlgssm_filter(p, y, t[..., None], hp, output_fields=[])
+    assert max_rel_err(ll_r, np.asarray(f.marginal_loglik)) < 1e-12 and max_rel_err(ll_f, ll_r) < 1e-12
+    for name in sorted(gf):
+        scale = np.max(np.abs(gf[name]))
+        err = np.max(np.abs(gr[name] - gf[name])) / scale
+        record(f"grad_long_run_reverse_vs_forward:{name}", err)
+        assert np.isfinite(gr[name]).all() and err < 1e-8, (name, err)
+
+
 def test_torch_autograd_wrapper_around_the_reverse_mode_kernel():
     """cd_dynamax_b200.autograd.ekf_marginal_log_prob: the custom_vjp-shaped wrapper (forward = CUDA filter, backward = the
     reverse-mode kernel).  `(-ll.sum()).backward()` -- fit_sgd's loss -- must put the summed gradients on shared leaves."""
