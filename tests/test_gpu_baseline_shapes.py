@@ -219,14 +219,14 @@ def test_c2_kf_n16_k500_vs_oracle(solver, dt0):
             assert scaled_err(getattr(s, fld), rs[fld]) < 1e-8, (stype, fld)
 
 
-@pytest.mark.parametrize("E", [1024, 600])
-def test_c5_enkf_light_mapping_is_bit_identical(E, monkeypatch):
+@pytest.mark.parametrize("E,cluster", [(1024, 4), (600, 4), (1000, 8), (200, 1)])
+def test_c5_enkf_light_mapping_is_bit_identical(E, cluster, monkeypatch):
     """The two-threads-per-member mapping (ensemble swept in place in shared memory, 512 threads) against the
     one-thread-per-member register mapping: same counters, same operation order -> identical bits (ragged last CTA at E = 600)."""
     cd = api()
     g, po, t, y = _l96_case(N=2, K=12, seed=51)
     hp = cd.EnKFHyperParams(N_particles=E, key=77, diffeqsolve_settings={"solver": "euler", "dt0": 0.005})
-    monkeypatch.setenv("CDK_ENKF_CLUSTER", "4")
+    monkeypatch.setenv("CDK_ENKF_CLUSTER", str(cluster))  # members per CTA: 256, 150, 125 (ragged), 200
     monkeypatch.setenv("CDK_ENKF_LIGHT", "0")
     f0 = cd.cdnlgssm_filter(nonlinear_params_api(g), y, t[..., None], hp)
     monkeypatch.setenv("CDK_ENKF_LIGHT", "1")
